@@ -1,0 +1,231 @@
+/* C ABI of the B200 annealing engine (libmegalania_cuda.so).
+ *
+ * This is the boundary a Megalania host binds instead of its per-bit CPU plug-ins: plain
+ * pointers and sizes, opaque handles, no C++ or torch types.  Every call returns 0 on
+ * success or a negative MG_E* code; mg_last_error() gives the text for the calling thread.
+ * All buffers named "host" are caller-owned host memory; the library owns its device
+ * memory and streams.  One host thread per handle.  There is no CPU fallback: without a
+ * CUDA device every compute entry point fails with MG_ECUDA.
+ *
+ * Each entry point states the reference interface it replaces (paths are relative to the
+ * reference tree).
+ */
+#ifndef MEGALANIA_CUDA_H
+#define MEGALANIA_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#include "output_interface.h"
+
+#if defined(__GNUC__)
+#define MG_API __attribute__((visibility("default")))
+#else
+#define MG_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- types shared with the host ------------------------------------------------------ */
+
+/* One slab slot.  Same 12-byte layout and type codes as src/lzma_packet.h:5-17. */
+#ifndef MG_HAVE_LZMA_PACKET
+#define MG_HAVE_LZMA_PACKET
+#define INVALID 0
+#define LITERAL 1
+#define MATCH 2
+#define SHORT_REP 3
+#define LONG_REP 4
+typedef struct {
+	uint8_t type;
+	uint32_t dist; /* MATCH: distance-1; LONG_REP: rep index 0..3; else 0 */
+	uint16_t len;  /* 1 for LITERAL/SHORT_REP, 2..273 otherwise */
+} LZMAPacket;
+#endif
+
+/* src/lzma_state.h:58-62.  Only lc = lp = pb = 0 is supported, like the reference. */
+#ifndef MG_HAVE_LZMA_PROPERTIES
+#define MG_HAVE_LZMA_PROPERTIES
+typedef struct {
+	uint8_t lc;
+	uint8_t lp;
+	uint8_t pb;
+} LZMAProperties;
+#endif
+
+enum {
+	MG_OK = 0,
+	MG_EINVAL = -1,  /* bad argument (null pointer, size 0, unsupported lc/lp/pb, k out of range) */
+	MG_ECUDA = -2,   /* CUDA runtime failure, or no usable device */
+	MG_ENOMEM = -3,  /* host or device allocation failed */
+	MG_ESLAB = -4,   /* a slab holds an undecodable packet or a query is not on a packet boundary */
+	MG_EOUTPUT = -5, /* OutputInterface.write returned false */
+	MG_ESTATE = -6   /* call order violated (e.g. run before set_slab) */
+};
+
+typedef struct mg_ctx mg_ctx;       /* one input file resident on one GPU */
+typedef struct mg_anneal mg_anneal; /* a population of annealing chains over that file */
+
+MG_API const char* mg_last_error(void);
+/* Library/ABI version, (major << 16) | minor. */
+MG_API uint32_t mg_version(void);
+
+/* ---- context ------------------------------------------------------------------------- */
+
+/* Replaces lzma_state_init (src/lzma_state.c:16-27), packet_enumerator_new
+ * (src/packet_enumerator.c:20-27 -> substring_enumerator_new, src/substring_enumerator.c:49-78:
+ * the bigram index is built on the device) and top_k_packet_finder_new
+ * (src/top_k_packet_finder.c:38-58).  Copies data[0..n) to device `device`. */
+MG_API int mg_ctx_create(const uint8_t* data, size_t n, LZMAProperties props, int device, mg_ctx** out);
+MG_API void mg_ctx_destroy(mg_ctx* ctx);
+MG_API size_t mg_ctx_size(const mg_ctx* ctx);
+MG_API int mg_ctx_device(const mg_ctx* ctx);
+
+/* ---- parity function 2: cost(data, slab) ----------------------------------------------- */
+
+/* Replaces the perplexity back end driven over a whole slab: lzma_encode_packet
+ * (src/lzma_packet_encoder.c:169-194) + perplexity_encoder (src/perplexity_encoder.c:6-17),
+ * as looped in src/packet_slab_neighbour.c:22-32 and src/main.c:116-118.
+ * slabs: nslabs consecutive slabs of n packets each (host).  out_cost[i] is the cost of slab i
+ * in 1/2048-bit units, exactly the reference's uint64 total. */
+MG_API int mg_score_slabs(mg_ctx* ctx, const LZMAPacket* slabs, size_t nslabs, uint64_t* out_cost);
+
+/* ---- parity function 1: topk(data, state, position, excluded) --------------------------- */
+
+/* Replaces top_k_packet_finder_find / _count / _pop (src/top_k_packet_finder.c:120-138,67-70)
+ * over packet_enumerator_for_each (src/packet_enumerator.c:57-74) and
+ * substring_enumerator_for_each (src/substring_enumerator.c:85-105).
+ *   state_mode 0: freshly initialised model with position forced to positions[q]
+ *                 (the recipe of src/main.c:53-57);
+ *   state_mode 1: the model reached by pricing slab[0 .. positions[q]); positions[q] must be
+ *                 a live packet boundary of the slab (any order).
+ * The excluded candidate is slab[positions[q]] (src/top_k_packet_finder.c:99-101).
+ * Results per query q: out_counts[q] candidates (<= k) in the reference's pop order, worst
+ * first, at out_pops[q*k ..]; out_prices (optional, may be NULL) receives the integer
+ * cost/len of each pop.  1 <= k <= 32 (the reference uses 20, src/main.c:49). */
+MG_API int mg_find_topk(mg_ctx* ctx, const LZMAPacket* slab, int state_mode, const uint64_t* positions,
+                 size_t npos, int k, LZMAPacket* out_pops, uint32_t* out_prices, int32_t* out_counts);
+
+/* ---- parity function 3: bytes(data, slab) ---------------------------------------------- */
+
+/* Replaces the final pass of src/main.c:110-119: lzma_encode_header
+ * (src/lzma_header_encoder.c:5-21) + lzma_encode_packet over range_encoder
+ * (src/range_encoder.c:18-101).  The range coder runs on the device; the finished stream is
+ * handed to `out` (header fields first, then the payload). */
+MG_API int mg_encode_slab(mg_ctx* ctx, const LZMAPacket* slab, OutputInterface* out);
+/* Same, into a caller buffer; *out_len receives the stream length (may exceed cap: then
+ * nothing past cap was written and the call returns MG_EINVAL). */
+MG_API int mg_encode_slab_buffer(mg_ctx* ctx, const LZMAPacket* slab, uint8_t* out, size_t cap, size_t* out_len);
+
+/* ---- the annealing loop ---------------------------------------------------------------- */
+
+enum {
+	MG_SCHEDULE_REFERENCE = 0, /* src/main.c:86 rule, evaluated in 64-bit integers */
+	MG_SCHEDULE_TEMPERATURE = 1 /* Metropolis at a fixed per-chain temperature (tempering) */
+};
+
+typedef struct {
+	uint32_t chains;            /* independent annealing chains (one warp each) */
+	uint32_t top_k;             /* candidates kept per find; reference: 20 */
+	uint32_t checkpoint_stride; /* bytes between model checkpoints, >= 512; 0 = default */
+	uint32_t edit_log_capacity; /* per-chain accept/reject buffer entries; 0 = default */
+	uint32_t track_best;        /* keep a per-chain best slab (src/main.c:89-92) */
+	uint32_t trace_capacity;    /* per-chain proposal trace records per run (0 = none) */
+	uint64_t seed;              /* chain c draws from splitmix64 seeded by (seed, c) */
+} mg_anneal_params;
+
+typedef struct {
+	uint32_t evals;        /* successful proposals to run per chain in this call */
+	uint32_t max_attempts; /* bound on proposals drawn per chain, 0 = 64*evals + 1024 */
+	uint32_t schedule;     /* MG_SCHEDULE_* */
+	uint32_t step;         /* reference schedule: `step` of src/main.c:69 */
+	uint32_t num_iters;    /* reference schedule: `num_iters` of src/main.c:67 (0 = n) */
+	uint32_t first_eval;   /* reference schedule: value of i for the first proposal */
+	const float* temperatures; /* MG_SCHEDULE_TEMPERATURE: host array [chains], 1/2048-bit units */
+} mg_anneal_run_params;
+
+typedef struct {
+	uint64_t evals;        /* successful proposals (the headline unit), all chains */
+	uint64_t attempts;     /* proposals drawn, including failed ones */
+	uint64_t accepted;
+	uint64_t new_best;
+	uint64_t packets_scored;   /* packets priced, all chains */
+	uint64_t bits_scored;      /* modelled bits priced (algorithmic work of the scorer) */
+	uint64_t slab_bytes_read;  /* algorithmic HBM bytes: slab slots + data walked */
+	uint64_t checkpoint_bytes; /* checkpoint bytes loaded + stored */
+	uint64_t finder_calls;
+	uint64_t finder_candidates; /* candidates enumerated and priced */
+	uint64_t edits;            /* slab edits logged */
+	uint64_t log_overflows;    /* proposals abandoned because the edit log was full */
+	double kernel_ms;          /* device time of the launch(es), CUDA events */
+	uint32_t launches;         /* kernels launched by this call */
+} mg_anneal_stats;
+
+typedef struct {
+	uint64_t cost;       /* proposal cost, 0 when the proposal failed */
+	uint32_t flags;      /* bit0 success, bit1 accepted, bit2 new best */
+	uint32_t undo_count; /* edits logged (packet_slab_neighbour_undo_count) */
+} mg_trace_rec;
+
+/* Allocates the chains: slab, best slab, double-buffered checkpoints, edit log per chain.
+ * Replaces packet_slab_new (src/packet_slab.c:15-35) per chain and packet_slab_undo_stack
+ * (src/packet_slab_undo_stack.c). */
+MG_API int mg_anneal_create(mg_ctx* ctx, const mg_anneal_params* params, mg_anneal** out);
+MG_API void mg_anneal_destroy(mg_anneal* an);
+/* Device bytes one chain needs under `params` (for sizing the population). */
+MG_API size_t mg_anneal_chain_bytes(const mg_ctx* ctx, const mg_anneal_params* params);
+
+/* Sets the current slab of chains [first, first+count) to `slab` (host, n packets; NULL = all
+ * LITERAL as packet_slab_new does), rescoring and checkpointing them.  The chains' current
+ * cost becomes the slab cost when adopt_cost != 0, else 0 ("first proposal always accepted",
+ * src/main.c:74,87).  Best slabs/costs are reset only when reset_best != 0. */
+MG_API int mg_anneal_set_slab(mg_anneal* an, uint32_t first, uint32_t count, const LZMAPacket* slab,
+                       int adopt_cost, int reset_best);
+
+/* Runs `evals` successful proposals on every chain: packet_slab_neighbour_generate
+ * (src/packet_slab_neighbour.c:154-173) + the accept/undo/best logic of src/main.c:78-102.
+ * Blocks until the device is done; stats may be NULL. */
+MG_API int mg_anneal_run(mg_anneal* an, const mg_anneal_run_params* run, mg_anneal_stats* stats);
+
+/* Per-chain costs (host arrays [chains], either may be NULL). */
+MG_API int mg_anneal_costs(mg_anneal* an, uint64_t* cur_cost, uint64_t* best_cost);
+/* Copies a chain's current (which = 0) or best (which = 1) slab to host, n packets. */
+MG_API int mg_anneal_get_slab(mg_anneal* an, uint32_t chain, int which, LZMAPacket* out_slab);
+/* Proposal trace of the last run for one chain: up to cap records, *count receives how many
+ * proposals the chain drew. */
+MG_API int mg_anneal_get_trace(mg_anneal* an, uint32_t chain, mg_trace_rec* out, size_t cap, size_t* count);
+/* Replica exchange helpers: swap the slabs of two chains on this device / import a slab into a
+ * chain keeping its cost (used by the multi-GPU host after the NCCL exchange). */
+MG_API int mg_anneal_swap_chains(mg_anneal* an, uint32_t a, uint32_t b);
+/* Device pointer and byte size of a chain's current (0) or best (1) packed slab, for hosts
+ * that move slabs between GPUs with NCCL themselves.  The packed format is private; only
+ * copy it between mg_anneal objects created over identical data. */
+MG_API int mg_anneal_device_slab(mg_anneal* an, uint32_t chain, int which, void** dev_ptr, size_t* bytes);
+/* After writing a chain's packed current slab through the pointer above: rescore it. */
+MG_API int mg_anneal_refresh_chain(mg_anneal* an, uint32_t chain, int adopt_cost);
+
+/* One-shot convenience = create + set_slab(all literal or `init`) + run + pick the best chain.
+ * Replaces src/main.c:64-105 for a fixed evaluation budget.  best_slab_out: host, n packets. */
+MG_API int mg_anneal_oneshot(mg_ctx* ctx, const mg_anneal_params* params, const mg_anneal_run_params* run,
+                      const LZMAPacket* init, LZMAPacket* best_slab_out, uint64_t* best_cost,
+                      mg_anneal_stats* stats);
+
+/* ---- debugging aid (used by the parity tests) ------------------------------------------- */
+
+/* Model after pricing slab[0..stop): probabilities in the reference's struct order
+ * (src/lzma_state.h:47-55, 2615 entries; slots unreachable at lc=lp=pb=0 stay 1024). */
+typedef struct {
+	uint16_t probs[2615];
+	uint8_t ctx_state;
+	uint32_t dists[4];
+	uint64_t position;
+	uint64_t cost;
+} mg_model_dump;
+MG_API int mg_debug_model_after_prefix(mg_ctx* ctx, const LZMAPacket* slab, size_t stop, mg_model_dump* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

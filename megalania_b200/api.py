@@ -1,0 +1,333 @@
+"""ctypes binding of libmegalania_cuda.so — the Python mirror of the host interface.
+
+The names follow the reference's vocabulary (slab, packet, top-k finder, perplexity = cost):
+  Context(data)                 lzma_state_init + packet_enumerator_new + top_k_packet_finder_new
+  Context.score_slabs(slabs)    perplexity_encoder total of a slab          (src/perplexity_encoder.c)
+  Context.find_topk(...)        top_k_packet_finder_find + pop loop         (src/top_k_packet_finder.c)
+  Context.encode_slab(slab)     header + range_encoder pass                 (src/main.c:110-119)
+  Annealer(ctx, chains, ...)    the loop of src/main.c:78-102 on many chains
+
+There is no CPU path: importing works anywhere, but every compute call needs the CUDA library
+(built in-tree by megalania_b200.build) and a GPU, and raises MegalaniaError otherwise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+# LZMAPacket, reference src/lzma_packet.h:13-17
+PACKET_DTYPE = np.dtype({"names": ["type", "dist", "len"], "formats": ["u1", "<u4", "<u2"],
+                         "offsets": [0, 4, 8], "itemsize": 12})
+TRACE_DTYPE = np.dtype([("cost", "<u8"), ("flags", "<u4"), ("undo_count", "<u4")])
+MODEL_DTYPE = np.dtype({"names": ["probs", "ctx_state", "dists", "position", "cost"],
+                        "formats": [("<u2", 2615), "u1", ("<u4", 4), "<u8", "<u8"],
+                        "offsets": [0, 5230, 5232, 5248, 5256], "itemsize": 5264})
+INVALID, LITERAL, MATCH, SHORT_REP, LONG_REP = 0, 1, 2, 3, 4
+SCHEDULE_REFERENCE, SCHEDULE_TEMPERATURE = 0, 1
+
+ERRORS = {-1: "MG_EINVAL", -2: "MG_ECUDA", -3: "MG_ENOMEM", -4: "MG_ESLAB", -5: "MG_EOUTPUT", -6: "MG_ESTATE"}
+
+
+class MegalaniaError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"{ERRORS.get(code, code)}: {message}")
+        self.code = code
+
+
+class LZMAProperties(C.Structure):
+    _fields_ = [("lc", C.c_uint8), ("lp", C.c_uint8), ("pb", C.c_uint8)]
+
+
+class AnnealParams(C.Structure):
+    _fields_ = [("chains", C.c_uint32), ("top_k", C.c_uint32), ("checkpoint_stride", C.c_uint32),
+                ("edit_log_capacity", C.c_uint32), ("track_best", C.c_uint32), ("trace_capacity", C.c_uint32),
+                ("seed", C.c_uint64)]
+
+
+class AnnealRunParams(C.Structure):
+    _fields_ = [("evals", C.c_uint32), ("max_attempts", C.c_uint32), ("schedule", C.c_uint32),
+                ("step", C.c_uint32), ("num_iters", C.c_uint32), ("first_eval", C.c_uint32),
+                ("temperatures", C.POINTER(C.c_float))]
+
+
+class AnnealStats(C.Structure):
+    _fields_ = [(name, C.c_uint64) for name in (
+        "evals", "attempts", "accepted", "new_best", "packets_scored", "bits_scored", "slab_bytes_read",
+        "checkpoint_bytes", "finder_calls", "finder_candidates", "edits", "log_overflows")] + [
+        ("kernel_ms", C.c_double), ("launches", C.c_uint32)]
+
+    def as_dict(self) -> dict:
+        return {name: getattr(self, name) for name, _ in self._fields_}
+
+
+WRITE_FN = C.CFUNCTYPE(C.c_bool, C.c_void_p, C.c_void_p, C.c_size_t)
+
+
+class OutputInterface(C.Structure):
+    """reference src/output_interface.h:8-13"""
+    _fields_ = [("write", WRITE_FN), ("private_data", C.c_void_p)]
+
+
+EXPORTS = [
+    "mg_last_error", "mg_version", "mg_ctx_create", "mg_ctx_destroy", "mg_ctx_size", "mg_ctx_device",
+    "mg_score_slabs", "mg_find_topk", "mg_encode_slab", "mg_encode_slab_buffer", "mg_anneal_create",
+    "mg_anneal_destroy", "mg_anneal_chain_bytes", "mg_anneal_set_slab", "mg_anneal_run", "mg_anneal_costs",
+    "mg_anneal_get_slab", "mg_anneal_get_trace", "mg_anneal_swap_chains", "mg_anneal_device_slab",
+    "mg_anneal_refresh_chain", "mg_anneal_oneshot", "mg_debug_model_after_prefix",
+]
+
+_lib = None
+
+
+def library_path() -> str:
+    return _build.LIB
+
+
+def load_library(build_if_missing: bool = True) -> C.CDLL:
+    """Loads the CUDA library; raises if it is absent (there is nothing to fall back to)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = library_path()
+    if not os.path.exists(path):
+        if not build_if_missing:
+            raise MegalaniaError(-2, f"{path} is missing: run `python -m megalania_b200.build`")
+        _build.build_library()
+    L = C.CDLL(path)
+    vp, sz, u32, u64, i32 = C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint64, C.c_int
+    L.mg_last_error.restype = C.c_char_p
+    L.mg_version.restype = u32
+    L.mg_ctx_create.argtypes = [vp, sz, LZMAProperties, i32, C.POINTER(vp)]
+    L.mg_ctx_destroy.argtypes = [vp]
+    L.mg_ctx_destroy.restype = None
+    L.mg_ctx_size.argtypes = [vp]
+    L.mg_ctx_size.restype = sz
+    L.mg_ctx_device.argtypes = [vp]
+    L.mg_score_slabs.argtypes = [vp, vp, sz, vp]
+    L.mg_find_topk.argtypes = [vp, vp, i32, vp, sz, i32, vp, vp, vp]
+    L.mg_encode_slab.argtypes = [vp, vp, C.POINTER(OutputInterface)]
+    L.mg_encode_slab_buffer.argtypes = [vp, vp, vp, sz, C.POINTER(sz)]
+    L.mg_anneal_create.argtypes = [vp, C.POINTER(AnnealParams), C.POINTER(vp)]
+    L.mg_anneal_destroy.argtypes = [vp]
+    L.mg_anneal_destroy.restype = None
+    L.mg_anneal_chain_bytes.argtypes = [vp, C.POINTER(AnnealParams)]
+    L.mg_anneal_chain_bytes.restype = sz
+    L.mg_anneal_set_slab.argtypes = [vp, u32, u32, vp, i32, i32]
+    L.mg_anneal_run.argtypes = [vp, C.POINTER(AnnealRunParams), C.POINTER(AnnealStats)]
+    L.mg_anneal_costs.argtypes = [vp, vp, vp]
+    L.mg_anneal_get_slab.argtypes = [vp, u32, i32, vp]
+    L.mg_anneal_get_trace.argtypes = [vp, u32, vp, sz, C.POINTER(sz)]
+    L.mg_anneal_swap_chains.argtypes = [vp, u32, u32]
+    L.mg_anneal_device_slab.argtypes = [vp, u32, i32, C.POINTER(vp), C.POINTER(sz)]
+    L.mg_anneal_refresh_chain.argtypes = [vp, u32, i32]
+    L.mg_anneal_oneshot.argtypes = [vp, C.POINTER(AnnealParams), C.POINTER(AnnealRunParams), vp, vp,
+                                    C.POINTER(u64), C.POINTER(AnnealStats)]
+    L.mg_debug_model_after_prefix.argtypes = [vp, vp, sz, vp]
+    _lib = L
+    return L
+
+
+def _check(rc: int) -> None:
+    if rc != 0:
+        raise MegalaniaError(rc, load_library().mg_last_error().decode(errors="replace"))
+
+
+def literal_slab(n: int) -> np.ndarray:
+    """packet_slab_new: every slot a LITERAL (src/packet_slab.c:30-32)."""
+    slab = np.zeros(n, dtype=PACKET_DTYPE)
+    slab["type"] = LITERAL
+    slab["len"] = 1
+    return slab
+
+
+def as_slab(slab: np.ndarray) -> np.ndarray:
+    """A contiguous array in the exact 12-byte LZMAPacket layout (numpy may repack struct dtypes)."""
+    if slab.dtype == PACKET_DTYPE and slab.flags["C_CONTIGUOUS"]:
+        return slab
+    out = np.zeros(slab.shape, dtype=PACKET_DTYPE)
+    for name in ("type", "dist", "len"):
+        out[name] = slab[name]
+    return out
+
+
+def _slab_ptr(slab: np.ndarray, n: int, count: int = 1):
+    if slab.dtype != PACKET_DTYPE or not slab.flags["C_CONTIGUOUS"] or slab.size != n * count:
+        raise ValueError(f"slab must be a contiguous PACKET_DTYPE array of {n * count} packets")
+    return slab.ctypes.data_as(C.c_void_p)
+
+
+class Context:
+    """One input resident on one GPU, with its bigram index and price tables."""
+
+    def __init__(self, data: bytes, device: int = 0):
+        self._lib = load_library()
+        self._data = np.ascontiguousarray(np.frombuffer(bytes(data), dtype=np.uint8))
+        self.n = int(self._data.size)
+        self._h = C.c_void_p()
+        _check(self._lib.mg_ctx_create(self._data.ctypes.data_as(C.c_void_p), self.n, LZMAProperties(0, 0, 0),
+                                       device, C.byref(self._h)))
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self._lib.mg_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def score_slabs(self, slabs: np.ndarray) -> np.ndarray:
+        slabs = as_slab(np.asarray(slabs))
+        count = slabs.size // self.n
+        out = np.zeros(count, dtype=np.uint64)
+        _check(self._lib.mg_score_slabs(self._h, _slab_ptr(slabs.reshape(-1), self.n, count), count,
+                                        out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def score_slab(self, slab: np.ndarray) -> int:
+        return int(self.score_slabs(slab)[0])
+
+    def find_topk(self, slab: np.ndarray, positions, state_mode: int = 0, k: int = 20):
+        pos = np.ascontiguousarray(positions, dtype=np.uint64)
+        slab = as_slab(slab)
+        pops = np.zeros((pos.size, k), dtype=PACKET_DTYPE)
+        prices = np.zeros((pos.size, k), dtype=np.uint32)
+        counts = np.zeros(pos.size, dtype=np.int32)
+        _check(self._lib.mg_find_topk(self._h, _slab_ptr(slab, self.n), state_mode, pos.ctypes.data_as(C.c_void_p),
+                                      pos.size, k, pops.ctypes.data_as(C.c_void_p),
+                                      prices.ctypes.data_as(C.c_void_p), counts.ctypes.data_as(C.c_void_p)))
+        return pops, prices, counts
+
+    def encode_slab(self, slab: np.ndarray) -> bytes:
+        """Through the OutputInterface plug-in, exactly as a C host would receive it."""
+        chunks: list[bytes] = []
+
+        def _write(_iface, ptr, size):
+            chunks.append(C.string_at(ptr, size))
+            return True
+
+        iface = OutputInterface(WRITE_FN(_write), None)
+        _check(self._lib.mg_encode_slab(self._h, _slab_ptr(slab, self.n), C.byref(iface)))
+        return b"".join(chunks)
+
+    def encode_slab_buffer(self, slab: np.ndarray) -> bytes:
+        cap = self.n * 2 + 8192
+        out = np.zeros(cap, dtype=np.uint8)
+        got = C.c_size_t(0)
+        _check(self._lib.mg_encode_slab_buffer(self._h, _slab_ptr(slab, self.n), out.ctypes.data_as(C.c_void_p), cap,
+                                               C.byref(got)))
+        return out[:got.value].tobytes()
+
+    def model_after_prefix(self, slab: np.ndarray, stop: int):
+        out = np.zeros(1, dtype=MODEL_DTYPE)
+        _check(self._lib.mg_debug_model_after_prefix(self._h, _slab_ptr(slab, self.n), stop,
+                                                     out.ctypes.data_as(C.c_void_p)))
+        return out[0]
+
+    def chain_bytes(self, **params) -> int:
+        p = AnnealParams(**params)
+        return int(self._lib.mg_anneal_chain_bytes(self._h, C.byref(p)))
+
+
+class Annealer:
+    """A population of annealing chains (one warp each) over one Context."""
+
+    def __init__(self, ctx: Context, chains: int, *, top_k: int = 20, checkpoint_stride: int = 0,
+                 edit_log_capacity: int = 0, track_best: bool = True, trace_capacity: int = 0, seed: int = 1673551):
+        self.ctx = ctx
+        self._lib = ctx._lib
+        self.chains = chains
+        self.params = AnnealParams(chains, top_k, checkpoint_stride, edit_log_capacity, int(track_best),
+                                   trace_capacity, seed)
+        self._h = C.c_void_p()
+        _check(self._lib.mg_anneal_create(ctx._h, C.byref(self.params), C.byref(self._h)))
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self._lib.mg_anneal_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_slab(self, slab: np.ndarray | None = None, first: int = 0, count: int | None = None,
+                 adopt_cost: bool | None = None, reset_best: bool = True) -> None:
+        if count is None:
+            count = self.chains - first
+        if adopt_cost is None:
+            adopt_cost = slab is not None
+        ptr = _slab_ptr(slab, self.ctx.n) if slab is not None else None
+        _check(self._lib.mg_anneal_set_slab(self._h, first, count, ptr, int(adopt_cost), int(reset_best)))
+
+    def run(self, evals: int, *, schedule: int = SCHEDULE_REFERENCE, step: int = 0, num_iters: int = 0,
+            first_eval: int = 0, max_attempts: int = 0, temperatures=None) -> dict:
+        temps = None
+        tptr = None
+        if temperatures is not None:
+            temps = np.ascontiguousarray(temperatures, dtype=np.float32)
+            if temps.size != self.chains:
+                raise ValueError("one temperature per chain")
+            tptr = temps.ctypes.data_as(C.POINTER(C.c_float))
+        rp = AnnealRunParams(evals, max_attempts, schedule, step, num_iters, first_eval, tptr)
+        st = AnnealStats()
+        _check(self._lib.mg_anneal_run(self._h, C.byref(rp), C.byref(st)))
+        return st.as_dict()
+
+    def costs(self):
+        cur = np.zeros(self.chains, dtype=np.uint64)
+        best = np.zeros(self.chains, dtype=np.uint64)
+        _check(self._lib.mg_anneal_costs(self._h, cur.ctypes.data_as(C.c_void_p), best.ctypes.data_as(C.c_void_p)))
+        return cur, best
+
+    def get_slab(self, chain: int, best: bool = False) -> np.ndarray:
+        out = np.zeros(self.ctx.n, dtype=PACKET_DTYPE)
+        _check(self._lib.mg_anneal_get_slab(self._h, chain, int(best), out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def trace(self, chain: int) -> np.ndarray:
+        cap = self.params.trace_capacity
+        out = np.zeros(cap, dtype=TRACE_DTYPE)
+        count = C.c_size_t(0)
+        _check(self._lib.mg_anneal_get_trace(self._h, chain, out.ctypes.data_as(C.c_void_p), cap, C.byref(count)))
+        return out[:min(cap, count.value)]
+
+    def swap_chains(self, a: int, b: int) -> None:
+        _check(self._lib.mg_anneal_swap_chains(self._h, a, b))
+
+    def device_slab(self, chain: int, best: bool = False):
+        ptr, size = C.c_void_p(), C.c_size_t()
+        _check(self._lib.mg_anneal_device_slab(self._h, chain, int(best), C.byref(ptr), C.byref(size)))
+        return ptr.value, size.value
+
+    def refresh_chain(self, chain: int, adopt_cost: bool = True) -> None:
+        _check(self._lib.mg_anneal_refresh_chain(self._h, chain, int(adopt_cost)))
+
+
+def anneal_oneshot(ctx: Context, *, chains: int, evals: int, init: np.ndarray | None = None, seed: int = 1673551,
+                   top_k: int = 20, schedule: int = SCHEDULE_REFERENCE, step: int = 0, num_iters: int = 0):
+    """Host buffers in, host buffers out: the call the end-to-end benchmark times."""
+    lib = ctx._lib
+    p = AnnealParams(chains, top_k, 0, 0, 1, 0, seed)
+    rp = AnnealRunParams(evals, 0, schedule, step, num_iters, 0, None)
+    st = AnnealStats()
+    best = np.zeros(ctx.n, dtype=PACKET_DTYPE)
+    cost = C.c_uint64(0)
+    iptr = _slab_ptr(init, ctx.n) if init is not None else None
+    _check(lib.mg_anneal_oneshot(ctx._h, C.byref(p), C.byref(rp), iptr, best.ctypes.data_as(C.c_void_p),
+                                 C.byref(cost), C.byref(st)))
+    return best, int(cost.value), st.as_dict()

@@ -1,0 +1,443 @@
+// Device-side LZMA cost model for the annealing hot path (sm_100a).
+//
+// One warp owns one model.  A packet is priced in ONE step: every probability slot a packet
+// touches belongs to a fixed lane ("slot class"), so the 9 modelled bits of a literal or the
+// up-to-23 of a match are read, priced and adapted by different lanes at once.  This is exact
+// because a packet never touches the same slot twice (reference
+// src/lzma_packet_encoder.c:21-38,48-61,80-103,123-135) and a slot is only ever touched from
+// its own lane, so the per-slot adaptation order is the reference's.
+//
+// The model lives in shared memory as a `Record` whose bytes are also the checkpoint format
+// in HBM, so checkpoints move with single TMA bulk copies (cp.async.bulk, UBLKCP in SASS).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace mg {
+
+constexpr uint32_t FULL = 0xffffffffu;
+
+// Packet types, reference src/lzma_packet.h:5-9
+constexpr uint32_t T_INVALID = 0, T_LITERAL = 1, T_MATCH = 2, T_SHORT_REP = 3, T_LONG_REP = 4;
+
+// ---- slot map at lc = lp = pb = 0 (only the reachable slots of src/lzma_state.h:15-55) ----
+constexpr uint32_t LEN_LOW = 2, LEN_MID = 10, LEN_HIGH = 18, LEN_SLOTS = 274;
+constexpr uint32_t S_LIT = 0;                       // [0x300]
+constexpr uint32_t S_LEN = 768;                     // choice1, choice2, low[8], mid[8], high[256]
+constexpr uint32_t S_REPLEN = S_LEN + LEN_SLOTS;    // 1042
+constexpr uint32_t S_POSSLOT = S_REPLEN + LEN_SLOTS;  // 1316, [4][64]
+constexpr uint32_t S_ALIGN = S_POSSLOT + 256;       // 1572, [16]
+constexpr uint32_t S_POSCODER = S_ALIGN + 16;       // 1588, [115]
+constexpr uint32_t S_ISMATCH = S_POSCODER + 115;    // 1703, [12]
+constexpr uint32_t S_ISREP = S_ISMATCH + 12;        // 1715
+constexpr uint32_t S_ISREPG0 = S_ISREP + 12;        // 1727
+constexpr uint32_t S_ISREPG1 = S_ISREPG0 + 12;      // 1739
+constexpr uint32_t S_ISREPG2 = S_ISREPG1 + 12;      // 1751
+constexpr uint32_t S_ISREP0LONG = S_ISREPG2 + 12;   // 1763
+constexpr uint32_t S_TOTAL = S_ISREP0LONG + 12;     // 1775
+constexpr uint32_t S_CTX = S_TOTAL;                 // spare slot 1775 holds ctx_state in a checkpoint
+
+// Working set of one warp == checkpoint record in HBM.  3584 bytes = 224 x 16.
+struct alignas(16) Record {
+	uint16_t probs[S_TOTAL + 1];  // 3552 B
+	uint32_t rep[4];
+	uint32_t pos;   // byte position of the next packet
+	uint32_t pidx;  // index of that packet in the live chain
+	uint64_t cost;  // cost of everything before pos, 1/2048 bit
+};
+static_assert(sizeof(Record) == 3584, "record must stay a multiple of 16 bytes for cp.async.bulk");
+
+// Packed slab slot: dist[31:0] | len[47:32] | type[55:48]
+__host__ __device__ __forceinline__ uint64_t pk_pack(uint32_t type, uint32_t dist, uint32_t len)
+{
+	return (uint64_t)dist | ((uint64_t)len << 32) | ((uint64_t)type << 48);
+}
+__host__ __device__ __forceinline__ uint32_t pk_type(uint64_t p) { return (uint32_t)(p >> 48) & 0xff; }
+__host__ __device__ __forceinline__ uint32_t pk_len(uint64_t p) { return (uint32_t)(p >> 32) & 0xffff; }
+__host__ __device__ __forceinline__ uint32_t pk_dist(uint64_t p) { return (uint32_t)p; }
+constexpr uint64_t PK_LITERAL = (1ull << 48) | (1ull << 32);
+constexpr uint64_t PK_SHORT_REP = (3ull << 48) | (1ull << 32);
+
+// Registers every lane of the warp holds identically.
+struct Model {
+	uint32_t pos, pidx, ctx;
+	uint32_t rep0, rep1, rep2, rep3;
+};
+
+// ---- small PTX helpers --------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p)
+{
+	return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+	             : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity)
+{
+	uint32_t done;
+	asm volatile(
+	    "{\n\t.reg .pred p;\n\t"
+	    "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+	    "selp.b32 %0, 1, 0, p;\n\t}"
+	    : "=r"(done)
+	    : "r"(smem_u32(bar)), "r"(parity)
+	    : "memory");
+	return done != 0;
+}
+// global -> shared bulk copy (TMA), completion on an mbarrier
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar)
+{
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+	                 smem_u32(smem_dst)),
+	             "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+	             : "memory");
+}
+// shared -> global bulk copy (TMA), bulk-group completion
+__device__ __forceinline__ void bulk_s2g(void* gmem_dst, const void* smem_src, uint32_t bytes)
+{
+	asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst),
+	             "r"(smem_u32(smem_src)), "r"(bytes)
+	             : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ---- the 12-state automaton, src/lzma_state.c:29-57 ----------------------------------------
+__device__ __forceinline__ uint32_t next_ctx(uint32_t ctx, uint32_t type)
+{
+	if (type == T_LITERAL) return ctx < 4 ? 0 : (ctx < 10 ? ctx - 3 : ctx - 6);
+	if (type == T_MATCH) return ctx < 7 ? 7 : 10;
+	if (type == T_SHORT_REP) return ctx < 7 ? 9 : 11;
+	return ctx < 7 ? 8 : 11;
+}
+
+// One modelled bit: price it (src/perplexity_encoder.c:6-10) and adapt the slot
+// (src/probability_model.c:5-15).
+__device__ __forceinline__ void code_bit(uint16_t* probs, const uint16_t* price, uint32_t slot, uint32_t bit,
+                                         uint32_t& acc)
+{
+	uint32_t p = probs[slot];
+	acc += price[bit ? 2048u - p : p];
+	p = bit ? p - (p >> 5) : p + ((2048u - p) >> 5);
+	probs[slot] = (uint16_t)p;
+}
+
+__device__ __forceinline__ uint32_t bit_price(const uint16_t* probs, const uint16_t* price, uint32_t slot,
+                                              uint32_t bit)
+{
+	uint32_t p = probs[slot];
+	return price[bit ? 2048u - p : p];
+}
+
+// ---- lane -> (slot, bit) maps ----------------------------------------------------------------
+// Length coder (src/lzma_packet_encoder.c:42-63): rel 0 choice_1, rel 1 choice_2, rel 2..9 tree.
+__device__ __forceinline__ bool len_event(int rel, uint32_t base, uint32_t len, uint32_t& slot, uint32_t& bit)
+{
+	uint32_t v = len - 2;
+	if (rel == 0) {
+		slot = base;
+		bit = v >= 8;
+		return true;
+	}
+	if (rel == 1) {
+		slot = base + 1;
+		bit = v >= 16;
+		return v >= 8;
+	}
+	if (rel < 2 || rel > 9) return false;
+	uint32_t t = (uint32_t)rel - 2;
+	if (v < 16) {
+		if (t >= 3) return false;
+		uint32_t w = v & 7;
+		slot = base + (v < 8 ? LEN_LOW : LEN_MID) + ((1u << t) | (w >> (3 - t)));
+		bit = (w >> (2 - t)) & 1;
+		return true;
+	}
+	uint32_t w = v - 16;
+	slot = base + LEN_HIGH + ((1u << t) | (w >> (8 - t)));
+	bit = (w >> (7 - t)) & 1;
+	return true;
+}
+
+struct DistParts {
+	uint32_t pslot, nlow, low, rbase, rbits;  // rbits: bits coded by the reverse tree (0 when dist < 4)
+	uint32_t direct;                          // number of direct bits
+};
+
+// src/lzma_packet_encoder.c:71-104
+__device__ __forceinline__ DistParts dist_parts(uint32_t dist)
+{
+	DistParts d;
+	if (dist < 4) {
+		d.pslot = dist;
+		d.nlow = d.low = d.rbase = d.rbits = d.direct = 0;
+		return d;
+	}
+	d.nlow = 30u - (uint32_t)__clz(dist);
+	d.low = dist & ((1u << d.nlow) - 1);
+	uint32_t high = dist >> d.nlow;
+	d.pslot = d.nlow * 2 + high;
+	if (d.pslot < 14) {
+		d.rbase = S_POSCODER + (high << d.nlow) - d.pslot;
+		d.rbits = d.nlow;
+		d.direct = 0;
+	} else {
+		d.rbase = S_ALIGN;
+		d.rbits = 4;
+		d.direct = d.nlow - 4;
+		d.low &= 15;  // the part the align tree codes; the direct bits carry no cost state
+	}
+	return d;
+}
+
+// Distance coder: rel 0..5 pos-slot tree, rel 6..10 reverse tree (pos_coder or align).
+__device__ __forceinline__ bool dist_event(int rel, const DistParts& d, uint32_t lctx, uint32_t& slot, uint32_t& bit)
+{
+	if (rel < 0 || rel > 10) return false;
+	if (rel < 6) {
+		uint32_t t = (uint32_t)rel;
+		slot = S_POSSLOT + lctx * 64 + ((1u << t) | (d.pslot >> (6 - t)));
+		bit = (d.pslot >> (5 - t)) & 1;
+		return true;
+	}
+	uint32_t i = (uint32_t)rel - 6;
+	if (i >= d.rbits) return false;
+	uint32_t prefix = i ? (__brev(d.low & ((1u << i) - 1)) >> (32 - i)) : 0;
+	slot = d.rbase + ((1u << i) | prefix);
+	bit = (d.low >> i) & 1;
+	return true;
+}
+
+// Literal tree (src/lzma_packet_encoder.c:106-136): depth 0..7 on lanes 1..8.
+__device__ __forceinline__ void lit_event(uint32_t depth, uint32_t byte, bool matched_mode, uint32_t mbyte,
+                                          uint32_t& slot, uint32_t& bit)
+{
+	uint32_t top = byte >> (8 - depth);
+	uint32_t node = (1u << depth) | top;
+	bit = (byte >> (7 - depth)) & 1;
+	if (matched_mode && (mbyte >> (8 - depth)) == top) node += (1u + ((mbyte >> (7 - depth)) & 1)) << 8;
+	slot = S_LIT + node;
+}
+
+// Lane's event for a whole packet.  Lane order == the reference's coding order, which the
+// range-coder kernel relies on (direct bits sit between lanes 17 and 18 of a MATCH).
+//   LITERAL   : 0 is_match | 1..8 literal tree
+//   MATCH     : 0 is_match | 1 is_rep | 2..11 length | 12..17 pos slot | 18..22 reverse/align
+//   SHORT_REP : 0 is_match | 1 is_rep | 2 is_rep_g0 | 3 is_rep0_long
+//   LONG_REP  : 0 is_match | 1 is_rep | 2 g0 | 3 rep0_long or g1 | 4 g2 | 5..14 length
+__device__ __forceinline__ bool packet_event(int lane, uint32_t type, uint32_t len, uint32_t dist, uint32_t ctx,
+                                             uint32_t byte, uint32_t mbyte, const DistParts& dp, uint32_t& slot,
+                                             uint32_t& bit)
+{
+	if (lane == 0) {
+		slot = S_ISMATCH + ctx;
+		bit = type != T_LITERAL;
+		return true;
+	}
+	if (type == T_LITERAL) {
+		if (lane > 8) return false;
+		lit_event((uint32_t)lane - 1, byte, ctx >= 7, mbyte, slot, bit);
+		return true;
+	}
+	if (lane == 1) {
+		slot = S_ISREP + ctx;
+		bit = type != T_MATCH;
+		return true;
+	}
+	if (type == T_MATCH) {
+		if (lane < 12) return len_event(lane - 2, S_LEN, len, slot, bit);
+		uint32_t lctx = len - 2 < 3 ? len - 2 : 3;
+		return dist_event(lane - 12, dp, lctx, slot, bit);
+	}
+	if (type == T_SHORT_REP) {
+		if (lane == 2) {
+			slot = S_ISREPG0 + ctx;
+			bit = 0;
+			return true;
+		}
+		if (lane == 3) {
+			slot = S_ISREP0LONG + ctx;
+			bit = 0;
+			return true;
+		}
+		return false;
+	}
+	// LONG_REP, dist = rep index
+	if (lane == 2) {
+		slot = S_ISREPG0 + ctx;
+		bit = dist != 0;
+		return true;
+	}
+	if (lane == 3) {
+		if (dist == 0) {
+			slot = S_ISREP0LONG + ctx;
+			bit = 1;
+		} else {
+			slot = S_ISREPG1 + ctx;
+			bit = dist != 1;
+		}
+		return true;
+	}
+	if (lane == 4) {
+		slot = S_ISREPG2 + ctx;
+		bit = dist != 2;
+		return dist >= 2;
+	}
+	return len_event(lane - 5, S_REPLEN, len, slot, bit);
+}
+
+// src/lzma_state.c:59-81 + src/lzma_packet_encoder.c:192-193
+__device__ __forceinline__ void model_advance(Model& m, uint32_t type, uint32_t len, uint32_t dist)
+{
+	if (type == T_MATCH) {
+		m.rep3 = m.rep2;
+		m.rep2 = m.rep1;
+		m.rep1 = m.rep0;
+		m.rep0 = dist;
+	} else if (type == T_LONG_REP) {
+		uint32_t d = dist == 0 ? m.rep0 : dist == 1 ? m.rep1 : dist == 2 ? m.rep2 : m.rep3;
+		if (dist > 2) m.rep3 = m.rep2;
+		if (dist > 1) m.rep2 = m.rep1;
+		if (dist > 0) m.rep1 = m.rep0;
+		m.rep0 = d;
+	}
+	m.ctx = next_ctx(m.ctx, type);
+	m.pos += len;
+	m.pidx += 1;
+}
+
+__device__ __forceinline__ uint32_t model_rep(const Model& m, uint32_t idx)
+{
+	return idx == 0 ? m.rep0 : idx == 1 ? m.rep1 : idx == 2 ? m.rep2 : m.rep3;
+}
+
+// Price + adapt one packet across the warp.  `byte` = data[pos]; mbyte only read when the packet
+// is a literal in matched mode.  Returns the number of modelled bits (uniform).
+__device__ __forceinline__ uint32_t apply_packet(int lane, uint16_t* probs, const uint16_t* price, Model& m,
+                                                 uint32_t type, uint32_t len, uint32_t dist, uint32_t byte,
+                                                 uint32_t mbyte, uint32_t& acc)
+{
+	DistParts dp;
+	dp.pslot = dp.nlow = dp.low = dp.rbase = dp.rbits = dp.direct = 0;
+	if (type == T_MATCH) dp = dist_parts(dist);
+	uint32_t slot = 0, bit = 0;
+	bool active = packet_event(lane, type, len, dist, m.ctx, byte, mbyte, dp, slot, bit);
+	if (active) code_bit(probs, price, slot, bit, acc);
+	if (lane == 0) acc += dp.direct << 11;  // src/perplexity_encoder.c:12-17
+	model_advance(m, type, len, dist);
+	return __popc(__ballot_sync(FULL, active));
+}
+
+__device__ __forceinline__ void model_init(int lane, uint16_t* probs, Model& m)
+{
+	for (uint32_t i = (uint32_t)lane; i <= S_TOTAL; i += 32) probs[i] = 1024;
+	m.pos = m.pidx = m.ctx = 0;
+	m.rep0 = m.rep1 = m.rep2 = m.rep3 = 0;
+	__syncwarp();
+}
+
+// Window of 32 consecutive slab slots + data bytes held across the warp's registers, with the
+// next window prefetched, so the live-chain walk costs shuffles instead of dependent loads.
+struct Window {
+	uint64_t pk, pk_next;
+	uint32_t byte, byte_next;
+	uint32_t base;  // multiple of 32; 0xffffffff = empty
+};
+
+__device__ __forceinline__ void window_load(int lane, const uint64_t* __restrict__ slab,
+                                            const uint8_t* __restrict__ data, uint32_t n, uint32_t base,
+                                            uint64_t& pk, uint32_t& byte)
+{
+	uint32_t i = base + (uint32_t)lane;
+	bool in = i < n && base < n;
+	pk = in ? slab[i] : 0;
+	byte = in ? data[i] : 0;
+}
+
+__device__ __forceinline__ void window_seek(int lane, Window& w, const uint64_t* __restrict__ slab,
+                                            const uint8_t* __restrict__ data, uint32_t n, uint32_t pos)
+{
+	uint32_t want = pos & ~31u;
+	if (want == w.base) return;
+	if (w.base != 0xffffffffu && want == w.base + 32) {
+		w.pk = w.pk_next;
+		w.byte = w.byte_next;
+	} else {
+		window_load(lane, slab, data, n, want, w.pk, w.byte);
+	}
+	w.base = want;
+	window_load(lane, slab, data, n, want + 32, w.pk_next, w.byte_next);
+}
+
+__device__ __forceinline__ uint64_t window_packet(const Window& w, uint32_t pos)
+{
+	return __shfl_sync(FULL, w.pk, (int)(pos - w.base));
+}
+__device__ __forceinline__ uint32_t window_byte(const Window& w, uint32_t pos)
+{
+	return __shfl_sync(FULL, w.byte, (int)(pos - w.base));
+}
+
+// Checkpoint traffic: one TMA bulk copy each way, issued by lane 0.
+__device__ __forceinline__ void record_store(int lane, Record* rec, const Model& m, uint64_t cost, Record* dst)
+{
+	__syncwarp();
+	if (lane == 0) {
+		rec->probs[S_CTX] = (uint16_t)m.ctx;
+		rec->rep[0] = m.rep0;
+		rec->rep[1] = m.rep1;
+		rec->rep[2] = m.rep2;
+		rec->rep[3] = m.rep3;
+		rec->pos = m.pos;
+		rec->pidx = m.pidx;
+		rec->cost = cost;
+		fence_async_smem();
+		bulk_s2g(dst, rec, (uint32_t)sizeof(Record));
+		bulk_commit();
+		bulk_wait_read();
+	}
+	__syncwarp();
+}
+
+__device__ __forceinline__ void record_load(int lane, Record* rec, Model& m, uint64_t& cost, const Record* src,
+                                            uint64_t* bar, uint32_t& parity)
+{
+	__syncwarp();
+	if (lane == 0) {
+		mbar_expect_tx(bar, (uint32_t)sizeof(Record));
+		bulk_g2s(rec, src, (uint32_t)sizeof(Record), bar);
+	}
+	while (!mbar_try_wait(bar, parity)) {
+	}
+	parity ^= 1;
+	__syncwarp();
+	m.ctx = rec->probs[S_CTX];
+	m.rep0 = rec->rep[0];
+	m.rep1 = rec->rep[1];
+	m.rep2 = rec->rep[2];
+	m.rep3 = rec->rep[3];
+	m.pos = rec->pos;
+	m.pidx = rec->pidx;
+	cost = rec->cost;
+	__syncwarp();
+}
+
+// splitmix64, the chains' counter-based generator (top 31 bits, like rand()).
+__device__ __forceinline__ uint32_t rng31(uint64_t& s)
+{
+	s += 0x9E3779B97F4A7C15ull;
+	uint64_t z = s;
+	z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+	z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+	z ^= z >> 31;
+	return (uint32_t)(z >> 33);
+}
+
+}  // namespace mg

@@ -1,0 +1,286 @@
+// Warp-level match finder + exact top-k (sm_100a).
+//
+// Replaces substring_enumerator_for_each -> packet_enumerator -> top_k_packet_finder ->
+// max_heap of the reference.  32 earlier occurrences of the bigram at `pos` are examined per
+// step, one per lane: each lane extends its match, prices all of its candidates from the
+// pre-state (a packet's price is a pure function of the model before it, so no state copy
+// per candidate), and only lanes that could still enter the heap replay their candidates,
+// in the reference's enumeration order, into a bounded max-heap kept in shared memory with
+// the reference's exact tie behaviour (src/max_heap.c:82-121, `<=` eviction
+// src/top_k_packet_finder.c:89).  Once the heap is full its root never increases, so
+// skipping a lane whose cheapest candidate is above the root is exact.
+#pragma once
+#include "mg_device.cuh"
+
+namespace mg {
+
+constexpr int MAX_K = 32;
+constexpr uint32_t MAX_MATCH = 273;  // src/packet_enumerator.c:6-7
+
+struct FindScratch {
+	uint64_t ent_pk[MAX_K];
+	uint32_t ent_price[MAX_K];
+	uint32_t len_price[2][MAX_MATCH - 1];  // [0] match lengths, [1] rep lengths; index len-2
+	uint8_t store[MAX_K];                  // heap order -> entry index
+	uint8_t pop_order[MAX_K];              // entry indices, worst first
+	uint32_t count;
+	uint32_t pops;
+};
+
+// floor(c / len) for c*len < 2^32 via one multiply: recip[len] = floor((2^32-1)/len) + 1
+__device__ __forceinline__ uint32_t per_byte(uint32_t cost, uint32_t len, const uint32_t* recip)
+{
+	return len == 1 ? cost : __umulhi(cost, recip[len]);
+}
+
+__device__ __forceinline__ bool heap_gt(const FindScratch* fs, uint32_t a, uint32_t b)
+{
+	return fs->ent_price[a] > fs->ent_price[b];
+}
+
+// src/max_heap.c:82-105
+__device__ __forceinline__ void heap_sift_down(FindScratch* fs, uint32_t parent)
+{
+	uint32_t count = fs->count;
+	for (;;) {
+		uint32_t l = parent * 2 + 1, r = l + 1;
+		if (l >= count) break;
+		uint32_t big = l;
+		if (r < count && heap_gt(fs, fs->store[r], fs->store[l])) big = r;
+		if (!heap_gt(fs, fs->store[big], fs->store[parent])) break;
+		uint8_t t = fs->store[big];
+		fs->store[big] = fs->store[parent];
+		fs->store[parent] = t;
+		parent = big;
+	}
+}
+
+// src/max_heap.c:107-121
+__device__ __forceinline__ void heap_sift_up(FindScratch* fs, uint32_t node)
+{
+	while (node > 0) {
+		uint32_t parent = (node - 1) / 2;
+		if (!heap_gt(fs, fs->store[node], fs->store[parent])) break;
+		uint8_t t = fs->store[node];
+		fs->store[node] = fs->store[parent];
+		fs->store[parent] = t;
+		node = parent;
+	}
+}
+
+// src/top_k_packet_finder.c:72-93,99-101.  Called by exactly one lane at a time.
+__device__ __forceinline__ void heap_offer(FindScratch* fs, uint32_t k, uint64_t pk, uint32_t price, uint64_t excluded)
+{
+	if (pk == excluded) return;
+	uint32_t count = fs->count;
+	if (count < k) {
+		fs->ent_pk[count] = pk;
+		fs->ent_price[count] = price;
+		fs->store[count] = (uint8_t)count;
+		fs->count = count + 1;
+		heap_sift_up(fs, count);
+		return;
+	}
+	uint32_t top = fs->store[0];
+	if (price <= fs->ent_price[top]) {
+		fs->ent_pk[top] = pk;
+		fs->ent_price[top] = price;
+		heap_sift_down(fs, 0);
+	}
+}
+
+__device__ __forceinline__ uint32_t tree_price(const uint16_t* probs, const uint16_t* price, uint32_t base,
+                                               uint32_t nbits, uint32_t value)
+{
+	uint32_t c = 0, node = 1;
+	for (uint32_t i = nbits; i-- > 0;) {
+		uint32_t bit = (value >> i) & 1;
+		c += bit_price(probs, price, base + node, bit);
+		node = (node << 1) | bit;
+	}
+	return c;
+}
+
+// src/lzma_packet_encoder.c:42-63 priced from the pre-state
+__device__ __forceinline__ uint32_t length_price(const uint16_t* probs, const uint16_t* price, uint32_t base,
+                                                 uint32_t len)
+{
+	uint32_t v = len - 2;
+	if (v < 8) return bit_price(probs, price, base, 0) + tree_price(probs, price, base + LEN_LOW, 3, v);
+	uint32_t c = bit_price(probs, price, base, 1);
+	if (v < 16) return c + bit_price(probs, price, base + 1, 0) + tree_price(probs, price, base + LEN_MID, 3, v - 8);
+	return c + bit_price(probs, price, base + 1, 1) + tree_price(probs, price, base + LEN_HIGH, 8, v - 16);
+}
+
+// Literal price at the model's position (src/lzma_packet_encoder.c:106-136)
+__device__ __forceinline__ uint32_t literal_price(const uint16_t* probs, const uint16_t* price, uint32_t ctx,
+                                                  uint32_t byte, uint32_t mbyte)
+{
+	uint32_t c = bit_price(probs, price, S_ISMATCH + ctx, 0);
+	for (uint32_t d = 0; d < 8; d++) {
+		uint32_t slot, bit;
+		lit_event(d, byte, ctx >= 7, mbyte, slot, bit);
+		c += bit_price(probs, price, slot, bit);
+	}
+	return c;
+}
+
+// Distance price without the pos-slot tree: reverse/align tree + direct bits
+__device__ __forceinline__ uint32_t dist_tail_price(const uint16_t* probs, const uint16_t* price, const DistParts& d)
+{
+	uint32_t c = d.direct << 11, node = 1, v = d.low;
+	for (uint32_t i = 0; i < d.rbits; i++) {
+		uint32_t bit = v & 1;
+		c += bit_price(probs, price, d.rbase + node, bit);
+		node = (node << 1) | bit;
+		v >>= 1;
+	}
+	return c;
+}
+
+// Fills fs with the top-k of position m.pos and pops them (fs->pop_order, worst first).
+// probs: the warp's live model (read only here).  Returns the candidate count kept.
+// `candidates` accumulates, per lane, how many candidates that lane priced.
+__device__ __noinline__ uint32_t warp_find(int lane, const uint16_t* probs, const uint16_t* price,
+                                           const uint32_t* recip, FindScratch* fs, const uint8_t* __restrict__ data,
+                                           uint32_t n, const uint32_t* __restrict__ occ_start,
+                                           const uint32_t* __restrict__ occ, const Model& m, uint64_t excluded,
+                                           uint32_t k, uint32_t& candidates)
+{
+	__syncwarp();
+	const uint32_t pos = m.pos, ctx = m.ctx;
+	if (lane == 0) {
+		fs->count = 0;
+		fs->pops = 0;
+	}
+	// packet headers, src/lzma_packet_encoder.c:13-40
+	const uint32_t p_match = bit_price(probs, price, S_ISMATCH + ctx, 1);
+	const uint32_t hdr_match = p_match + bit_price(probs, price, S_ISREP + ctx, 0);
+	const uint32_t hdr_rep = p_match + bit_price(probs, price, S_ISREP + ctx, 1);
+	const uint32_t g0_0 = bit_price(probs, price, S_ISREPG0 + ctx, 0), g0_1 = bit_price(probs, price, S_ISREPG0 + ctx, 1);
+	const uint32_t g1_0 = bit_price(probs, price, S_ISREPG1 + ctx, 0), g1_1 = bit_price(probs, price, S_ISREPG1 + ctx, 1);
+	const uint32_t g2_0 = bit_price(probs, price, S_ISREPG2 + ctx, 0), g2_1 = bit_price(probs, price, S_ISREPG2 + ctx, 1);
+	const uint32_t r0l_0 = bit_price(probs, price, S_ISREP0LONG + ctx, 0);
+	const uint32_t r0l_1 = bit_price(probs, price, S_ISREP0LONG + ctx, 1);
+	const uint32_t hdr_lrep0 = hdr_rep + g0_0 + r0l_1;
+	const uint32_t hdr_lrep1 = hdr_rep + g0_1 + g1_0;
+	const uint32_t hdr_lrep2 = hdr_rep + g0_1 + g1_1 + g2_0;
+	const uint32_t hdr_lrep3 = hdr_rep + g0_1 + g1_1 + g2_1;
+
+	const uint32_t byte = data[pos];
+	const uint32_t rep_byte = pos > 0 ? data[pos - m.rep0 - 1] : 0;
+	__syncwarp();
+	if (lane == 0) {
+		// packet_enumerator.c:60-66: LITERAL, then SHORT_REP when the rep0 byte matches
+		heap_offer(fs, k, PK_LITERAL, literal_price(probs, price, ctx, byte, rep_byte), excluded);
+		if (pos > 0 && byte == rep_byte) heap_offer(fs, k, PK_SHORT_REP, hdr_rep + g0_0 + r0l_0, excluded);
+	}
+	if (lane == 0) candidates += 1 + (pos > 0 && byte == rep_byte);
+	__syncwarp();
+
+	// substring_enumerator.c:87-88
+	if (pos != 0 && pos != n - 1) {
+		const uint32_t key = ((uint32_t)byte << 8) | data[pos + 1];
+		const uint32_t begin = occ_start[key], end = occ_start[key + 1];
+		const uint32_t max_len = n - pos < MAX_MATCH ? n - pos : MAX_MATCH;
+		uint32_t have_len[2] = {1, 1};  // len_price filled for lengths 2..have_len
+		for (uint32_t chunk = begin; chunk < end; chunk += 32) {
+			const uint32_t idx = chunk + (uint32_t)lane;
+			const uint32_t o = idx < end ? occ[idx] : 0xffffffffu;
+			const bool valid = o < pos;  // ascending bucket: stop at the first occurrence >= pos
+			const uint32_t valid_mask = __ballot_sync(FULL, valid);
+			if (valid_mask == 0) break;
+			uint32_t L = 0;
+			if (valid) {
+				L = 2;
+				while (L < max_len && data[pos + L] == data[o + L]) L++;
+			}
+			const uint32_t dist = pos - o - 1;
+			uint32_t rep_mask = 0;
+			if (valid) {
+				rep_mask = (dist == m.rep0 ? 1u : 0u) | (dist == m.rep1 ? 2u : 0u) | (dist == m.rep2 ? 4u : 0u) |
+				           (dist == m.rep3 ? 8u : 0u);
+			}
+			// extend the shared length price tables to the longest match of this step
+			const uint32_t need0 = __reduce_max_sync(FULL, L);
+			const uint32_t need1 = __reduce_max_sync(FULL, rep_mask ? L : 0u);
+			if (need0 > have_len[0]) {
+				for (uint32_t l = have_len[0] + 1 + (uint32_t)lane; l <= need0; l += 32)
+					fs->len_price[0][l - 2] = length_price(probs, price, S_LEN, l);
+				have_len[0] = need0;
+			}
+			if (need1 > have_len[1]) {
+				for (uint32_t l = have_len[1] + 1 + (uint32_t)lane; l <= need1; l += 32)
+					fs->len_price[1][l - 2] = length_price(probs, price, S_REPLEN, l);
+				have_len[1] = need1;
+			}
+			__syncwarp();
+			// per-occurrence distance prices: tail once, pos-slot tree per length context
+			uint32_t base2 = 0, base3 = 0, base4 = 0, base5 = 0;
+			if (valid) {
+				const DistParts dp = dist_parts(dist);
+				const uint32_t tail = hdr_match + dist_tail_price(probs, price, dp);
+				base2 = tail + tree_price(probs, price, S_POSSLOT, 6, dp.pslot);
+				if (L > 2) base3 = tail + tree_price(probs, price, S_POSSLOT + 64, 6, dp.pslot);
+				if (L > 3) base4 = tail + tree_price(probs, price, S_POSSLOT + 128, 6, dp.pslot);
+				if (L > 4) base5 = tail + tree_price(probs, price, S_POSSLOT + 192, 6, dp.pslot);
+			}
+			const uint32_t hdr_r0 = hdr_lrep0, hdr_r1 = hdr_lrep1, hdr_r2 = hdr_lrep2, hdr_r3 = hdr_lrep3;
+			// cheapest candidate of this lane (lower bound test against the heap root)
+			const bool full = fs->count >= k;
+			const uint32_t root = full ? fs->ent_price[fs->store[0]] : 0xffffffffu;
+			uint32_t cheapest = 0xffffffffu;
+			if (valid) {
+				uint32_t rep_hdr_best = 0xffffffffu;
+				if (rep_mask & 1) rep_hdr_best = min(rep_hdr_best, hdr_r0);
+				if (rep_mask & 2) rep_hdr_best = min(rep_hdr_best, hdr_r1);
+				if (rep_mask & 4) rep_hdr_best = min(rep_hdr_best, hdr_r2);
+				if (rep_mask & 8) rep_hdr_best = min(rep_hdr_best, hdr_r3);
+				for (uint32_t len = 2; len <= L; len++) {
+					const uint32_t b = len == 2 ? base2 : len == 3 ? base3 : len == 4 ? base4 : base5;
+					cheapest = min(cheapest, per_byte(b + fs->len_price[0][len - 2], len, recip));
+					if (rep_mask) cheapest = min(cheapest, per_byte(rep_hdr_best + fs->len_price[1][len - 2], len, recip));
+				}
+				candidates += (L - 1) * (1 + __popc(rep_mask));
+			}
+			uint32_t pass = __ballot_sync(FULL, valid && cheapest <= root);
+			// replay survivors in enumeration order: occurrence-major, length ascending,
+			// MATCH before LONG_REP 0..3 (packet_enumerator.c:47-54)
+			while (pass) {
+				const int who = __ffs(pass) - 1;
+				pass &= pass - 1;
+				if (lane == who) {
+					for (uint32_t len = 2; len <= L; len++) {
+						const uint32_t b = len == 2 ? base2 : len == 3 ? base3 : len == 4 ? base4 : base5;
+						heap_offer(fs, k, pk_pack(T_MATCH, dist, len), per_byte(b + fs->len_price[0][len - 2], len, recip),
+						           excluded);
+						if (rep_mask) {
+							const uint32_t lp = fs->len_price[1][len - 2];
+							if (rep_mask & 1) heap_offer(fs, k, pk_pack(T_LONG_REP, 0, len), per_byte(hdr_r0 + lp, len, recip), excluded);
+							if (rep_mask & 2) heap_offer(fs, k, pk_pack(T_LONG_REP, 1, len), per_byte(hdr_r1 + lp, len, recip), excluded);
+							if (rep_mask & 4) heap_offer(fs, k, pk_pack(T_LONG_REP, 2, len), per_byte(hdr_r2 + lp, len, recip), excluded);
+							if (rep_mask & 8) heap_offer(fs, k, pk_pack(T_LONG_REP, 3, len), per_byte(hdr_r3 + lp, len, recip), excluded);
+						}
+					}
+				}
+				__syncwarp();
+			}
+			if (valid_mask != FULL) break;
+		}
+	}
+	__syncwarp();
+	// pop everything, worst first (top_k_packet_finder.c:127-138)
+	if (lane == 0) {
+		uint32_t pops = 0;
+		while (fs->count > 0) {
+			fs->pop_order[pops++] = fs->store[0];
+			fs->store[0] = fs->store[--fs->count];
+			heap_sift_down(fs, 0);
+		}
+		fs->pops = pops;
+	}
+	__syncwarp();
+	return fs->pops;
+}
+
+}  // namespace mg
