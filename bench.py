@@ -1,0 +1,368 @@
+#!/usr/bin/env python
+"""Benchmark of the annealing hot path (BASELINE.json: neighbour cost evals/sec).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # the CUDA path
+    python bench.py --impl reference [--gpus N] --steps K --warmup W  # the reference's CPU path
+
+A "step" = every chain runs `--evals` successful neighbour proposals (mutate, repair, full cost,
+accept/undo) on the 1 MiB synthetic mixed text/binary input of BASELINE.json configs[1], all
+chains starting from the all-literal slab like the reference does.  `value` counts successful
+evaluations of ALL chains on ALL GPUs per second of device time (CUDA events on the library's
+launch stream, max over ranks).  `e2e` is the same metric through the one-shot host call with
+host buffers in and out (input upload, index build, chain allocation, best slab read-back).
+
+Under torchrun (N > 1) every rank owns its own chains (weak scaling, no collective on the data
+path); after each step the ranks all-gather their best costs and the best slab is broadcast from
+the arg-min rank over NCCL (the reference's restart-from-best, src/main.c:75-77).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from tools import corpus  # noqa: E402
+
+METRIC = "neighbour_cost_evals_per_sec"
+UNIT = "evals/s"
+WORKLOAD = "1 MiB synthetic mixed text/binary (tools/corpus.py mixed, seed 7), all-literal start, reference schedule step 0"
+ISSUE_CEILING_BITS_PER_S = 148 * 1.965e9 * 32 / 3  # shared-memory bank ceiling for the scorer
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f), "measured"
+    return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int):
+        self.device = device
+        self.proc = None
+        self.lines: list[str] = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.QUERY}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU legs (the only places this file touches oracle/)
+# ------------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    """One host core: the reference's own loop (src/main.c:78-102) for `evals` evaluations."""
+    kind, n, evals, seed, which = args
+    from oracle import oracle_lib as ol
+    data = corpus.make(kind, n)
+    slab = ol.literal_slab(n)
+    best = slab.copy()
+    if which == "reference":
+        lib = ol.Ref()
+        t0 = time.perf_counter()
+        lib.anneal_epoch(data, slab, best, 0, 0, seed=seed, evals=evals)
+        dt = time.perf_counter() - t0
+    else:
+        lib = ol.Port()
+        t0 = time.perf_counter()
+        lib.anneal_epoch(data, slab, best, 0, 0, rng_mode=0, seed=seed, evals=evals)
+        dt = time.perf_counter() - t0
+    return evals, dt
+
+
+def cpu_kind() -> str:
+    from oracle import oracle_lib as ol
+    ol.build()
+    return "reference" if os.path.exists(ol.REF_SO) else "port"
+
+
+def cpu_baseline(n: int, evals: int) -> dict:
+    """Single-threaded reference on one host core, bounded sample (reported, not the target)."""
+    kind = cpu_kind()
+    done, dt = _cpu_worker(("mixed", n, evals, 1673551, kind))
+    return {"value": done / dt, "unit": UNIT, "cores": 1, "kind": kind,
+            "sample": f"first {done} successful evaluations from the all-literal slab, seed 1673551, {dt:.1f} s"}
+
+
+def run_reference(args) -> None:
+    """--impl reference: the reference's CPU implementation on all host cores it can use
+    (it is single-threaded, so one independent annealing process per core, different seeds)."""
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    n = args.size
+    kind = cpu_kind()
+    cores = max(1, min(os.cpu_count() or 1, args.cpu_procs))
+    evals = args.cpu_evals
+    ctx = mp.get_context("fork")
+    total_evals, total_time = 0, 0.0
+    with ctx.Pool(cores) as pool:
+        for step in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            res = pool.map(_cpu_worker, [("mixed", n, evals, 1673551 + step * cores + w, kind) for w in range(cores)])
+            dt = time.perf_counter() - t0
+            if step >= args.warmup:
+                total_evals += sum(r[0] for r in res)
+                total_time += dt
+    value = total_evals / total_time
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total_time / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u16/u64 integer",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD, "input_bytes": n, "chains": cores, "evals_per_chain_per_step": evals},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
+                             "sample": f"{cores} independent single-threaded annealing processes x {evals} successful "
+                                       f"evaluations per step from the all-literal slab"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# the CUDA arm
+# ------------------------------------------------------------------------------------------------
+def run_cuda(args) -> None:
+    import torch
+    import megalania_b200 as mg
+
+    rank, world, local = dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    mg.load_library()
+    n = args.size
+    data = corpus.make("mixed", n)
+    ctx = mg.Context(data, device=local)
+    props = torch.cuda.get_device_properties(local)
+    chains = args.chains or props.multi_processor_count * args.warps_per_sm
+    chain_bytes = ctx.chain_bytes(chains=chains, track_best=1)
+    free, _ = torch.cuda.mem_get_info(local)
+    while chains > 8 and chains * chain_bytes > 0.85 * free:
+        chains //= 2
+    an = mg.Annealer(ctx, chains, seed=args.seed + 1000003 * rank)
+    an.set_slab(None)
+    import_buf = torch.empty(n * 8, dtype=torch.uint8, device=f"cuda:{local}") if world > 1 else None
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    from megalania_b200.tempering import ReplicaExchange
+    rex = ReplicaExchange(dist, device=f"cuda:{local}", seed=args.seed)
+
+    def exchange():
+        """best-slab broadcast between steps (no collective inside a step): all-gather of the
+        ranks' best costs, NCCL broadcast of the winner's packed slab, the other ranks re-seed
+        their worst chain with it."""
+        if dist is None:
+            return
+        cur, best = an.costs()
+        nz = best[best > 0]
+        rex.broadcast_best(int(nz.min()) if nz.size else 0,
+                           lambda buf: an.export_slab(int(np.where(best > 0, best, np.iinfo(np.uint64).max).argmin()), True, buf.data_ptr()),
+                           lambda buf: an.import_slab(int(cur.argmax()), buf.data_ptr(), adopt_cost=True),
+                           import_buf)
+
+    def step(first_eval):
+        st = an.run(args.evals, schedule=mg.SCHEDULE_REFERENCE, step=0, first_eval=first_eval)
+        exchange()
+        return st
+
+    first_eval = 0
+    for _ in range(args.warmup):
+        step(first_eval)
+        first_eval += args.evals
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    t0 = time.perf_counter()
+    agg = None
+    per_launch_ms = []
+    for _ in range(args.steps):
+        st = step(first_eval)
+        first_eval += args.evals
+        per_launch_ms.append(st["kernel_ms"])
+        if agg is None:
+            agg = dict(st)
+        else:
+            for k, v in st.items():
+                agg[k] += v
+    barrier()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop()
+    device_s = agg["kernel_ms"] / 1e3
+
+    # max over ranks (device time), sum over ranks (work)
+    if dist is not None:
+        t = torch.tensor([device_s, wall], dtype=torch.float64, device=f"cuda:{local}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        device_s, wall = float(t[0]), float(t[1])
+        w = torch.tensor([agg["evals"], agg["bits_scored"], agg["packets_scored"], agg["launches"]], dtype=torch.int64,
+                         device=f"cuda:{local}")
+        dist.all_reduce(w, op=dist.ReduceOp.SUM)
+        total_evals, total_bits, total_packets, launches = (int(x) for x in w)
+    else:
+        total_evals, total_bits, total_packets, launches = agg["evals"], agg["bits_scored"], agg["packets_scored"], agg["launches"]
+    value = total_evals / device_s
+
+    # ---- roofline of the dominant kernel (anneal_kernel), this rank ---------------------------
+    pk, pk_src = peaks()
+    alg_bytes = agg["slab_bytes_read"] + agg["checkpoint_bytes"] + 16 * agg["edits"]
+    achieved = alg_bytes / (agg["kernel_ms"] / 1e3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                "frac": achieved / pk["hbm_gbs"], "traffic": None, "peak_source": pk_src, "kernel": "mg::anneal_kernel",
+                "algorithmic_bytes_per_launch": alg_bytes / max(1, agg["launches"]),
+                "avg_launch_ms": float(np.mean(per_launch_ms)),
+                "note": "the scorer is issue/shared-memory bound, not HBM bound: see roofline_issue"}
+    bits_per_s = agg["bits_scored"] / (agg["kernel_ms"] / 1e3)
+    roofline_issue = {"bound": "shared-memory banks / issue slots", "achieved": bits_per_s,
+                      "peak": ISSUE_CEILING_BITS_PER_S, "unit": "modelled bits/s", "frac": bits_per_s / ISSUE_CEILING_BITS_PER_S,
+                      "bits_per_eval": agg["bits_scored"] / max(1, agg["attempts"])}
+
+    # ---- end to end through the one-shot host call (host buffers in and out) -------------------
+    e2e = None
+    if not args.no_e2e:
+        an.close()
+        ctx.close()
+        e2e_chains = chains
+        barrier()
+        t0 = time.perf_counter()
+        e2e_evals = 0
+        for s in range(args.e2e_steps):
+            c2 = mg.Context(data, device=local)                   # H2D of the input + index build
+            best, cost, st2 = mg.anneal_oneshot(c2, chains=e2e_chains, evals=args.evals, seed=args.seed + s)
+            e2e_evals += st2["evals"]                              # best slab + cost came back to the host
+            c2.close()
+        barrier()
+        e2e_s = time.perf_counter() - t0
+        if dist is not None:
+            t = torch.tensor([e2e_s], dtype=torch.float64, device=f"cuda:{local}")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_s = float(t[0])
+            w = torch.tensor([e2e_evals], dtype=torch.int64, device=f"cuda:{local}")
+            dist.all_reduce(w, op=dist.ReduceOp.SUM)
+            e2e_evals = int(w[0])
+        e2e = {"value": e2e_evals / e2e_s, "unit": UNIT, "h2d_bytes_per_step": n, "d2h_bytes_per_step": 12 * n + 8,
+               "steps": args.e2e_steps, "call": "mg_ctx_create + mg_anneal_oneshot (host data in, best slab + cost out)"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu = cpu_baseline(n, args.cpu_evals)
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": 1e3 * device_s / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "u16 probabilities / u64 cost (integer)",
+                "data": "synthetic",
+                "config": {"workload": WORKLOAD, "input_bytes": n, "chains_per_gpu": chains,
+                           "evals_per_chain_per_step": args.evals, "top_k": 20, "l2": "inputs_exceed_l2",
+                           "per_gpu_slab_bytes": chains * n * 8,
+                           "multi_gpu": "independent chains per rank; all-gather of best costs + NCCL broadcast of the best slab after each step"},
+                "wall_ms_per_step": 1e3 * wall / args.steps,
+                "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
+                "roofline": roofline, "roofline_issue": roofline_issue, "cpu_baseline": cpu,
+                "stats": {"evals": total_evals, "modelled_bits": total_bits, "packets": total_packets,
+                          "attempts": agg["attempts"], "accepted": agg["accepted"],
+                          "finder_candidates": agg["finder_candidates"], "log_overflows": agg["log_overflows"]}}
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["cuda", "reference"], default="cuda")
+    ap.add_argument("--size", type=int, default=1 << 20)
+    ap.add_argument("--chains", type=int, default=0, help="chains per GPU (default: SMs x --warps-per-sm)")
+    ap.add_argument("--warps-per-sm", type=int, default=16)
+    ap.add_argument("--evals", type=int, default=2, help="successful evaluations per chain per step")
+    ap.add_argument("--seed", type=int, default=1673551)
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-evals", type=int, default=0, help="evaluations of the CPU sample (default: sized to ~15 s)")
+    ap.add_argument("--cpu-procs", type=int, default=1 << 30)
+    args = ap.parse_args()
+    if args.cpu_evals == 0:
+        # ~6.6 evals/s at 1 MiB on one core: ~15 s for the single-core sample,
+        # ~2 s per step per core for the all-cores reference arm
+        scale = max(1.0, (1 << 20) / args.size)
+        args.cpu_evals = int((100 if args.impl == "cuda" else 12) * scale * scale)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_cuda(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -203,6 +203,11 @@ MG_API int mg_anneal_swap_chains(mg_anneal* an, uint32_t a, uint32_t b);
  * that move slabs between GPUs with NCCL themselves.  The packed format is private; only
  * copy it between mg_anneal objects created over identical data. */
 MG_API int mg_anneal_device_slab(mg_anneal* an, uint32_t chain, int which, void** dev_ptr, size_t* bytes);
+/* Copies a chain's packed current (0) / best (1) slab into a caller DEVICE buffer of
+ * mg_ctx_size()*8 bytes (e.g. a tensor the host then broadcasts with NCCL), and the inverse:
+ * replaces a chain's current slab from such a buffer, then rescores and checkpoints it. */
+MG_API int mg_anneal_export_slab(mg_anneal* an, uint32_t chain, int which, void* dev_dst);
+MG_API int mg_anneal_import_slab(mg_anneal* an, uint32_t chain, const void* dev_src, int adopt_cost);
 /* After writing a chain's packed current slab through the pointer above: rescore it. */
 MG_API int mg_anneal_refresh_chain(mg_anneal* an, uint32_t chain, int adopt_cost);
 

@@ -77,7 +77,8 @@ EXPORTS = [
     "mg_score_slabs", "mg_find_topk", "mg_encode_slab", "mg_encode_slab_buffer", "mg_anneal_create",
     "mg_anneal_destroy", "mg_anneal_chain_bytes", "mg_anneal_set_slab", "mg_anneal_run", "mg_anneal_costs",
     "mg_anneal_get_slab", "mg_anneal_get_trace", "mg_anneal_swap_chains", "mg_anneal_device_slab",
-    "mg_anneal_refresh_chain", "mg_anneal_oneshot", "mg_debug_model_after_prefix",
+    "mg_anneal_refresh_chain", "mg_anneal_oneshot", "mg_debug_model_after_prefix", "mg_anneal_export_slab",
+    "mg_anneal_import_slab",
 ]
 
 _lib = None
@@ -124,6 +125,8 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
     L.mg_anneal_swap_chains.argtypes = [vp, u32, u32]
     L.mg_anneal_device_slab.argtypes = [vp, u32, i32, C.POINTER(vp), C.POINTER(sz)]
     L.mg_anneal_refresh_chain.argtypes = [vp, u32, i32]
+    L.mg_anneal_export_slab.argtypes = [vp, u32, i32, vp]
+    L.mg_anneal_import_slab.argtypes = [vp, u32, vp, i32]
     L.mg_anneal_oneshot.argtypes = [vp, C.POINTER(AnnealParams), C.POINTER(AnnealRunParams), vp, vp,
                                     C.POINTER(u64), C.POINTER(AnnealStats)]
     L.mg_debug_model_after_prefix.argtypes = [vp, vp, sz, vp]
@@ -313,6 +316,13 @@ class Annealer:
         ptr, size = C.c_void_p(), C.c_size_t()
         _check(self._lib.mg_anneal_device_slab(self._h, chain, int(best), C.byref(ptr), C.byref(size)))
         return ptr.value, size.value
+
+    def export_slab(self, chain: int, best: bool, device_ptr: int) -> None:
+        """Packed slab -> caller device buffer (n*8 bytes), e.g. a torch tensor's data_ptr()."""
+        _check(self._lib.mg_anneal_export_slab(self._h, chain, int(best), C.c_void_p(device_ptr)))
+
+    def import_slab(self, chain: int, device_ptr: int, adopt_cost: bool = True) -> None:
+        _check(self._lib.mg_anneal_import_slab(self._h, chain, C.c_void_p(device_ptr), int(adopt_cost)))
 
     def refresh_chain(self, chain: int, adopt_cost: bool = True) -> None:
         _check(self._lib.mg_anneal_refresh_chain(self._h, chain, int(adopt_cost)))

@@ -908,6 +908,28 @@ extern "C" MG_API int mg_anneal_device_slab(mg_anneal* an, uint32_t chain, int w
 	return MG_OK;
 }
 
+extern "C" MG_API int mg_anneal_export_slab(mg_anneal* an, uint32_t chain, int which, void* dev_dst)
+{
+	if (!an || chain >= an->p.chains || !dev_dst) return fail(MG_EINVAL, "mg_anneal_export_slab: bad argument");
+	if (which == 1 && !an->d_bests) return fail(MG_ESTATE, "mg_anneal_export_slab: chains were created without track_best");
+	CU(cudaSetDevice(an->ctx->device));
+	const size_t n = an->ctx->n;
+	const uint64_t* src = (which == 1 ? an->d_bests : an->d_slabs) + (size_t)chain * n;
+	CU(cudaMemcpyAsync(dev_dst, src, n * 8, cudaMemcpyDeviceToDevice, an->ctx->stream));
+	CU(cudaStreamSynchronize(an->ctx->stream));
+	return MG_OK;
+}
+
+extern "C" MG_API int mg_anneal_import_slab(mg_anneal* an, uint32_t chain, const void* dev_src, int adopt_cost)
+{
+	if (!an || chain >= an->p.chains || !dev_src) return fail(MG_EINVAL, "mg_anneal_import_slab: bad argument");
+	CU(cudaSetDevice(an->ctx->device));
+	const size_t n = an->ctx->n;
+	CU(cudaMemcpyAsync(an->d_slabs + (size_t)chain * n, dev_src, n * 8, cudaMemcpyDeviceToDevice, an->ctx->stream));
+	if (int rc = refresh_chains(an, chain, 1, adopt_cost, 0)) return rc;
+	return MG_OK;
+}
+
 // Swap two chains' slabs, checkpoints and costs (replica exchange on one device).
 extern "C" MG_API int mg_anneal_swap_chains(mg_anneal* an, uint32_t x, uint32_t y)
 {

@@ -25,6 +25,7 @@ struct FindScratch {
 	uint8_t pop_order[MAX_K];              // entry indices, worst first
 	uint32_t count;
 	uint32_t pops;
+	uint32_t candidates;  // candidates enumerated by the last find
 };
 
 // floor(c / len) for c*len < 2^32 via one multiply: recip[len] = floor((2^32-1)/len) + 1
@@ -139,14 +140,16 @@ __device__ __forceinline__ uint32_t dist_tail_price(const uint16_t* probs, const
 }
 
 // Fills fs with the top-k of position m.pos and pops them (fs->pop_order, worst first).
-// probs: the warp's live model (read only here).  Returns the candidate count kept.
-// `candidates` accumulates, per lane, how many candidates that lane priced.
-__device__ __noinline__ uint32_t warp_find(int lane, const uint16_t* probs, const uint16_t* price,
+// probs: the warp's live model (read only here).  Returns the candidate count kept;
+// fs->candidates receives how many candidates were enumerated.  The model is taken by value so
+// that the caller's copy stays in registers across this (deliberately out-of-line) call.
+__device__ __forceinline__ uint32_t warp_find(int lane, const uint16_t* probs, const uint16_t* price,
                                            const uint32_t* recip, FindScratch* fs, const uint8_t* __restrict__ data,
                                            uint32_t n, const uint32_t* __restrict__ occ_start,
-                                           const uint32_t* __restrict__ occ, const Model& m, uint64_t excluded,
-                                           uint32_t k, uint32_t& candidates)
+                                           const uint32_t* __restrict__ occ, const Model m, uint64_t excluded,
+                                           uint32_t k)
 {
+	uint32_t candidates = 0;
 	__syncwarp();
 	const uint32_t pos = m.pos, ctx = m.ctx;
 	if (lane == 0) {
@@ -269,8 +272,10 @@ __device__ __noinline__ uint32_t warp_find(int lane, const uint16_t* probs, cons
 		}
 	}
 	__syncwarp();
+	candidates = __reduce_add_sync(FULL, candidates);
 	// pop everything, worst first (top_k_packet_finder.c:127-138)
 	if (lane == 0) {
+		fs->candidates = candidates;
 		uint32_t pops = 0;
 		while (fs->count > 0) {
 			fs->pop_order[pops++] = fs->store[0];

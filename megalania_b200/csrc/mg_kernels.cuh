@@ -209,7 +209,8 @@ __global__ void __launch_bounds__(CTA_THREADS) topk_kernel(TopkArgs a)
 		uint32_t pops = 0;
 		if (!err) {
 			pops = warp_find(lane, ws->rec.probs, sh->price, sh->recip, &ws->fs, a.data, a.n, a.occ_start, a.occ, m,
-			                 a.slab[qpos], a.k, cand);
+			                 a.slab[qpos], a.k);
+			cand += ws->fs.candidates;
 			for (uint32_t i = lane; i < pops; i += 32) {
 				const uint32_t e = ws->fs.pop_order[i];
 				a.out_pk[(size_t)q * a.k + i] = ws->fs.ent_pk[e];
@@ -222,7 +223,6 @@ __global__ void __launch_bounds__(CTA_THREADS) topk_kernel(TopkArgs a)
 		}
 		__syncwarp();
 	}
-	cand = __reduce_add_sync(FULL, cand);
 	if (lane == 0 && cand) atomicAdd(a.candidates, (unsigned long long)cand);
 }
 
@@ -317,10 +317,11 @@ __device__ __forceinline__ void log_put(int lane, EditLog& lg, uint32_t pos, uin
 // src/packet_slab_neighbour.c:48-72.  Returns false when the finder has no alternative.
 __device__ __forceinline__ bool pick_from_topk(int lane, WarpShared* ws, const CtaShared* sh, const AnnealArgs& a,
                                                const Model& m, uint64_t excluded, bool best, uint64_t& rng,
-                                               uint64_t& chosen, uint32_t& cand)
+                                               uint64_t& chosen, unsigned long long& cand)
 {
 	const uint32_t count =
-	    warp_find(lane, ws->rec.probs, sh->price, sh->recip, &ws->fs, a.data, a.n, a.occ_start, a.occ, m, excluded, a.k, cand);
+	    warp_find(lane, ws->rec.probs, sh->price, sh->recip, &ws->fs, a.data, a.n, a.occ_start, a.occ, m, excluded, a.k);
+	cand += ws->fs.candidates;
 	if (count == 0) return false;
 	uint32_t choice = rng31(rng) % count;
 	for (int i = 1; i < 8; i++) {
@@ -354,7 +355,6 @@ __global__ void __launch_bounds__(CTA_THREADS) anneal_kernel(AnnealArgs a)
 	uint64_t rng = st.rng;
 	uint32_t parity = 0;
 	ChainStats cs = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-	uint32_t cand = 0;
 	EditLog lg;
 	lg.e = a.logs + (size_t)c * a.log_cap;
 	lg.cap = a.log_cap;
@@ -427,7 +427,7 @@ __global__ void __launch_bounds__(CTA_THREADS) anneal_kernel(AnnealArgs a)
 		bool ok = true;
 		if (!mutated) {
 			cs.finds++;
-			ok = pick_from_topk(lane, ws, sh, a, m, first, false, rng, newpk, cand);
+			ok = pick_from_topk(lane, ws, sh, a, m, first, false, rng, newpk, cs.candidates);
 			if (ok) log_put(lane, lg, pos, newpk);
 		}
 		if (!ok) {
@@ -502,7 +502,7 @@ __global__ void __launch_bounds__(CTA_THREADS) anneal_kernel(AnnealArgs a)
 					const bool best = rng31(rng) % 4 == 0;
 					cs.finds++;
 					uint64_t chosen = pk;
-					pick_from_topk(lane, ws, sh, a, m, pk, best, rng, chosen, cand);
+					pick_from_topk(lane, ws, sh, a, m, pk, best, rng, chosen, cs.candidates);
 					pk = chosen;
 				}
 			}
@@ -577,7 +577,6 @@ __global__ void __launch_bounds__(CTA_THREADS) anneal_kernel(AnnealArgs a)
 
 	cs.evals = done;
 	cs.attempts = attempts;
-	cs.candidates = __reduce_add_sync(FULL, cand);
 	if (lane == 0) {
 		st.rng = rng;
 		a.state[c] = st;

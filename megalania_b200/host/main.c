@@ -1,0 +1,146 @@
+/* megalania: drop-in CLI of the reference (src/main.c) over the B200 annealing engine.
+ *
+ *   megalania [options] <file>  ->  .lzma on stdout, progress on stderr, exit 255 on usage/IO error
+ *
+ * The structure of src/main.c:64-119 is kept: `steps` rounds of `epochs` restarts, step 0 from the
+ * all-literal slab and later steps from the best slab so far, the reference's acceptance rule,
+ * then one range-coder pass over the winning slab through the OutputInterface plug-in.  What
+ * changes is the engine: every epoch runs on thousands of chains at once (mg_anneal_run), and
+ * the iteration budget is explicit because the stock 3 x 200 x n schedule is O(n^2).
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "file_output.h"
+#include "megalania_cuda.h"
+#include "memory_mapper.h"
+
+static void usage(const char* argv0)
+{
+	fprintf(stderr,
+	        "usage: %s [--chains N] [--iters N] [--epochs N] [--steps N] [--seed N] [--device N] [--top-k N] filename\n",
+	        argv0);
+}
+
+static int die(const char* what)
+{
+	fprintf(stderr, "%s: %s\n", what, mg_last_error());
+	return -1;
+}
+
+int main(int argc, char** argv)
+{
+	unsigned chains = 1184, iters = 0, epochs = 2, steps = 3, device = 0, top_k = 20;
+	unsigned long long seed = 1673551; /* src/main.c:68 */
+	const char* filename = NULL;
+	for (int i = 1; i < argc; i++) {
+		const char* a = argv[i];
+		unsigned* target = NULL;
+		if (!strcmp(a, "--chains")) target = &chains;
+		else if (!strcmp(a, "--iters")) target = &iters;
+		else if (!strcmp(a, "--epochs")) target = &epochs;
+		else if (!strcmp(a, "--steps")) target = &steps;
+		else if (!strcmp(a, "--device")) target = &device;
+		else if (!strcmp(a, "--top-k")) target = &top_k;
+		if (target) {
+			if (++i >= argc) { usage(argv[0]); return -1; }
+			*target = (unsigned)strtoul(argv[i], NULL, 10);
+		} else if (!strcmp(a, "--seed")) {
+			if (++i >= argc) { usage(argv[0]); return -1; }
+			seed = strtoull(argv[i], NULL, 10);
+		} else if (a[0] == '-' && a[1] == '-') {
+			usage(argv[0]);
+			return -1;
+		} else if (filename == NULL) {
+			filename = a;
+		} else {
+			usage(argv[0]);
+			return -1;
+		}
+	}
+	if (filename == NULL || chains == 0 || steps == 0 || epochs == 0) {
+		usage(argv[0]);
+		return -1;
+	}
+
+	const uint8_t* file_data;
+	size_t file_size;
+	if (map_file(filename, &file_data, &file_size) < 0) return -1;
+	if (file_size == 0) return 0;
+	if (iters == 0) iters = file_size < 2000 ? (unsigned)file_size : 2000;
+
+	LZMAProperties properties = { 0, 0, 0 };
+	mg_ctx* ctx = NULL;
+	if (mg_ctx_create(file_data, file_size, properties, (int)device, &ctx)) return die("mg_ctx_create");
+
+	mg_anneal_params params;
+	memset(&params, 0, sizeof(params));
+	params.chains = chains;
+	params.top_k = top_k;
+	params.track_best = 1;
+	params.seed = seed;
+	mg_anneal* an = NULL;
+	if (mg_anneal_create(ctx, &params, &an)) return die("mg_anneal_create");
+
+	LZMAPacket* packets_best = malloc(sizeof(LZMAPacket) * file_size);
+	uint64_t* best_costs = malloc(sizeof(uint64_t) * chains);
+	if (!packets_best || !best_costs) {
+		fprintf(stderr, "out of memory\n");
+		return -1;
+	}
+	uint64_t best_perplexity = 0;
+	int have_best = 0;
+	unsigned long long evals = 0;
+	double device_ms = 0;
+
+	for (unsigned step = 0; step < steps; step++) {
+		for (unsigned epoch = 0; epoch < epochs; epoch++) {
+			/* src/main.c:71-77: fresh slab in step 0, the best so far afterwards; cost 0 means
+			 * "first proposal always accepted" */
+			if (mg_anneal_set_slab(an, 0, chains, (step != 0 && have_best) ? packets_best : NULL, 0, 0))
+				return die("mg_anneal_set_slab");
+			mg_anneal_run_params run;
+			memset(&run, 0, sizeof(run));
+			run.evals = iters;
+			run.schedule = MG_SCHEDULE_REFERENCE;
+			run.step = step;
+			run.num_iters = iters;
+			mg_anneal_stats stats;
+			if (mg_anneal_run(an, &run, &stats)) return die("mg_anneal_run");
+			evals += stats.evals;
+			device_ms += stats.kernel_ms;
+			if (mg_anneal_costs(an, NULL, best_costs)) return die("mg_anneal_costs");
+			unsigned arg = 0;
+			for (unsigned c = 1; c < chains; c++)
+				if (best_costs[c] != 0 && (best_costs[arg] == 0 || best_costs[c] < best_costs[arg])) arg = c;
+			if (best_costs[arg] != 0 && (!have_best || best_costs[arg] < best_perplexity)) {
+				best_perplexity = best_costs[arg];
+				if (mg_anneal_get_slab(an, arg, 1, packets_best)) return die("mg_anneal_get_slab");
+				have_best = 1;
+			}
+			fprintf(stderr, "current file size: %f\tstep: %u\tepoch: %04u - %llu evals, %.0f evals/s\n",
+			        18 + best_perplexity / 16384.f, step + 1, epoch, evals, evals / (device_ms / 1e3));
+		}
+	}
+	mg_anneal_destroy(an);
+	if (!have_best) {
+		/* no position had an alternative packet (the reference loops forever here): all literals */
+		for (size_t i = 0; i < file_size; i++) {
+			packets_best[i].type = LITERAL;
+			packets_best[i].dist = 0;
+			packets_best[i].len = 1;
+		}
+	}
+
+	OutputInterface output;
+	file_output_new(&output, stdout);
+	if (mg_encode_slab(ctx, packets_best, &output)) return die("mg_encode_slab");
+	fflush(stdout);
+
+	free(best_costs);
+	free(packets_best);
+	mg_ctx_destroy(ctx);
+	if (unmap(file_data, file_size) < 0) return -1;
+	return 0;
+}

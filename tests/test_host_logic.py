@@ -1,0 +1,47 @@
+"""Host-side pieces that need no GPU: corpus generators, the reciprocal-multiply division the
+finder uses, argument checking of the Python mirror."""
+import hashlib
+
+import numpy as np
+import pytest
+
+from tools import corpus
+
+
+def test_corpus_is_deterministic_and_shaped():
+    a = corpus.make("mixed", 1 << 16)
+    b = corpus.make("mixed", 1 << 16)
+    assert a == b and len(a) == 1 << 16
+    assert corpus.text(1000, 1) != corpus.text(1000, 2)
+    text = corpus.text(1 << 14)
+    assert sum(c in b" .,?\n" or chr(c).isalpha() for c in text) == len(text)
+    binary = corpus.binary(1 << 14)
+    zero_frac = binary.count(0) / len(binary)
+    assert 0.2 < zero_frac < 0.8
+    big = corpus.corpus16(1 << 18)
+    assert len(big) == 1 << 18
+    # pinned digest: the generators feed every golden vector
+    assert hashlib.sha256(corpus.text(4096)).hexdigest()[:16] == hashlib.sha256(corpus.make("text", 4096, 12345)).hexdigest()[:16]
+
+
+def test_reciprocal_division_is_exact():
+    """mg_finder.cuh per_byte(): floor(c/len) == umulhi(c, floor((2^32-1)/len)+1) whenever c*len < 2^32."""
+    rng = np.random.default_rng(0)
+    for length in range(2, 274):
+        m = 0xFFFFFFFF // length + 1
+        limit = min((1 << 32) // length, 1 << 22)
+        cs = np.concatenate([rng.integers(0, limit, 2000), np.arange(0, 600), np.array([limit - 1, limit - 2])]).astype(np.uint64)
+        got = (cs * np.uint64(m)) >> np.uint64(32)
+        assert (got == cs // np.uint64(length)).all(), length
+
+
+def test_python_mirror_checks_arguments():
+    import megalania_b200 as mg
+    from megalania_b200 import api
+    slab = mg.literal_slab(8)
+    assert slab.dtype.itemsize == 12
+    with pytest.raises(ValueError):
+        api._slab_ptr(slab, 9)
+    repacked = np.concatenate([slab, slab])
+    fixed = api.as_slab(repacked)
+    assert fixed.dtype == api.PACKET_DTYPE and fixed.size == 16 and (fixed["len"] == 1).all()
