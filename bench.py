@@ -4,9 +4,9 @@
     python bench.py [--gpus N] [--steps K] [--warmup W]            # the CUDA path
     python bench.py --impl reference [--gpus N] --steps K --warmup W  # the reference's CPU path
 
-A "step" = every chain runs `--evals` successful neighbour proposals (mutate, repair, full cost,
-accept/undo) on the 1 MiB synthetic mixed text/binary input of BASELINE.json configs[1], all
-chains starting from the all-literal slab like the reference does.  `value` counts successful
+A "step" = every chain runs successful neighbour proposals (mutate, repair, full cost, accept/undo)
+until it has priced `--packet-budget` packets, on the 1 MiB synthetic mixed text/binary input of
+BASELINE.json configs[1], all chains starting from the all-literal slab like the reference does.  `value` counts successful
 evaluations of ALL chains on ALL GPUs per second of device time (CUDA events on the library's
 launch stream, max over ranks).  `e2e` is the same metric through the one-shot host call with
 host buffers in and out (input upload, index build, chain allocation, best slab read-back).
@@ -109,11 +109,20 @@ def dist_env():
 # ------------------------------------------------------------------------------------------------
 # CPU legs (the only places this file touches oracle/)
 # ------------------------------------------------------------------------------------------------
+_CORPUS_CACHE: dict = {}
+
+
+def _corpus(kind: str, n: int) -> bytes:
+    if (kind, n) not in _CORPUS_CACHE:
+        _CORPUS_CACHE[(kind, n)] = corpus.make(kind, n)
+    return _CORPUS_CACHE[(kind, n)]
+
+
 def _cpu_worker(args):
     """One host core: the reference's own loop (src/main.c:78-102) for `evals` evaluations."""
     kind, n, evals, seed, which = args
     from oracle import oracle_lib as ol
-    data = corpus.make(kind, n)
+    data = _corpus(kind, n)
     slab = ol.literal_slab(n)
     best = slab.copy()
     if which == "reference":
@@ -154,6 +163,7 @@ def run_reference(args) -> None:
     kind = cpu_kind()
     cores = max(1, min(os.cpu_count() or 1, args.cpu_procs))
     evals = args.cpu_evals
+    _corpus("mixed", n)  # generated once, inherited by the forked workers
     ctx = mp.get_context("fork")
     total_evals, total_time = 0, 0.0
     with ctx.Pool(cores) as pool:
@@ -196,7 +206,7 @@ def run_cuda(args) -> None:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     mg.load_library()
     n = args.size
-    data = corpus.make("mixed", n)
+    data = _corpus("mixed", n)
     ctx = mg.Context(data, device=local)
     props = torch.cuda.get_device_properties(local)
     chains = args.chains or props.multi_processor_count * args.warps_per_sm
@@ -230,7 +240,8 @@ def run_cuda(args) -> None:
                            import_buf)
 
     def step(first_eval):
-        st = an.run(args.evals, schedule=mg.SCHEDULE_REFERENCE, step=0, first_eval=first_eval)
+        st = an.run(args.evals, schedule=mg.SCHEDULE_REFERENCE, step=0, first_eval=mg.CONTINUE_EVALS,
+                    packet_budget=args.packet_budget)
         exchange()
         return st
 
@@ -296,7 +307,8 @@ def run_cuda(args) -> None:
         e2e_evals = 0
         for s in range(args.e2e_steps):
             c2 = mg.Context(data, device=local)                   # H2D of the input + index build
-            best, cost, st2 = mg.anneal_oneshot(c2, chains=e2e_chains, evals=args.evals, seed=args.seed + s)
+            best, cost, st2 = mg.anneal_oneshot(c2, chains=e2e_chains, evals=args.evals, seed=args.seed + s,
+                                                packet_budget=args.packet_budget)
             e2e_evals += st2["evals"]                              # best slab + cost came back to the host
             c2.close()
         barrier()
@@ -321,7 +333,8 @@ def run_cuda(args) -> None:
                 "scaling": "weak", "vs_baseline": None, "dtype": "u16 probabilities / u64 cost (integer)",
                 "data": "synthetic",
                 "config": {"workload": WORKLOAD, "input_bytes": n, "chains_per_gpu": chains,
-                           "evals_per_chain_per_step": args.evals, "top_k": 20, "l2": "inputs_exceed_l2",
+                           "step": f"each chain runs whole evaluations until it has priced {args.packet_budget} packets "
+                                   f"(cap {args.evals} evaluations)", "top_k": 20, "l2": "inputs_exceed_l2",
                            "per_gpu_slab_bytes": chains * n * 8,
                            "multi_gpu": "independent chains per rank; all-gather of best costs + NCCL broadcast of the best slab after each step"},
                 "wall_ms_per_step": 1e3 * wall / args.steps,
@@ -345,7 +358,10 @@ def main() -> None:
     ap.add_argument("--size", type=int, default=1 << 20)
     ap.add_argument("--chains", type=int, default=0, help="chains per GPU (default: SMs x --warps-per-sm)")
     ap.add_argument("--warps-per-sm", type=int, default=16)
-    ap.add_argument("--evals", type=int, default=2, help="successful evaluations per chain per step")
+    ap.add_argument("--evals", type=int, default=1000, help="cap on successful evaluations per chain per step")
+    ap.add_argument("--packet-budget", type=int, default=4_000_000,
+                    help="a chain ends its step after the evaluation that brings its priced packets to this many "
+                         "(time-boxed steps keep all warps busy; about 8 evaluations per chain per step at 1 MiB)")
     ap.add_argument("--seed", type=int, default=1673551)
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-e2e", action="store_true")

@@ -142,9 +142,14 @@ typedef struct {
 	uint32_t schedule;     /* MG_SCHEDULE_* */
 	uint32_t step;         /* reference schedule: `step` of src/main.c:69 */
 	uint32_t num_iters;    /* reference schedule: `num_iters` of src/main.c:67 (0 = n) */
-	uint32_t first_eval;   /* reference schedule: value of i for the first proposal */
+	uint32_t first_eval;   /* reference schedule: value of i for the first proposal, or
+	                          MG_CONTINUE_EVALS to carry each chain's own count on from its last run */
 	const float* temperatures; /* MG_SCHEDULE_TEMPERATURE: host array [chains], 1/2048-bit units */
+	uint64_t packet_budget; /* 0 = none; else a chain also stops after the evaluation that brings the
+	                           packets it priced in this call to this many (time-boxed steps: every
+	                           warp then finishes at about the same moment whatever its suffix lengths) */
 } mg_anneal_run_params;
+#define MG_CONTINUE_EVALS 0xffffffffu
 
 typedef struct {
 	uint64_t evals;        /* successful proposals (the headline unit), all chains */

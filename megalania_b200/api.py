@@ -28,6 +28,7 @@ MODEL_DTYPE = np.dtype({"names": ["probs", "ctx_state", "dists", "position", "co
                         "offsets": [0, 5230, 5232, 5248, 5256], "itemsize": 5264})
 INVALID, LITERAL, MATCH, SHORT_REP, LONG_REP = 0, 1, 2, 3, 4
 SCHEDULE_REFERENCE, SCHEDULE_TEMPERATURE = 0, 1
+CONTINUE_EVALS = 0xFFFFFFFF
 
 ERRORS = {-1: "MG_EINVAL", -2: "MG_ECUDA", -3: "MG_ENOMEM", -4: "MG_ESLAB", -5: "MG_EOUTPUT", -6: "MG_ESTATE"}
 
@@ -51,7 +52,7 @@ class AnnealParams(C.Structure):
 class AnnealRunParams(C.Structure):
     _fields_ = [("evals", C.c_uint32), ("max_attempts", C.c_uint32), ("schedule", C.c_uint32),
                 ("step", C.c_uint32), ("num_iters", C.c_uint32), ("first_eval", C.c_uint32),
-                ("temperatures", C.POINTER(C.c_float))]
+                ("temperatures", C.POINTER(C.c_float)), ("packet_budget", C.c_uint64)]
 
 
 class AnnealStats(C.Structure):
@@ -85,7 +86,8 @@ _lib = None
 
 
 def library_path() -> str:
-    return _build.LIB
+    """The in-tree library; MEGALANIA_CUDA_LIB selects another build of the same sources (kernel experiments)."""
+    return os.environ.get("MEGALANIA_CUDA_LIB") or _build.LIB
 
 
 def load_library(build_if_missing: bool = True) -> C.CDLL:
@@ -278,7 +280,7 @@ class Annealer:
         _check(self._lib.mg_anneal_set_slab(self._h, first, count, ptr, int(adopt_cost), int(reset_best)))
 
     def run(self, evals: int, *, schedule: int = SCHEDULE_REFERENCE, step: int = 0, num_iters: int = 0,
-            first_eval: int = 0, max_attempts: int = 0, temperatures=None) -> dict:
+            first_eval: int = 0, max_attempts: int = 0, temperatures=None, packet_budget: int = 0) -> dict:
         temps = None
         tptr = None
         if temperatures is not None:
@@ -286,7 +288,7 @@ class Annealer:
             if temps.size != self.chains:
                 raise ValueError("one temperature per chain")
             tptr = temps.ctypes.data_as(C.POINTER(C.c_float))
-        rp = AnnealRunParams(evals, max_attempts, schedule, step, num_iters, first_eval, tptr)
+        rp = AnnealRunParams(evals, max_attempts, schedule, step, num_iters, first_eval, tptr, packet_budget)
         st = AnnealStats()
         _check(self._lib.mg_anneal_run(self._h, C.byref(rp), C.byref(st)))
         return st.as_dict()
@@ -329,11 +331,12 @@ class Annealer:
 
 
 def anneal_oneshot(ctx: Context, *, chains: int, evals: int, init: np.ndarray | None = None, seed: int = 1673551,
-                   top_k: int = 20, schedule: int = SCHEDULE_REFERENCE, step: int = 0, num_iters: int = 0):
+                   top_k: int = 20, schedule: int = SCHEDULE_REFERENCE, step: int = 0, num_iters: int = 0,
+                   packet_budget: int = 0):
     """Host buffers in, host buffers out: the call the end-to-end benchmark times."""
     lib = ctx._lib
     p = AnnealParams(chains, top_k, 0, 0, 1, 0, seed)
-    rp = AnnealRunParams(evals, 0, schedule, step, num_iters, 0, None)
+    rp = AnnealRunParams(evals, 0, schedule, step, num_iters, 0, None, packet_budget)
     st = AnnealStats()
     best = np.zeros(ctx.n, dtype=PACKET_DTYPE)
     cost = C.c_uint64(0)

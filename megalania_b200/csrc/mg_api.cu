@@ -42,7 +42,7 @@ struct mg_ctx {
 	uint8_t* d_data = nullptr;      // n + 32 bytes, zero padded
 	uint32_t* d_occ_start = nullptr;  // 65537
 	uint32_t* d_occ = nullptr;        // n
-	uint16_t* d_price = nullptr;
+	uint32_t* d_trans = nullptr;
 	uint32_t* d_recip = nullptr;
 	Tables tables{};
 	int sm_count = 0;
@@ -126,7 +126,7 @@ extern "C" MG_API int mg_ctx_create(const uint8_t* data, size_t n, LZMAPropertie
 {
 	if (!data || !out || n == 0) return fail(MG_EINVAL, "mg_ctx_create: data, out and a non-zero size are required");
 	if (props.lc || props.lp || props.pb) return fail(MG_EINVAL, "only lc = lp = pb = 0 is supported (as in the reference)");
-	if (n >= 0xfffff000ull) return fail(MG_EINVAL, "input larger than 4 GiB - 4 KiB is not supported");
+	if (n >= 0x7fffff00ull) return fail(MG_EINVAL, "inputs of 2 GiB and more are not supported");
 	int count = 0;
 	if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
 		return fail(MG_ECUDA, "no CUDA device available (this library has no CPU path)");
@@ -151,18 +151,25 @@ extern "C" MG_API int mg_ctx_create(const uint8_t* data, size_t n, LZMAPropertie
 		CUB(cudaMalloc(&ctx->d_data, n + 32));
 		CUB(cudaMemsetAsync(ctx->d_data + n, 0, 32, ctx->stream));
 		CUB(cudaMemcpyAsync(ctx->d_data, data, n, cudaMemcpyHostToDevice, ctx->stream));
-		// price table: reference generate_table.py:7-9, -int(log2(i/2048.)*2048)
-		std::vector<uint16_t> price(2048);
+		// price table: reference generate_table.py:7-9, -int(log2(i/2048.)*2048); fused with the
+		// probability update of src/probability_model.c:5-15 into one transition table
+		std::vector<uint32_t> price(2048);
 		price[0] = 0;
-		for (int i = 1; i < 2048; i++) price[i] = (uint16_t)(-(long)(std::log2((double)i / 2048.0) * 2048.0));
+		for (int i = 1; i < 2048; i++) price[i] = (uint32_t)(-(long)(std::log2((double)i / 2048.0) * 2048.0));
+		std::vector<uint32_t> trans(4096);
+		for (uint32_t p = 0; p < 2048; p++) {
+			trans[p] = (p + ((2048u - p) >> 5)) | (price[p] << 16);                        // bit 0
+			trans[2048 + p] = (p - (p >> 5)) | (price[(2048u - p) & 2047u] << 16);        // bit 1
+		}
+		trans[0] = 0;  // probability 0 never occurs in a model: (0, bit 0) is the zero-price fixed point idle lanes sit on
 		std::vector<uint32_t> recip(RECIP_ENTRIES, 0);
 		for (uint32_t i = 1; i < RECIP_ENTRIES; i++) recip[i] = 0xffffffffu / i + 1u;
-		CUB(cudaMalloc(&ctx->d_price, 2048 * sizeof(uint16_t)));
+		CUB(cudaMalloc(&ctx->d_trans, 4096 * sizeof(uint32_t)));
 		CUB(cudaMalloc(&ctx->d_recip, RECIP_ENTRIES * sizeof(uint32_t)));
-		CUB(cudaMemcpyAsync(ctx->d_price, price.data(), 2048 * sizeof(uint16_t), cudaMemcpyHostToDevice, ctx->stream));
+		CUB(cudaMemcpyAsync(ctx->d_trans, trans.data(), 4096 * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
 		CUB(cudaMemcpyAsync(ctx->d_recip, recip.data(), RECIP_ENTRIES * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
 		CUB(cudaStreamSynchronize(ctx->stream));
-		ctx->tables.price = ctx->d_price;
+		ctx->tables.trans = ctx->d_trans;
 		ctx->tables.recip = ctx->d_recip;
 		rc = build_index(ctx);
 #undef CUB
@@ -183,7 +190,7 @@ extern "C" MG_API void mg_ctx_destroy(mg_ctx* ctx)
 	cudaFree(ctx->d_data);
 	cudaFree(ctx->d_occ_start);
 	cudaFree(ctx->d_occ);
-	cudaFree(ctx->d_price);
+	cudaFree(ctx->d_trans);
 	cudaFree(ctx->d_recip);
 	if (ctx->stream) cudaStreamDestroy(ctx->stream);
 	delete ctx;
@@ -257,6 +264,7 @@ static int score_device(mg_ctx* ctx, const uint64_t* d_slabs, uint32_t nslabs, u
 	a.ck_pidx = ck_pidx;
 	a.stride = stride;
 	a.nslots = nslots ? nslots : 1;
+	a.ck_chain_stride = a.nslots - 1;
 	a.final_model = final_model;
 	a.tables = ctx->tables;
 	const int blocks = (int)((nslabs + WARPS_PER_CTA - 1) / WARPS_PER_CTA);
@@ -323,7 +331,7 @@ static void export_model(const Record& r, mg_model_dump* out)
 		put(ref_ctx + 228 + s, S_ISREPG2 + s);
 		put(ref_ctx + 240 + (s << 4), S_ISREP0LONG + s);
 	}
-	out->ctx_state = (uint8_t)r.probs[S_CTX];
+	out->ctx_state = (uint8_t)r.ctx;
 	for (int i = 0; i < 4; i++) out->dists[i] = r.rep[i];
 	out->position = r.pos;
 	out->cost = r.cost;
@@ -690,6 +698,7 @@ static int refresh_chains(mg_anneal* an, uint32_t first, uint32_t count, int ado
 		a.ck_pidx = an->d_ck_pidx + (size_t)c * 2 * nck;
 		a.stride = an->stride;
 		a.nslots = an->nslots;
+		a.ck_chain_stride = 0;
 		a.final_model = nullptr;
 		a.tables = ctx->tables;
 		score_kernel<<<1, CTA_THREADS, sizeof(CtaShared), ctx->stream>>>(a);
@@ -712,6 +721,7 @@ static int refresh_chains(mg_anneal* an, uint32_t first, uint32_t count, int ado
 		st[i].cur_cost = adopt_cost ? cost[i] : 0;
 		st[i].live_count = live[i];
 		st[i].err = 0;
+		st[i].eval_index = 0;
 		if (reset_best) st[i].best_cost = 0;
 	}
 	CU(cudaMemcpyAsync(an->d_state + first, st.data(), count * sizeof(ChainState), cudaMemcpyHostToDevice, ctx->stream));
@@ -758,6 +768,7 @@ extern "C" MG_API int mg_anneal_set_slab(mg_anneal* an, uint32_t first, uint32_t
 			st[i].cur_cost = st[0].cur_cost;
 			st[i].live_count = st[0].live_count;
 			st[i].err = 0;
+			st[i].eval_index = 0;
 			if (reset_best) st[i].best_cost = 0;
 			an->have_slab[first + i] = 1;
 		}
@@ -816,6 +827,7 @@ extern "C" MG_API int mg_anneal_run(mg_anneal* an, const mg_anneal_run_params* r
 	a.step = run->step;
 	a.num_iters = run->num_iters ? run->num_iters : ctx->n;
 	a.first_eval = run->first_eval;
+	a.packet_budget = run->packet_budget;
 	a.temps = run->temperatures ? an->d_temps : nullptr;
 	if (an->nslots <= 1) {
 		// a single slot has no checkpoints: the kernel's nck is 0

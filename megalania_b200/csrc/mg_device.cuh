@@ -35,17 +35,20 @@ constexpr uint32_t S_ISREPG1 = S_ISREPG0 + 12;      // 1739
 constexpr uint32_t S_ISREPG2 = S_ISREPG1 + 12;      // 1751
 constexpr uint32_t S_ISREP0LONG = S_ISREPG2 + 12;   // 1763
 constexpr uint32_t S_TOTAL = S_ISREP0LONG + 12;     // 1775
-constexpr uint32_t S_CTX = S_TOTAL;                 // spare slot 1775 holds ctx_state in a checkpoint
+constexpr uint32_t S_DUMMY = S_TOTAL;               // spare slot: lanes with no event of their own adapt this one
 
-// Working set of one warp == checkpoint record in HBM.  3584 bytes = 224 x 16.
+// Working set of one warp == checkpoint record in HBM.  3600 bytes = 225 x 16.
 struct alignas(16) Record {
 	uint16_t probs[S_TOTAL + 1];  // 3552 B
 	uint32_t rep[4];
 	uint32_t pos;   // byte position of the next packet
 	uint32_t pidx;  // index of that packet in the live chain
+	uint32_t ctx;   // the 12-state automaton
+	uint32_t pad0;
 	uint64_t cost;  // cost of everything before pos, 1/2048 bit
+	uint64_t pad1;
 };
-static_assert(sizeof(Record) == 3584, "record must stay a multiple of 16 bytes for cp.async.bulk");
+static_assert(sizeof(Record) == 3600, "record must stay a multiple of 16 bytes for cp.async.bulk");
 
 // Packed slab slot: dist[31:0] | len[47:32] | type[55:48]
 __host__ __device__ __forceinline__ uint64_t pk_pack(uint32_t type, uint32_t dist, uint32_t len)
@@ -118,22 +121,22 @@ __device__ __forceinline__ uint32_t next_ctx(uint32_t ctx, uint32_t type)
 	return ctx < 7 ? 8 : 11;
 }
 
-// One modelled bit: price it (src/perplexity_encoder.c:6-10) and adapt the slot
-// (src/probability_model.c:5-15).
-__device__ __forceinline__ void code_bit(uint16_t* probs, const uint16_t* price, uint32_t slot, uint32_t bit,
+// Transition table, 4096 x u32, indexed by (bit << 11) | p:
+//   low 16 bits  = the adapted probability  (src/probability_model.c:5-15)
+//   high 16 bits = the price of coding `bit` at probability p (src/perplexity_encoder.c:6-10)
+// One shared-memory load replaces the price lookup plus the shift/add/select update.
+__device__ __forceinline__ void code_bit(uint16_t* probs, const uint32_t* trans, uint32_t slot, uint32_t bit11,
                                          uint32_t& acc)
 {
-	uint32_t p = probs[slot];
-	acc += price[bit ? 2048u - p : p];
-	p = bit ? p - (p >> 5) : p + ((2048u - p) >> 5);
-	probs[slot] = (uint16_t)p;
+	const uint32_t t = trans[probs[slot] | bit11];
+	acc += t >> 16;
+	probs[slot] = (uint16_t)t;
 }
 
-__device__ __forceinline__ uint32_t bit_price(const uint16_t* probs, const uint16_t* price, uint32_t slot,
+__device__ __forceinline__ uint32_t bit_price(const uint16_t* probs, const uint32_t* trans, uint32_t slot,
                                               uint32_t bit)
 {
-	uint32_t p = probs[slot];
-	return price[bit ? 2048u - p : p];
+	return trans[probs[slot] | (bit << 11)] >> 16;
 }
 
 // ---- lane -> (slot, bit) maps ----------------------------------------------------------------
@@ -320,7 +323,7 @@ __device__ __forceinline__ uint32_t model_rep(const Model& m, uint32_t idx)
 
 // Price + adapt one packet across the warp.  `byte` = data[pos]; mbyte only read when the packet
 // is a literal in matched mode.  Returns the number of modelled bits (uniform).
-__device__ __forceinline__ uint32_t apply_packet(int lane, uint16_t* probs, const uint16_t* price, Model& m,
+__device__ __forceinline__ uint32_t apply_packet(int lane, uint16_t* probs, const uint32_t* trans, Model& m,
                                                  uint32_t type, uint32_t len, uint32_t dist, uint32_t byte,
                                                  uint32_t mbyte, uint32_t& acc)
 {
@@ -329,7 +332,7 @@ __device__ __forceinline__ uint32_t apply_packet(int lane, uint16_t* probs, cons
 	if (type == T_MATCH) dp = dist_parts(dist);
 	uint32_t slot = 0, bit = 0;
 	bool active = packet_event(lane, type, len, dist, m.ctx, byte, mbyte, dp, slot, bit);
-	if (active) code_bit(probs, price, slot, bit, acc);
+	if (active) code_bit(probs, trans, slot, bit << 11, acc);
 	if (lane == 0) acc += dp.direct << 11;  // src/perplexity_encoder.c:12-17
 	model_advance(m, type, len, dist);
 	return __popc(__ballot_sync(FULL, active));
@@ -343,46 +346,74 @@ __device__ __forceinline__ void model_init(int lane, uint16_t* probs, Model& m)
 	__syncwarp();
 }
 
+// Shared-memory accessors with 32-bit shared addresses (LDS/STS without generic-address math).
+__device__ __forceinline__ uint32_t lds_u16(uint32_t addr)
+{
+	uint16_t v;
+	asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr) : "memory");
+	return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr)
+{
+	uint32_t v;
+	asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+	return v;
+}
+__device__ __forceinline__ void sts_u16(uint32_t addr, uint32_t v)
+{
+	asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((uint16_t)v) : "memory");
+}
+
 // Window of 32 consecutive slab slots + data bytes held across the warp's registers, with the
-// next window prefetched, so the live-chain walk costs shuffles instead of dependent loads.
+// next window prefetched, so the live-chain walk costs one shuffle per packet instead of a
+// dependent load.  meta = type[2:0] | len[11:3] | data byte[23:16]; dist separately (only
+// matches and long reps need it).
+constexpr uint32_t META_LITERAL = T_LITERAL | (1u << 3);
+__device__ __forceinline__ uint32_t meta_type(uint32_t meta) { return meta & 7; }
+__device__ __forceinline__ uint32_t meta_len(uint32_t meta) { return (meta >> 3) & 0x1fff; }
+__device__ __forceinline__ uint32_t meta_byte(uint32_t meta) { return meta >> 16; }
+
 struct Window {
-	uint64_t pk, pk_next;
-	uint32_t byte, byte_next;
-	uint32_t base;  // multiple of 32; 0xffffffff = empty
+	uint32_t meta, dist, meta_next, dist_next;
+	uint32_t base;  // multiple of 32; WINDOW_NONE = nothing loaded
 };
+constexpr uint32_t WINDOW_NONE = 0x7fffffe0u;  // never within 32 of a real position (inputs < 2 GiB... see mg_ctx_create)
 
 __device__ __forceinline__ void window_load(int lane, const uint64_t* __restrict__ slab,
                                             const uint8_t* __restrict__ data, uint32_t n, uint32_t base,
-                                            uint64_t& pk, uint32_t& byte)
+                                            uint32_t& meta, uint32_t& dist)
 {
-	uint32_t i = base + (uint32_t)lane;
-	bool in = i < n && base < n;
-	pk = in ? slab[i] : 0;
-	byte = in ? data[i] : 0;
+	const uint32_t i = base + (uint32_t)lane;
+	const bool in = i < n;
+	const uint64_t pk = in ? slab[i] : 0;
+	const uint32_t byte = in ? data[i] : 0;
+	const uint32_t len = pk_len(pk);
+	meta = pk_type(pk) | ((len < 0x1fff ? len : 0x1fff) << 3) | (byte << 16);
+	dist = pk_dist(pk);
 }
 
 __device__ __forceinline__ void window_seek(int lane, Window& w, const uint64_t* __restrict__ slab,
                                             const uint8_t* __restrict__ data, uint32_t n, uint32_t pos)
 {
-	uint32_t want = pos & ~31u;
+	const uint32_t want = pos & ~31u;
 	if (want == w.base) return;
-	if (w.base != 0xffffffffu && want == w.base + 32) {
-		w.pk = w.pk_next;
-		w.byte = w.byte_next;
+	if (want == w.base + 32) {
+		w.meta = w.meta_next;
+		w.dist = w.dist_next;
 	} else {
-		window_load(lane, slab, data, n, want, w.pk, w.byte);
+		window_load(lane, slab, data, n, want, w.meta, w.dist);
 	}
 	w.base = want;
-	window_load(lane, slab, data, n, want + 32, w.pk_next, w.byte_next);
+	window_load(lane, slab, data, n, want + 32, w.meta_next, w.dist_next);
 }
 
-__device__ __forceinline__ uint64_t window_packet(const Window& w, uint32_t pos)
+__device__ __forceinline__ uint32_t window_meta(const Window& w, uint32_t pos)
 {
-	return __shfl_sync(FULL, w.pk, (int)(pos - w.base));
+	return __shfl_sync(FULL, w.meta, (int)(pos - w.base));
 }
-__device__ __forceinline__ uint32_t window_byte(const Window& w, uint32_t pos)
+__device__ __forceinline__ uint32_t window_dist(const Window& w, uint32_t pos)
 {
-	return __shfl_sync(FULL, w.byte, (int)(pos - w.base));
+	return __shfl_sync(FULL, w.dist, (int)(pos - w.base));
 }
 
 // Checkpoint traffic: one TMA bulk copy each way, issued by lane 0.
@@ -390,7 +421,7 @@ __device__ __forceinline__ void record_store(int lane, Record* rec, const Model&
 {
 	__syncwarp();
 	if (lane == 0) {
-		rec->probs[S_CTX] = (uint16_t)m.ctx;
+		rec->ctx = m.ctx;
 		rec->rep[0] = m.rep0;
 		rec->rep[1] = m.rep1;
 		rec->rep[2] = m.rep2;
@@ -418,7 +449,7 @@ __device__ __forceinline__ void record_load(int lane, Record* rec, Model& m, uin
 	}
 	parity ^= 1;
 	__syncwarp();
-	m.ctx = rec->probs[S_CTX];
+	m.ctx = rec->ctx;
 	m.rep0 = rec->rep[0];
 	m.rep1 = rec->rep[1];
 	m.rep2 = rec->rep[2];

@@ -16,7 +16,7 @@ struct WarpShared {
 	uint64_t bar;
 };
 struct CtaShared {
-	uint16_t price[2048];
+	uint32_t trans[4096];  // see code_bit()
 	uint32_t recip[RECIP_ENTRIES];
 	WarpShared warp[WARPS_PER_CTA];
 };
@@ -24,13 +24,13 @@ static_assert(sizeof(WarpShared) % 16 == 0, "per-warp shared block must keep the
 static_assert(offsetof(CtaShared, warp) % 16 == 0, "record alignment");
 
 struct Tables {
-	const uint16_t* price;  // [2048] floor(-log2(i/2048)*2048), reference generate_table.py:7-9
+	const uint32_t* trans;  // [4096] adapted probability | price << 16 (price: reference generate_table.py:7-9)
 	const uint32_t* recip;  // [RECIP_ENTRIES]
 };
 
 __device__ __forceinline__ void cta_tables_load(CtaShared* sh, const Tables& t)
 {
-	for (int i = threadIdx.x; i < 2048; i += blockDim.x) sh->price[i] = t.price[i];
+	for (int i = threadIdx.x; i < 4096; i += blockDim.x) sh->trans[i] = t.trans[i];
 	for (int i = threadIdx.x; i < (int)RECIP_ENTRIES; i += blockDim.x) sh->recip[i] = t.recip[i];
 	if ((threadIdx.x & 31) == 0) mbar_init(&sh->warp[threadIdx.x >> 5].bar, 1);
 	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -58,7 +58,7 @@ __device__ __forceinline__ bool packet_ok(const Model& m, uint32_t n, uint32_t t
 struct Tally {
 	uint64_t total;  // uniform: cost flushed so far
 	uint32_t acc;    // per lane: cost since the last flush
-	uint32_t packets, bits;
+	uint32_t packets, bits;  // bits: modelled bits in excess of 9 per packet (two's complement)
 };
 
 __device__ __forceinline__ void tally_flush(Tally& t)
@@ -67,42 +67,312 @@ __device__ __forceinline__ void tally_flush(Tally& t)
 	t.acc = 0;
 }
 
-// Prices slab packets from m.pos until `stop_pidx` packets or `stop_pos` bytes are reached.
-// Writes a checkpoint each time the walk crosses a multiple of `stride` when ck != nullptr
-// (ck indexed by slot-1, slot = pos / stride).
-__device__ __forceinline__ uint32_t walk_plain(int lane, uint16_t* probs, const uint16_t* price, Record* rec, Model& m,
-                                               Tally& t, Window& w, const uint64_t* __restrict__ slab,
-                                               const uint8_t* __restrict__ data, uint32_t n, uint32_t stop_pos,
-                                               uint32_t stop_pidx, Record* ck, uint32_t* ck_pos, uint32_t* ck_pidx,
-                                               uint32_t stride)
+// memcmp(data+pos-d-1, data+pos, len) == 0 across the warp (src/packet_slab_neighbour.c:74-80)
+__device__ __forceinline__ bool rep_matches(int lane, const uint8_t* __restrict__ data, uint32_t pos, uint32_t d,
+                                            uint32_t len)
 {
-	uint32_t next_ck = ck ? (m.pos / stride + 1) * stride : 0xffffffffu;
-	while (m.pos < stop_pos && m.pidx < stop_pidx) {
-		if ((m.pos & ~31u) != w.base) {
-			tally_flush(t);
-			window_seek(lane, w, slab, data, n, m.pos);
+	bool same = true;
+	const uint8_t* a = data + pos;
+	const uint8_t* b = data + (pos - d - 1);
+	for (uint32_t i = lane; i < len; i += 32) same = same && a[i] == b[i];
+	return __all_sync(FULL, same);
+}
+
+// ---- the accept/reject buffer of one proposal (replaces packet_slab_undo_stack) -------------------
+struct Edit {
+	uint32_t pos;
+	uint32_t pad;
+	uint64_t pk;
+};
+
+struct EditLog {
+	Edit* e;
+	uint32_t cap;
+	uint32_t stored;    // physical entries
+	uint32_t count;     // logical edits (what the reference's undo stack would hold)
+	uint32_t dup_pos;   // position whose entry may be rewritten (pos+1 of a shrink), or ~0
+	uint32_t dup_index;
+	bool overflow;
+};
+
+__device__ __forceinline__ void log_put(int lane, EditLog& lg, uint32_t pos, uint64_t pk)
+{
+	lg.count++;
+	if (pos == lg.dup_pos) {
+		if (lane == 0) lg.e[lg.dup_index].pk = pk;
+		return;
+	}
+	if (lg.stored >= lg.cap) {
+		lg.overflow = true;
+		return;
+	}
+	if (lane == 0) {
+		lg.e[lg.stored].pos = pos;
+		lg.e[lg.stored].pk = pk;
+	}
+	lg.stored++;
+}
+
+// ---- the walk ----------------------------------------------------------------------------------------
+// Everything a walking warp needs besides its registers.  Lane roles in the literal fast path:
+// lane 0 owns is_match[ctx], lanes 1..8 own literal-tree depth 0..7, lanes 9..31 adapt the
+// dummy slot (value 0 is a zero-price fixed point of the transition table), so the fast path
+// is branch-free across the warp.
+struct WalkEnv {
+	int lane;
+	uint16_t* probs;
+	const uint32_t* trans;
+	Record* rec;
+	const uint64_t* __restrict__ slab;
+	const uint8_t* __restrict__ data;
+	uint32_t n;
+	uint32_t trans_addr;  // shared address of trans[]
+	uint32_t lit_addr;    // shared address of this lane's first slot
+	uint32_t lit_sh;      // byte >> lit_sh = tree prefix at this lane's depth
+	uint32_t bitmask;     // 0x800 on tree lanes
+	uint32_t ctxmask;     // ~0 on lane 0
+	uint32_t treemask;    // ~0 on tree lanes
+};
+
+__device__ __forceinline__ WalkEnv make_env(int lane, WarpShared* ws, const CtaShared* sh, const uint64_t* slab,
+                                            const uint8_t* data, uint32_t n)
+{
+	WalkEnv e;
+	e.lane = lane;
+	e.probs = ws->rec.probs;
+	e.trans = sh->trans;
+	e.rec = &ws->rec;
+	e.slab = slab;
+	e.data = data;
+	e.n = n;
+	e.trans_addr = smem_u32(sh->trans);
+	const bool tree = lane >= 1 && lane <= 8;
+	const uint32_t first = lane == 0 ? S_ISMATCH : tree ? S_LIT + (1u << (lane - 1)) : S_DUMMY;
+	e.lit_addr = smem_u32(ws->rec.probs) + 2 * first;
+	e.lit_sh = tree ? 9u - (uint32_t)lane : 8u;
+	e.bitmask = tree ? 0x800u : 0u;
+	e.ctxmask = lane == 0 ? 0xffffffffu : 0u;
+	e.treemask = tree ? 0xffffffffu : 0u;
+	return e;
+}
+
+// Where checkpoints of the walk go (all null when the walk writes none)
+struct CkSink {
+	Record* ck;          // indexed by slot-1
+	uint32_t* ck_pos;    // optional
+	uint32_t* ck_pidx;   // optional
+	const uint8_t* live; // anneal: which of the two buffers is current per slot-1 (write the other); null = buffer 0
+	uint32_t nck;        // anneal: records per buffer
+	uint32_t stride;
+	uint32_t next;       // next position that triggers a checkpoint
+	uint32_t written;    // count, for stats
+};
+
+// The state a walk keeps in registers.  The rep distances stay in e.rec->rep[] (shared memory):
+// only matches touch them, and keeping them out of the register loop keeps the literal path tight.
+struct Walker {
+	uint32_t pos;
+	uint32_t delta;  // pos - packet index: constant across single-byte packets
+	uint32_t ctx;
+	uint32_t mb;     // data[pos - rep0 - 1], valid whenever ctx >= 7 (fetched right after a non-literal packet)
+	Tally t;
+	Window w;
+};
+
+__device__ __forceinline__ uint32_t walker_pidx(const Walker& k) { return k.pos - k.delta; }
+
+__device__ __forceinline__ Model walker_model(const WalkEnv& e, const Walker& k)
+{
+	Model m;
+	m.pos = k.pos;
+	m.pidx = k.pos - k.delta;
+	m.ctx = k.ctx;
+	m.rep0 = e.rec->rep[0];
+	m.rep1 = e.rec->rep[1];
+	m.rep2 = e.rec->rep[2];
+	m.rep3 = e.rec->rep[3];
+	return m;
+}
+
+__device__ __forceinline__ void walker_fetch_mb(const WalkEnv& e, Walker& k)
+{
+	const uint32_t rep0 = e.rec->rep[0];
+	k.mb = (k.pos < e.n && rep0 < k.pos) ? e.data[k.pos - rep0 - 1] : 0;
+}
+
+__device__ __forceinline__ void walker_init(const WalkEnv& e, Walker& k)
+{
+	Model m;
+	model_init(e.lane, e.probs, m);
+	if (e.lane < 4) e.rec->rep[e.lane] = 0;
+	if (e.lane == 0) e.probs[S_DUMMY] = 0;
+	__syncwarp();
+	k.pos = k.delta = k.ctx = k.mb = 0;
+	k.t = {0, 0, 0, 0};
+	k.w.base = WINDOW_NONE;
+}
+
+__device__ __forceinline__ void walker_load(const WalkEnv& e, Walker& k, const Record* src, uint64_t* bar, uint32_t& parity)
+{
+	Model m;
+	uint64_t cost;
+	record_load(e.lane, e.rec, m, cost, src, bar, parity);
+	k.pos = m.pos;
+	k.delta = m.pos - m.pidx;
+	k.ctx = m.ctx;
+	k.t = {cost, 0, 0, 0};
+	k.w.base = WINDOW_NONE;
+	k.mb = 0;
+	if (k.ctx >= 7) walker_fetch_mb(e, k);
+}
+
+// Generic (any packet type) price + adapt: the slow path of the walk.
+__device__ __forceinline__ void walker_apply(const WalkEnv& e, Walker& k, Model& m, uint32_t type, uint32_t len,
+                                             uint32_t dist, uint32_t byte)
+{
+	k.t.bits += apply_packet(e.lane, e.probs, e.trans, m, type, len, dist, byte, k.mb, k.t.acc) - 9u;
+	k.pos = m.pos;
+	k.delta = m.pos - m.pidx;
+	k.ctx = m.ctx;
+	if (type == T_MATCH || type == T_LONG_REP) {
+		// every lane holds the same values; each writes them so that it can read them back unsynchronised
+		e.rec->rep[0] = m.rep0;
+		e.rec->rep[1] = m.rep1;
+		e.rec->rep[2] = m.rep2;
+		e.rec->rep[3] = m.rep3;
+	}
+	if (type != T_LITERAL) walker_fetch_mb(e, k);
+}
+
+__device__ __forceinline__ void walker_store(const WalkEnv& e, const Walker& k, Record* dst)
+{
+	const Model m = walker_model(e, k);
+	record_store(e.lane, e.rec, m, k.t.total, dst);
+}
+
+__device__ __forceinline__ void walker_checkpoint(const WalkEnv& e, Walker& k, CkSink& ck)
+{
+	tally_flush(k.t);
+	const uint32_t slot = k.pos / ck.stride;
+	const uint32_t buf = ck.live ? (ck.live[slot - 1] ^ 1u) : 0u;
+	walker_store(e, k, ck.ck + (size_t)buf * ck.nck + (slot - 1));
+	if (e.lane == 0) {
+		if (ck.ck_pos) ck.ck_pos[(size_t)buf * ck.nck + (slot - 1)] = k.pos;
+		if (ck.ck_pidx) ck.ck_pidx[(size_t)buf * ck.nck + (slot - 1)] = walker_pidx(k);
+	}
+	ck.next = (slot + 1) * ck.stride;
+	ck.written++;
+}
+
+enum WalkMode { WALK_PLAIN = 0, WALK_REPAIR_HEAD = 1, WALK_REPAIR = 2 };
+enum WalkResult { WALK_DONE = 0, WALK_NEED_FIND = 1, WALK_ERROR = 2 };
+
+// Prices packets from k.pos until stop_pos bytes or packet index stop_pidx is reached.
+//   WALK_PLAIN        the slab as it is (neighbour.c:22-32, main.c:116-118)
+//   WALK_REPAIR_HEAD  repair rules for the first three packets after a mutation (neighbour.c:82-98)
+//   WALK_REPAIR       repair rules from the fourth packet on: a LITERAL slot can no longer change
+//                     there, so literals take the same fast path as in WALK_PLAIN
+// Returns WALK_NEED_FIND with `pending` = the failed LONG_REP (index forced to 3, neighbour.c:99-108)
+// when the caller has to pick a replacement from the top-k at k.pos.
+// k.t.bits only accumulates the EXCESS over 9 bits per packet; see walker_bits().
+template <int MODE, bool CKPT>
+__device__ __forceinline__ uint32_t walk(const WalkEnv& e, Walker& k, uint32_t stop_pos, uint32_t stop_pidx, CkSink& ck,
+                                         EditLog* lg, uint32_t override_pos, uint64_t override_pk, uint64_t& pending,
+                                         uint64_t& pending_old, uint32_t& err)
+{
+	for (;;) {
+		if (k.pos >= stop_pos || k.pos - k.delta == stop_pidx) return WALK_DONE;
+		if (CKPT && k.pos >= ck.next) walker_checkpoint(e, k, ck);
+		if (k.pos - k.w.base >= 32u) {
+			tally_flush(k.t);
+			window_seek(e.lane, k.w, e.slab, e.data, e.n, k.pos);
 		}
-		const uint64_t pk = window_packet(w, m.pos);
-		const uint32_t byte = window_byte(w, m.pos);
-		const uint32_t type = pk_type(pk), len = pk_len(pk), dist = pk_dist(pk);
-		if (!packet_ok(m, n, type, len, dist)) return ERR_BAD_PACKET;
-		uint32_t mbyte = 0;
-		if (type == T_LITERAL && m.ctx >= 7) mbyte = data[m.pos - m.rep0 - 1];
-		t.bits += apply_packet(lane, probs, price, m, type, len, dist, byte, mbyte, t.acc);
-		t.packets++;
-		if (m.pos >= next_ck && m.pos < n) {
-			tally_flush(t);
-			const uint32_t slot = m.pos / stride;
-			record_store(lane, rec, m, t.total, ck + (slot - 1));
-			if (lane == 0) {
-				if (ck_pos) ck_pos[slot - 1] = m.pos;
-				if (ck_pidx) ck_pidx[slot - 1] = m.pidx;
+		uint32_t limit = k.w.base + 32 < stop_pos ? k.w.base + 32 : stop_pos;
+		if (CKPT) limit = ck.next < limit ? ck.next : limit;
+		if (stop_pidx != 0xffffffffu) {
+			// the packet index only drifts from the position on multi-byte packets (slow path)
+			const uint32_t stop_at = stop_pidx + k.delta;
+			limit = stop_at < limit ? stop_at : limit;
+		}
+		while (k.pos < limit) {
+			const uint32_t meta = window_meta(k.w, k.pos);
+			if (MODE != WALK_REPAIR_HEAD && (meta & 0xffffu) == META_LITERAL) {
+				// ---- literal fast path, branch-free across lanes ----------------------------------
+				const uint32_t byte = meta >> 16;
+				const uint32_t top = byte >> e.lit_sh;
+				const uint32_t bit11 = (byte << (12 - e.lit_sh)) & e.bitmask;
+				const uint32_t ctx = k.ctx;
+				uint32_t off = top + (ctx & e.ctxmask);
+				if (ctx >= 7) {
+					// matched literal (lzma_packet_encoder.c:123-130): the tree follows the match
+					// byte for as long as the prefixes agree
+					const uint32_t extra = (0x100u + ((k.mb << (9 - e.lit_sh)) & 0x100u)) & e.treemask;
+					if ((k.mb >> e.lit_sh) == top) off += extra;
+					k.ctx = ctx < 10 ? ctx - 3 : ctx - 6;
+				} else {
+					k.ctx = ctx < 4 ? 0 : ctx - 3;
+				}
+				const uint32_t addr = e.lit_addr + 2 * off;
+				const uint32_t tr = lds_u32(e.trans_addr + ((lds_u16(addr) | bit11) << 2));
+				sts_u16(addr, tr);
+				k.t.acc += tr >> 16;
+				k.pos++;
+				continue;
 			}
-			next_ck = (slot + 1) * stride;
+			// ---- every other packet ---------------------------------------------------------------
+			Model m = walker_model(e, k);
+			uint32_t type = meta_type(meta), len = meta_len(meta), dist = 0;
+			const uint32_t byte = meta_byte(meta) & 0xff;
+			if (type == T_MATCH || type == T_LONG_REP) dist = window_dist(k.w, k.pos);
+			if (MODE == WALK_REPAIR_HEAD && k.pos == override_pos) {
+				type = pk_type(override_pk);
+				len = pk_len(override_pk);
+				dist = pk_dist(override_pk);
+			}
+			if (MODE != WALK_PLAIN) {
+				const uint64_t old = pk_pack(type, dist, len);
+				if (type == T_SHORT_REP || type == T_LITERAL) {
+					const uint32_t rep_byte = (m.rep0 < m.pos) ? e.data[m.pos - m.rep0 - 1] : 0x100u;
+					if (byte == rep_byte) {
+						if (MODE == WALK_REPAIR_HEAD) type = T_SHORT_REP;  // only the first three packets convert
+					} else {
+						type = T_LITERAL;
+					}
+					dist = 0;
+					len = 1;
+				} else if (type == T_LONG_REP) {
+					if (len < 2 || len > e.n - m.pos || dist > 3) {
+						err = ERR_BAD_PACKET;
+						return WALK_ERROR;
+					}
+					bool good = model_rep(m, dist) < m.pos && rep_matches(e.lane, e.data, m.pos, model_rep(m, dist), len);
+					for (uint32_t idx = 0; idx < 4 && !good; idx++) {
+						dist = idx;
+						good = model_rep(m, dist) < m.pos && rep_matches(e.lane, e.data, m.pos, model_rep(m, dist), len);
+					}
+					if (!good) {
+						pending = pk_pack(T_LONG_REP, dist, len);
+						pending_old = old;
+						return WALK_NEED_FIND;
+					}
+				}
+				const uint64_t now = pk_pack(type, dist, len);
+				if (now != old) log_put(e.lane, *lg, m.pos, now);
+			}
+			if (!packet_ok(m, e.n, type, len, dist)) {
+				err = ERR_BAD_PACKET;
+				return WALK_ERROR;
+			}
+			walker_apply(e, k, m, type, len, dist, byte);
+			break;  // the packet index may have drifted: recompute the limits
 		}
 	}
-	tally_flush(t);
-	return 0;
+}
+
+// modelled bits priced since packet index pidx_from (fast-path literals count 9 each)
+__device__ __forceinline__ uint64_t walker_bits(const Walker& k, uint32_t pidx_from)
+{
+	return (uint64_t)(walker_pidx(k) - pidx_from) * 9 + (int64_t)(int32_t)k.t.bits;
 }
 
 // ---- K3a: score whole slabs ---------------------------------------------------------------------
@@ -119,6 +389,7 @@ struct ScoreArgs {
 	uint32_t* ck_pos;        // [nslabs][nslots-1] or null
 	uint32_t* ck_pidx;       // [nslabs][nslots-1] or null
 	uint32_t stride, nslots;
+	uint32_t ck_chain_stride;  // records between consecutive slabs' checkpoint blocks
 	Record* final_model;     // [nslabs] model after the walk, or null
 	Tables tables;
 };
@@ -132,20 +403,31 @@ __global__ void __launch_bounds__(CTA_THREADS) score_kernel(ScoreArgs a)
 	const uint32_t s = blockIdx.x * WARPS_PER_CTA + warp;
 	if (s >= a.nslabs) return;
 	WarpShared* ws = &sh->warp[warp];
-	Model m;
-	model_init(lane, ws->rec.probs, m);
-	Tally t = {0, 0, 0, 0};
-	Window w;
-	w.base = 0xffffffffu;
-	const size_t ckoff = (size_t)s * (a.nslots - 1);
-	uint32_t err = walk_plain(lane, ws->rec.probs, sh->price, &ws->rec, m, t, w, a.slabs + (size_t)s * a.n, a.data, a.n,
-	                          a.stop_pos, 0xffffffffu, a.ck ? a.ck + ckoff : nullptr,
-	                          a.ck_pos ? a.ck_pos + ckoff : nullptr, a.ck_pidx ? a.ck_pidx + ckoff : nullptr, a.stride);
-	if (!err && m.pos != a.stop_pos) err = ERR_NOT_BOUNDARY;
-	if (a.final_model) record_store(lane, &ws->rec, m, t.total, a.final_model + s);
+	const WalkEnv e = make_env(lane, ws, sh, a.slabs + (size_t)s * a.n, a.data, a.n);
+	Walker k;
+	walker_init(e, k);
+	const size_t ckoff = (size_t)s * a.ck_chain_stride;
+	CkSink ck;
+	ck.ck = a.ck ? a.ck + ckoff : nullptr;
+	ck.ck_pos = a.ck_pos ? a.ck_pos + ckoff : nullptr;
+	ck.ck_pidx = a.ck_pidx ? a.ck_pidx + ckoff : nullptr;
+	ck.live = nullptr;
+	ck.nck = 0;
+	ck.stride = a.stride;
+	ck.next = a.stride;
+	ck.written = 0;
+	uint64_t pending = 0, pending_old = 0;
+	uint32_t err = 0;
+	if (a.ck)
+		walk<WALK_PLAIN, true>(e, k, a.stop_pos, 0xffffffffu, ck, nullptr, 0xffffffffu, 0, pending, pending_old, err);
+	else
+		walk<WALK_PLAIN, false>(e, k, a.stop_pos, 0xffffffffu, ck, nullptr, 0xffffffffu, 0, pending, pending_old, err);
+	tally_flush(k.t);
+	if (!err && k.pos != a.stop_pos) err = ERR_NOT_BOUNDARY;
+	if (a.final_model) walker_store(e, k, a.final_model + s);
 	if (lane == 0) {
-		a.out_cost[s] = t.total;
-		if (a.out_count) a.out_count[s] = m.pidx;
+		a.out_cost[s] = k.t.total;
+		if (a.out_count) a.out_count[s] = walker_pidx(k);
 		a.out_err[s] = err;
 	}
 }
@@ -178,43 +460,41 @@ __global__ void __launch_bounds__(CTA_THREADS) topk_kernel(TopkArgs a)
 	cta_tables_load(sh, a.tables);
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	WarpShared* ws = &sh->warp[warp];
+	const WalkEnv e = make_env(lane, ws, sh, a.slab, a.data, a.n);
 	uint32_t parity = 0;
-	uint32_t cand = 0;
+	unsigned long long cand = 0;
 	for (uint32_t q = blockIdx.x * WARPS_PER_CTA + warp; q < a.npos; q += gridDim.x * WARPS_PER_CTA) {
 		const uint32_t qpos = a.positions[q];
-		Model m;
+		Walker k;
 		uint32_t err = 0;
 		if (qpos >= a.n) {
 			err = ERR_NOT_BOUNDARY;
 		} else if (a.state_mode == 0) {
-			model_init(lane, ws->rec.probs, m);
-			m.pos = qpos;
+			walker_init(e, k);
+			k.pos = k.delta = qpos;
 		} else {
 			// last checkpoint at or before the query
 			uint32_t below = 0;
 			for (uint32_t j = lane; j + 1 < a.nslots; j += 32) below += a.ck_pos[j] <= qpos ? 1u : 0u;
 			below = __reduce_add_sync(FULL, below);
-			uint64_t cost = 0;
 			if (below == 0)
-				model_init(lane, ws->rec.probs, m);
+				walker_init(e, k);
 			else
-				record_load(lane, &ws->rec, m, cost, a.ck + (below - 1), &ws->bar, parity);
-			Tally t = {cost, 0, 0, 0};
-			Window w;
-			w.base = 0xffffffffu;
-			err = walk_plain(lane, ws->rec.probs, sh->price, &ws->rec, m, t, w, a.slab, a.data, a.n, qpos, 0xffffffffu,
-			                 nullptr, nullptr, nullptr, a.stride);
-			if (!err && m.pos != qpos) err = ERR_NOT_BOUNDARY;
+				walker_load(e, k, a.ck + (below - 1), &ws->bar, parity);
+			CkSink ck = {};
+			uint64_t pending = 0, pending_old = 0;
+			walk<WALK_PLAIN, false>(e, k, qpos, 0xffffffffu, ck, nullptr, 0xffffffffu, 0, pending, pending_old, err);
+			if (!err && k.pos != qpos) err = ERR_NOT_BOUNDARY;
 		}
 		uint32_t pops = 0;
 		if (!err) {
-			pops = warp_find(lane, ws->rec.probs, sh->price, sh->recip, &ws->fs, a.data, a.n, a.occ_start, a.occ, m,
-			                 a.slab[qpos], a.k);
+			pops = warp_find(lane, e.probs, sh->trans, sh->recip, &ws->fs, a.data, a.n, a.occ_start, a.occ,
+			                 walker_model(e, k), a.slab[qpos], a.k);
 			cand += ws->fs.candidates;
 			for (uint32_t i = lane; i < pops; i += 32) {
-				const uint32_t e = ws->fs.pop_order[i];
-				a.out_pk[(size_t)q * a.k + i] = ws->fs.ent_pk[e];
-				a.out_price[(size_t)q * a.k + i] = ws->fs.ent_price[e];
+				const uint32_t en = ws->fs.pop_order[i];
+				a.out_pk[(size_t)q * a.k + i] = ws->fs.ent_pk[en];
+				a.out_price[(size_t)q * a.k + i] = ws->fs.ent_price[en];
 			}
 		}
 		if (lane == 0) {
@@ -223,22 +503,18 @@ __global__ void __launch_bounds__(CTA_THREADS) topk_kernel(TopkArgs a)
 		}
 		__syncwarp();
 	}
-	if (lane == 0 && cand) atomicAdd(a.candidates, (unsigned long long)cand);
+	if (lane == 0 && cand) atomicAdd(a.candidates, cand);
 }
 
 // ---- K3/K4: the annealing loop ---------------------------------------------------------------------
-struct Edit {
-	uint32_t pos;
-	uint32_t pad;
-	uint64_t pk;
-};
-
 struct ChainState {
 	uint64_t rng;
 	uint64_t cur_cost;
 	uint64_t best_cost;
 	uint32_t live_count;
 	uint32_t err;
+	uint32_t eval_index;  // successful evaluations since the chain's slab was last set
+	uint32_t pad;
 };
 
 struct ChainStats {
@@ -272,68 +548,14 @@ struct AnnealArgs {
 	uint32_t* attempts_out;  // [chains]
 	// run parameters
 	uint32_t evals, max_attempts, schedule, step, num_iters, first_eval;
+	unsigned long long packet_budget;
 	const float* temps;
 };
 
-// memcmp(data+pos-d-1, data+pos, len) == 0 across the warp (src/packet_slab_neighbour.c:74-80)
-__device__ __forceinline__ bool rep_matches(int lane, const uint8_t* __restrict__ data, uint32_t pos, uint32_t d,
-                                            uint32_t len)
-{
-	bool same = true;
-	const uint8_t* a = data + pos;
-	const uint8_t* b = data + (pos - d - 1);
-	for (uint32_t i = lane; i < len; i += 32) same = same && a[i] == b[i];
-	return __all_sync(FULL, same);
-}
-
-struct EditLog {
-	Edit* e;
-	uint32_t cap;
-	uint32_t stored;    // physical entries
-	uint32_t count;     // logical edits (what the reference's undo stack would hold)
-	uint32_t dup_pos;   // position whose entry may be rewritten (pos+1 of a shrink), or ~0
-	uint32_t dup_index;
-	bool overflow;
-};
-
-__device__ __forceinline__ void log_put(int lane, EditLog& lg, uint32_t pos, uint64_t pk)
-{
-	lg.count++;
-	if (pos == lg.dup_pos) {
-		if (lane == 0) lg.e[lg.dup_index].pk = pk;
-		return;
-	}
-	if (lg.stored >= lg.cap) {
-		lg.overflow = true;
-		return;
-	}
-	if (lane == 0) {
-		lg.e[lg.stored].pos = pos;
-		lg.e[lg.stored].pk = pk;
-	}
-	lg.stored++;
-}
-
-// src/packet_slab_neighbour.c:48-72.  Returns false when the finder has no alternative.
-__device__ __forceinline__ bool pick_from_topk(int lane, WarpShared* ws, const CtaShared* sh, const AnnealArgs& a,
-                                               const Model& m, uint64_t excluded, bool best, uint64_t& rng,
-                                               uint64_t& chosen, unsigned long long& cand)
-{
-	const uint32_t count =
-	    warp_find(lane, ws->rec.probs, sh->price, sh->recip, &ws->fs, a.data, a.n, a.occ_start, a.occ, m, excluded, a.k);
-	cand += ws->fs.candidates;
-	if (count == 0) return false;
-	uint32_t choice = rng31(rng) % count;
-	for (int i = 1; i < 8; i++) {
-		const uint32_t c = rng31(rng) % count;
-		choice = c > choice ? c : choice;
-	}
-	if (rng31(rng) % 8 == 0 || best) choice = count - 1;
-	chosen = ws->fs.ent_pk[ws->fs.pop_order[choice]];
-	return true;
-}
-
-__global__ void __launch_bounds__(CTA_THREADS) anneal_kernel(AnnealArgs a)
+#ifndef MG_ANNEAL_MIN_CTAS
+#define MG_ANNEAL_MIN_CTAS 2
+#endif
+__global__ void __launch_bounds__(CTA_THREADS, MG_ANNEAL_MIN_CTAS) anneal_kernel(AnnealArgs a)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	CtaShared* sh = reinterpret_cast<CtaShared*>(smem_raw);
@@ -342,13 +564,10 @@ __global__ void __launch_bounds__(CTA_THREADS) anneal_kernel(AnnealArgs a)
 	const uint32_t c = blockIdx.x * WARPS_PER_CTA + warp;
 	if (c >= a.chains) return;
 	WarpShared* ws = &sh->warp[warp];
-	uint16_t* probs = ws->rec.probs;
-	const uint16_t* price = sh->price;
-	const uint8_t* __restrict__ data = a.data;
 	const uint32_t n = a.n, nck = a.nslots - 1;
-
 	uint64_t* slab = a.slabs + (size_t)c * n;
-	Record* ck = a.ck + (size_t)c * 2 * nck;
+	const WalkEnv e = make_env(lane, ws, sh, slab, a.data, n);
+	Record* ck_base = a.ck + (size_t)c * 2 * nck;
 	uint32_t* ck_pidx = a.ck_pidx + (size_t)c * 2 * nck;
 	uint8_t* ck_live = a.ck_live + (size_t)c * nck;
 	ChainState st = a.state[c];
@@ -361,7 +580,9 @@ __global__ void __launch_bounds__(CTA_THREADS) anneal_kernel(AnnealArgs a)
 	const float temp = a.temps ? a.temps[c] : 0.f;
 
 	uint32_t done = 0, attempts = 0;
-	while (done < a.evals && attempts < a.max_attempts && st.err == 0) {
+	const uint32_t first_eval = a.first_eval == 0xffffffffu ? st.eval_index : a.first_eval;
+	while (done < a.evals && attempts < a.max_attempts && st.err == 0 &&
+	       (a.packet_budget == 0 || cs.packets < a.packet_budget)) {
 		attempts++;
 		lg.stored = lg.count = 0;
 		lg.dup_pos = 0xffffffffu;
@@ -373,35 +594,49 @@ __global__ void __launch_bounds__(CTA_THREADS) anneal_kernel(AnnealArgs a)
 		uint32_t below = 0;
 		for (uint32_t j = lane; j < nck; j += 32) below += ck_pidx[(size_t)ck_live[j] * nck + j] <= target ? 1u : 0u;
 		const uint32_t j0 = __reduce_add_sync(FULL, below);  // checkpoint slot to resume from (0 = start of file)
-		Model m;
-		Tally t = {0, 0, 0, 0};
+		Walker k;
 		if (j0 == 0) {
-			model_init(lane, probs, m);
+			walker_init(e, k);
 		} else {
-			record_load(lane, &ws->rec, m, t.total, ck + (size_t)ck_live[j0 - 1] * nck + (j0 - 1), &ws->bar, parity);
+			walker_load(e, k, ck_base + (size_t)ck_live[j0 - 1] * nck + (j0 - 1), &ws->bar, parity);
 			cs.ck_bytes += sizeof(Record);
 		}
-		Window w;
-		w.base = 0xffffffffu;
-		const uint32_t start_pos = m.pos;
+		const uint32_t start_pos = k.pos, start_pidx = walker_pidx(k);
+		CkSink ck;
+		ck.ck = ck_base;
+		ck.ck_pos = nullptr;
+		ck.ck_pidx = ck_pidx;
+		ck.live = ck_live;
+		ck.nck = nck;
+		ck.stride = a.stride;
+		ck.next = (j0 + 1) * a.stride;
+		ck.written = 0;
+		uint64_t pending = 0, pending_old = 0;
+		uint32_t err = 0;
 
 		// ---- prefix: neighbour.c:22-32 from the checkpoint instead of from byte 0 ----------
-		uint32_t err = walk_plain(lane, probs, price, &ws->rec, m, t, w, slab, data, n, n, target, nullptr, nullptr,
-		                          nullptr, a.stride);
-		if (err || m.pos >= n) {
+		walk<WALK_PLAIN, false>(e, k, n, target, ck, nullptr, 0xffffffffu, 0, pending, pending_old, err);
+		if (err || k.pos >= n) {
 			st.err = err ? err : ERR_NOT_BOUNDARY;
 			break;
 		}
 
 		// ---- mutate: neighbour.c:119-152 ---------------------------------------------------
-		const uint32_t pos = m.pos;
-		if ((pos & ~31u) != w.base) window_seek(lane, w, slab, data, n, pos);
-		const uint64_t first = window_packet(w, pos);
-		const uint32_t byte0 = window_byte(w, pos);
+		const uint32_t pos = k.pos;
+		if (pos - k.w.base >= 32u) {
+			tally_flush(k.t);
+			window_seek(lane, k.w, slab, a.data, n, pos);
+		}
+		const uint32_t meta0 = window_meta(k.w, pos);
+		const uint32_t dist0 = window_dist(k.w, pos);
+		const uint64_t first = pk_pack(meta_type(meta0), dist0, meta_len(meta0));
+		const uint32_t byte0 = meta_byte(meta0) & 0xff;
 		uint64_t newpk = 0;
 		uint64_t override_pk = 0;
 		uint32_t override_pos = 0xffffffffu;
-		bool mutated = false;
+		// what the single find site below is asked to do: 0 nothing, 1 mutation pick, 2 repair pick
+		uint32_t want_find = 1;
+		bool pick_best = false;
 		if (pos + 1 < n && rng31(rng) % 2 == 0) {
 			const uint64_t second = slab[pos + 1];
 			const uint32_t ft = pk_type(first), flen = pk_len(first);
@@ -414,113 +649,106 @@ __global__ void __launch_bounds__(CTA_THREADS) anneal_kernel(AnnealArgs a)
 				lg.dup_index = lg.stored;
 				log_put(lane, lg, pos + 1, override_pk);
 				lg.dup_pos = pos + 1;  // a later repair of this slot rewrites the entry in place
-				mutated = true;
+				want_find = 0;
 			} else if ((ft == T_LITERAL || ft == T_SHORT_REP) && (stype == T_MATCH || stype == T_LONG_REP)) {
-				const int64_t src = (int64_t)pos - (int64_t)(stype == T_LONG_REP ? model_rep(m, sdist & 3) : sdist);
-				if (slen < MAX_MATCH && src > 0 && byte0 == data[src - 1]) {
+				const int64_t src = (int64_t)pos - (int64_t)(stype == T_LONG_REP ? model_rep(walker_model(e, k), sdist & 3) : sdist);
+				if (slen < MAX_MATCH && src > 0 && byte0 == a.data[src - 1]) {
 					newpk = pk_pack(stype, sdist, slen + 1);
 					log_put(lane, lg, pos, newpk);
-					mutated = true;
+					want_find = 0;
 				}
 			}
 		}
-		bool ok = true;
-		if (!mutated) {
-			cs.finds++;
-			ok = pick_from_topk(lane, ws, sh, a, m, first, false, rng, newpk, cs.candidates);
-			if (ok) log_put(lane, lg, pos, newpk);
+
+		// ---- the proposal body: at most one find per pass, walks in between -------------------
+		uint64_t excluded = first;
+		uint32_t phase = 0;  // 0: mutated packet pending, 1: repair head, 2: repair tail, 3: done
+		uint32_t head_stop = 0;
+		bool failed = false;
+		while (phase < 3) {
+			if (want_find) {
+				cs.finds++;
+				const uint32_t count = warp_find(lane, e.probs, sh->trans, sh->recip, &ws->fs, a.data, n, a.occ_start, a.occ,
+				                                 walker_model(e, k), excluded, a.k);
+				cs.candidates += ws->fs.candidates;
+				uint64_t chosen = 0;
+				bool have = false;
+				if (count != 0) {
+					// neighbour.c:48-72
+					uint32_t choice = rng31(rng) % count;
+					for (int i = 1; i < 8; i++) {
+						const uint32_t r = rng31(rng) % count;
+						choice = r > choice ? r : choice;
+					}
+					if (rng31(rng) % 8 == 0 || pick_best) choice = count - 1;
+					chosen = ws->fs.ent_pk[ws->fs.pop_order[choice]];
+					have = true;
+				}
+				if (want_find == 1) {
+					if (!have) {
+						failed = true;  // no alternative at this position: not an evaluation (main.c:81-84)
+						break;
+					}
+					newpk = chosen;
+					log_put(lane, lg, pos, newpk);
+				} else {
+					// repair pick: the slot keeps the forced LONG_REP(3) if the finder is empty
+					const uint64_t now = have ? chosen : pending;
+					if (now != pending_old) log_put(lane, lg, k.pos, now);
+					newpk = now;
+				}
+				want_find = 0;
+			}
+			if (phase == 0 || newpk != 0) {
+				// price a packet chosen outside the walk: the mutated one or a repair pick
+				const uint32_t type = pk_type(newpk), len = pk_len(newpk), dist = pk_dist(newpk);
+				Model m = walker_model(e, k);
+				if (!packet_ok(m, n, type, len, dist)) {
+					st.err = ERR_BAD_PACKET;
+					break;
+				}
+				if (k.pos >= ck.next) walker_checkpoint(e, k, ck);
+				const uint32_t byte = phase == 0 ? byte0 : a.data[k.pos];
+				walker_apply(e, k, m, type, len, dist, byte);
+				newpk = 0;
+				if (phase == 0) {
+					phase = 1;
+					head_stop = walker_pidx(k) + 3;
+				}
+			}
+			uint32_t res;
+			if (phase == 1) {
+				res = walk<WALK_REPAIR_HEAD, true>(e, k, n, head_stop, ck, &lg, override_pos, override_pk, pending, pending_old, err);
+				if (res == WALK_DONE) {
+					phase = 2;
+					continue;
+				}
+			} else {
+				res = walk<WALK_REPAIR, true>(e, k, n, 0xffffffffu, ck, &lg, 0xffffffffu, 0, pending, pending_old, err);
+				if (res == WALK_DONE) phase = 3;
+			}
+			if (res == WALK_NEED_FIND) {
+				pick_best = rng31(rng) % 4 == 0;  // neighbour.c:107
+				excluded = pending;
+				want_find = 2;
+			} else if (res == WALK_ERROR) {
+				st.err = err;
+				break;
+			}
 		}
-		if (!ok) {
-			// no alternative at this position: not an evaluation (main.c:81-84)
+		if (st.err) break;
+		tally_flush(k.t);
+		cs.packets += walker_pidx(k) - start_pidx;
+		cs.bits += walker_bits(k, start_pidx);
+		cs.slab_bytes += (uint64_t)(k.pos - start_pos) * 9;
+		cs.ck_bytes += (uint64_t)ck.written * sizeof(Record);
+		if (failed) {
 			if (a.trace && attempts <= a.trace_cap && lane == 0) {
 				TraceRec r = {0, 0, 0};
 				a.trace[(size_t)c * a.trace_cap + attempts - 1] = r;
 			}
-			cs.packets += t.packets;
-			cs.bits += t.bits;
-			cs.slab_bytes += (uint64_t)(m.pos - start_pos) * 9;
 			continue;
 		}
-
-		// ---- price the mutated packet (neighbour.c:169) ------------------------------------
-		{
-			const uint32_t type = pk_type(newpk), len = pk_len(newpk), dist = pk_dist(newpk);
-			if (!packet_ok(m, n, type, len, dist)) {
-				st.err = ERR_BAD_PACKET;
-				break;
-			}
-			uint32_t mbyte = 0;
-			if (type == T_LITERAL && m.ctx >= 7) mbyte = data[m.pos - m.rep0 - 1];
-			t.bits += apply_packet(lane, probs, price, m, type, len, dist, byte0, mbyte, t.acc);
-			t.packets++;
-		}
-
-		// ---- repair + price the rest (neighbour.c:82-117), checkpointing as we go ------------
-		uint32_t next_ck = (j0 + 1) * a.stride;
-		uint32_t seen = 0;
-		while (m.pos < n) {
-			seen++;
-			if ((m.pos & ~31u) != w.base) {
-				tally_flush(t);
-				window_seek(lane, w, slab, data, n, m.pos);
-			}
-			// a checkpoint belongs to the boundary reached before this packet is touched
-			if (m.pos >= next_ck) {
-				tally_flush(t);
-				const uint32_t slot = m.pos / a.stride;
-				const uint32_t buf = ck_live[slot - 1] ^ 1u;
-				record_store(lane, &ws->rec, m, t.total, ck + (size_t)buf * nck + (slot - 1));
-				if (lane == 0) ck_pidx[(size_t)buf * nck + (slot - 1)] = m.pidx;
-				cs.ck_bytes += sizeof(Record);
-				next_ck = (slot + 1) * a.stride;
-			}
-			const uint64_t old = m.pos == override_pos ? override_pk : window_packet(w, m.pos);
-			const uint32_t byte = window_byte(w, m.pos);
-			uint64_t pk = old;
-			uint32_t type = pk_type(pk);
-			const uint32_t rep_byte = data[m.pos - m.rep0 - 1];
-			if (type == T_SHORT_REP || type == T_LITERAL) {
-				if (byte == rep_byte) {
-					if (seen < 4) pk = PK_SHORT_REP;
-				} else {
-					pk = PK_LITERAL;
-				}
-			} else if (type == T_LONG_REP) {
-				const uint32_t len = pk_len(pk);
-				uint32_t idx_now = pk_dist(pk);
-				if (len > n - m.pos || idx_now > 3) {
-					st.err = ERR_BAD_PACKET;
-					break;
-				}
-				bool good = rep_matches(lane, data, m.pos, model_rep(m, idx_now), len);
-				for (uint32_t idx = 0; idx < 4 && !good; idx++) {
-					idx_now = idx;
-					good = rep_matches(lane, data, m.pos, model_rep(m, idx_now), len);
-				}
-				pk = pk_pack(T_LONG_REP, idx_now, len);
-				if (!good) {
-					const bool best = rng31(rng) % 4 == 0;
-					cs.finds++;
-					uint64_t chosen = pk;
-					pick_from_topk(lane, ws, sh, a, m, pk, best, rng, chosen, cs.candidates);
-					pk = chosen;
-				}
-			}
-			if (pk != old) log_put(lane, lg, m.pos, pk);
-			type = pk_type(pk);
-			const uint32_t len = pk_len(pk), dist = pk_dist(pk);
-			if (!packet_ok(m, n, type, len, dist)) {
-				st.err = ERR_BAD_PACKET;
-				break;
-			}
-			t.bits += apply_packet(lane, probs, price, m, type, len, dist, byte, rep_byte, t.acc);
-			t.packets++;
-		}
-		if (st.err) break;
-		tally_flush(t);
-		cs.packets += t.packets;
-		cs.bits += t.bits;
-		cs.slab_bytes += (uint64_t)(n - start_pos) * 9;
 		cs.edits += lg.count;
 		if (lg.overflow) {
 			// accept/reject buffer too small for this proposal: drop it, uncounted
@@ -533,23 +761,23 @@ __global__ void __launch_bounds__(CTA_THREADS) anneal_kernel(AnnealArgs a)
 		}
 
 		// ---- accept / reject: main.c:86-96 ---------------------------------------------------
-		const uint64_t cost = t.total;
+		const uint64_t cost = k.t.total;
 		const uint32_t r = rng31(rng);
 		bool uphill;
 		if (a.schedule == 0) {
-			const uint64_t i = (uint64_t)a.first_eval + done;
+			const uint64_t i = (uint64_t)first_eval + done;
 			const uint64_t mod = i * i + 1 + (uint64_t)a.step * (uint64_t)a.num_iters / 2;
 			const uint64_t x = (uint64_t)r % mod;
 			uphill = x * x < (uint64_t)a.num_iters;
 		} else {
-			const float e = -__logf(((float)r + 0.5f) * (1.0f / 2147483648.0f));
-			uphill = (float)(cost - st.cur_cost) <= temp * e;
+			const float ex = -__logf(((float)r + 0.5f) * (1.0f / 2147483648.0f));
+			uphill = (float)(cost - st.cur_cost) <= temp * ex;
 		}
 		uint32_t flags = 1;
 		if (st.cur_cost == 0 || cost < st.cur_cost || uphill) {
 			flags |= 2;
 			st.cur_cost = cost;
-			st.live_count = m.pidx;
+			st.live_count = walker_pidx(k);
 			// commit the accept/reject buffer and the checkpoints written on the way
 			__syncwarp();
 			for (uint32_t i = lane; i < lg.stored; i += 32) slab[lg.e[i].pos] = lg.e[i].pk;
@@ -561,7 +789,6 @@ __global__ void __launch_bounds__(CTA_THREADS) anneal_kernel(AnnealArgs a)
 				flags |= 4;
 				cs.new_best++;
 				if (a.track_best) {
-					__threadfence_block();
 					uint64_t* best = a.bests + (size_t)c * n;
 					for (uint32_t i = lane; i < n; i += 32) best[i] = slab[i];
 				}
@@ -579,6 +806,7 @@ __global__ void __launch_bounds__(CTA_THREADS) anneal_kernel(AnnealArgs a)
 	cs.attempts = attempts;
 	if (lane == 0) {
 		st.rng = rng;
+		st.eval_index = first_eval + done;
 		a.state[c] = st;
 		a.stats[c] = cs;
 		a.attempts_out[c] = attempts;
@@ -667,13 +895,13 @@ __global__ void __launch_bounds__(32) encode_kernel(EncodeArgs a)
 	model_init(lane, rec.probs, m);
 	RangeCoder rc = {0, 0xFFFFFFFFu, 0, 1, a.out, a.cap, 0};
 	Window w;
-	w.base = 0xffffffffu;
+	w.base = WINDOW_NONE;
 	uint32_t err = 0;
 	while (m.pos < a.n) {
 		window_seek(lane, w, a.slab, a.data, a.n, m.pos);
-		const uint64_t pk = window_packet(w, m.pos);
-		const uint32_t byte = window_byte(w, m.pos);
-		const uint32_t type = pk_type(pk), len = pk_len(pk), dist = pk_dist(pk);
+		const uint32_t meta = window_meta(w, m.pos);
+		const uint32_t type = meta_type(meta), len = meta_len(meta), dist = window_dist(w, m.pos);
+		const uint32_t byte = meta_byte(meta) & 0xff;
 		if (!packet_ok(m, a.n, type, len, dist)) {
 			err = ERR_BAD_PACKET;
 			break;
