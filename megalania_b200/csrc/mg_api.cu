@@ -75,6 +75,10 @@ static int set_smem_attrs()
 	CU(cudaFuncSetAttribute(score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CtaShared)));
 	CU(cudaFuncSetAttribute(topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CtaShared)));
 	CU(cudaFuncSetAttribute(anneal_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CtaShared)));
+	// the model lives in shared memory: ask for the largest carve-out so that occupancy is set by registers
+	CU(cudaFuncSetAttribute(score_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+	CU(cudaFuncSetAttribute(topk_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+	CU(cudaFuncSetAttribute(anneal_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
 	done = true;
 	return 0;
 }
@@ -537,6 +541,7 @@ struct mg_anneal {
 	uint32_t* d_ck_pidx = nullptr;
 	uint8_t* d_ck_live = nullptr;
 	Edit* d_logs = nullptr;
+	Edit* d_journal = nullptr;
 	ChainState* d_state = nullptr;
 	ChainStats* d_stats = nullptr;
 	TraceRec* d_trace = nullptr;
@@ -570,7 +575,7 @@ extern "C" MG_API size_t mg_anneal_chain_bytes(const mg_ctx* ctx, const mg_annea
 	const size_t nslots = (n + p.checkpoint_stride - 1) / p.checkpoint_stride;
 	const size_t nck = nslots > 1 ? nslots - 1 : 1;
 	size_t b = n * 8;
-	if (p.track_best) b += n * 8;
+	if (p.track_best) b += n * 8 + (size_t)JOURNAL_CAP * sizeof(Edit);
 	b += nck * 2 * (sizeof(Record) + 4) + nck;
 	b += (size_t)p.edit_log_capacity * sizeof(Edit);
 	b += sizeof(ChainState) + sizeof(ChainStats) + 4 + 4 + 8 + 4 + 4;
@@ -589,6 +594,7 @@ extern "C" MG_API void mg_anneal_destroy(mg_anneal* an)
 	cudaFree(an->d_ck_pidx);
 	cudaFree(an->d_ck_live);
 	cudaFree(an->d_logs);
+	cudaFree(an->d_journal);
 	cudaFree(an->d_state);
 	cudaFree(an->d_stats);
 	cudaFree(an->d_trace);
@@ -633,6 +639,7 @@ extern "C" MG_API int mg_anneal_create(mg_ctx* ctx, const mg_anneal_params* para
 	A(an->d_ck_pidx, C * 2 * nck * 4);
 	A(an->d_ck_live, C * nck);
 	A(an->d_logs, C * (size_t)p.edit_log_capacity * sizeof(Edit));
+	if (p.track_best) A(an->d_journal, C * (size_t)JOURNAL_CAP * sizeof(Edit));
 	A(an->d_state, C * sizeof(ChainState));
 	A(an->d_stats, C * sizeof(ChainStats));
 	if (p.trace_capacity) A(an->d_trace, C * (size_t)p.trace_capacity * sizeof(TraceRec));
@@ -722,6 +729,8 @@ static int refresh_chains(mg_anneal* an, uint32_t first, uint32_t count, int ado
 		st[i].live_count = live[i];
 		st[i].err = 0;
 		st[i].eval_index = 0;
+		st[i].journal_count = 0;
+		st[i].journal_overflow = reset_best ? 0 : 1;  // best slab == current slab only right after a reset
 		if (reset_best) st[i].best_cost = 0;
 	}
 	CU(cudaMemcpyAsync(an->d_state + first, st.data(), count * sizeof(ChainState), cudaMemcpyHostToDevice, ctx->stream));
@@ -769,6 +778,8 @@ extern "C" MG_API int mg_anneal_set_slab(mg_anneal* an, uint32_t first, uint32_t
 			st[i].live_count = st[0].live_count;
 			st[i].err = 0;
 			st[i].eval_index = 0;
+			st[i].journal_count = 0;
+			st[i].journal_overflow = reset_best ? 0 : 1;
 			if (reset_best) st[i].best_cost = 0;
 			an->have_slab[first + i] = 1;
 		}
@@ -816,6 +827,7 @@ extern "C" MG_API int mg_anneal_run(mg_anneal* an, const mg_anneal_run_params* r
 	a.ck_pidx = an->d_ck_pidx;
 	a.ck_live = an->d_ck_live;
 	a.logs = an->d_logs;
+	a.journal = an->d_journal;
 	a.state = an->d_state;
 	a.stats = an->d_stats;
 	a.trace = an->d_trace;
@@ -974,6 +986,8 @@ extern "C" MG_API int mg_anneal_swap_chains(mg_anneal* an, uint32_t x, uint32_t 
 	nx.live_count = sy.live_count;
 	ny.cur_cost = sx.cur_cost;
 	ny.live_count = sx.live_count;
+	nx.journal_count = ny.journal_count = 0;
+	nx.journal_overflow = ny.journal_overflow = 1;  // the best slabs stayed, the current ones moved
 	CU(cudaMemcpy(an->d_state + x, &nx, sizeof(ChainState), cudaMemcpyHostToDevice));
 	CU(cudaMemcpy(an->d_state + y, &ny, sizeof(ChainState), cudaMemcpyHostToDevice));
 	return MG_OK;

@@ -359,6 +359,12 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t addr)
 	asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
 	return v;
 }
+__device__ __forceinline__ uint32_t lds_u8(uint32_t addr)
+{
+	uint32_t v;
+	asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+	return v;
+}
 __device__ __forceinline__ void sts_u16(uint32_t addr, uint32_t v)
 {
 	asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((uint16_t)v) : "memory");
@@ -375,7 +381,8 @@ __device__ __forceinline__ uint32_t meta_byte(uint32_t meta) { return meta >> 16
 
 struct Window {
 	uint32_t meta, dist, meta_next, dist_next;
-	uint32_t base;  // multiple of 32; WINDOW_NONE = nothing loaded
+	uint32_t base;     // multiple of 32; WINDOW_NONE = nothing loaded
+	uint32_t litmask;  // bit i: slot base+i is a canonical LITERAL
 };
 constexpr uint32_t WINDOW_NONE = 0x7fffffe0u;  // never within 32 of a real position (inputs < 2 GiB... see mg_ctx_create)
 
@@ -392,8 +399,10 @@ __device__ __forceinline__ void window_load(int lane, const uint64_t* __restrict
 	dist = pk_dist(pk);
 }
 
+// wbytes: shared address of the warp's 32-byte staging buffer; the window's data bytes are
+// mirrored there so that the literal-run loop can read them without a shuffle.
 __device__ __forceinline__ void window_seek(int lane, Window& w, const uint64_t* __restrict__ slab,
-                                            const uint8_t* __restrict__ data, uint32_t n, uint32_t pos)
+                                            const uint8_t* __restrict__ data, uint32_t n, uint32_t pos, uint32_t wbytes)
 {
 	const uint32_t want = pos & ~31u;
 	if (want == w.base) return;
@@ -404,6 +413,10 @@ __device__ __forceinline__ void window_seek(int lane, Window& w, const uint64_t*
 		window_load(lane, slab, data, n, want, w.meta, w.dist);
 	}
 	w.base = want;
+	w.litmask = __ballot_sync(FULL, (w.meta & 0xffffu) == META_LITERAL);
+	__syncwarp();  // readers of the previous window's bytes are done
+	asm volatile("st.shared.u8 [%0], %1;" ::"r"(wbytes + (uint32_t)lane), "r"(w.meta >> 16) : "memory");
+	__syncwarp();
 	window_load(lane, slab, data, n, want + 32, w.meta_next, w.dist_next);
 }
 

@@ -14,6 +14,8 @@ struct WarpShared {
 	Record rec;
 	FindScratch fs;
 	uint64_t bar;
+	uint32_t wbytes[8];  // data bytes of the current slab window (see window_seek)
+	uint64_t pad;
 };
 struct CtaShared {
 	uint32_t trans[4096];  // see code_bit()
@@ -127,6 +129,7 @@ struct WalkEnv {
 	const uint8_t* __restrict__ data;
 	uint32_t n;
 	uint32_t trans_addr;  // shared address of trans[]
+	uint32_t wb_addr;     // shared address of the window byte mirror
 	uint32_t lit_addr;    // shared address of this lane's first slot
 	uint32_t lit_sh;      // byte >> lit_sh = tree prefix at this lane's depth
 	uint32_t bitmask;     // 0x800 on tree lanes
@@ -146,6 +149,7 @@ __device__ __forceinline__ WalkEnv make_env(int lane, WarpShared* ws, const CtaS
 	e.data = data;
 	e.n = n;
 	e.trans_addr = smem_u32(sh->trans);
+	e.wb_addr = smem_u32(ws->wbytes);
 	const bool tree = lane >= 1 && lane <= 8;
 	const uint32_t first = lane == 0 ? S_ISMATCH : tree ? S_LIT + (1u << (lane - 1)) : S_DUMMY;
 	e.lit_addr = smem_u32(ws->rec.probs) + 2 * first;
@@ -285,7 +289,7 @@ __device__ __forceinline__ uint32_t walk(const WalkEnv& e, Walker& k, uint32_t s
 		if (CKPT && k.pos >= ck.next) walker_checkpoint(e, k, ck);
 		if (k.pos - k.w.base >= 32u) {
 			tally_flush(k.t);
-			window_seek(e.lane, k.w, e.slab, e.data, e.n, k.pos);
+			window_seek(e.lane, k.w, e.slab, e.data, e.n, k.pos, e.wb_addr);
 		}
 		uint32_t limit = k.w.base + 32 < stop_pos ? k.w.base + 32 : stop_pos;
 		if (CKPT) limit = ck.next < limit ? ck.next : limit;
@@ -297,21 +301,51 @@ __device__ __forceinline__ uint32_t walk(const WalkEnv& e, Walker& k, uint32_t s
 		while (k.pos < limit) {
 			const uint32_t meta = window_meta(k.w, k.pos);
 			if (MODE != WALK_REPAIR_HEAD && (meta & 0xffffu) == META_LITERAL) {
-				// ---- literal fast path, branch-free across lanes ----------------------------------
+				const uint32_t ctx = k.ctx;
+				if (ctx < 7) {
+					// ---- run of plain literals: every lane follows its own slot class through the
+					// whole run (lane 0 is_match, lanes 1..8 one tree depth, the rest the idle slot);
+					// classes never share a slot, so no cross-lane traffic is needed per packet ---------
+					const uint32_t idx = k.pos - k.w.base;
+					uint32_t run = (uint32_t)__ffs((int)~(k.w.litmask >> idx)) - 1u;
+					run = run < limit - k.pos ? run : limit - k.pos;
+					uint32_t baddr = e.wb_addr + idx;
+					const uint32_t bend = baddr + run;
+					uint32_t cj = ctx;
+					uint32_t next_byte = lds_u8(baddr);  // one packet ahead, off the dependent chain
+					// the automaton reaches state 0 after at most three literals (lzma_state.c:34-40)
+					while (cj != 0 && baddr != bend) {
+						const uint32_t byte = next_byte;
+						next_byte = lds_u8(++baddr);
+						const uint32_t addr = e.lit_addr + 2 * ((byte >> e.lit_sh) + (cj & e.ctxmask));
+						const uint32_t bit11 = (byte << (12 - e.lit_sh)) & e.bitmask;
+						const uint32_t tr = lds_u32(e.trans_addr + ((lds_u16(addr) | bit11) << 2));
+						sts_u16(addr, tr);
+						k.t.acc += tr >> 16;
+						cj = (cj > 3 ? cj : 3) - 3;
+					}
+					while (baddr != bend) {
+						const uint32_t byte = next_byte;
+						next_byte = lds_u8(++baddr);
+						const uint32_t addr = e.lit_addr + 2 * (byte >> e.lit_sh);
+						const uint32_t bit11 = (byte << (12 - e.lit_sh)) & e.bitmask;
+						const uint32_t tr = lds_u32(e.trans_addr + ((lds_u16(addr) | bit11) << 2));
+						sts_u16(addr, tr);
+						k.t.acc += tr >> 16;
+					}
+					k.ctx = cj;
+					k.pos += run;
+					continue;
+				}
+				// ---- one matched literal (lzma_packet_encoder.c:123-130): the tree follows the match
+				// byte for as long as the prefixes agree ------------------------------------------------
 				const uint32_t byte = meta >> 16;
 				const uint32_t top = byte >> e.lit_sh;
 				const uint32_t bit11 = (byte << (12 - e.lit_sh)) & e.bitmask;
-				const uint32_t ctx = k.ctx;
 				uint32_t off = top + (ctx & e.ctxmask);
-				if (ctx >= 7) {
-					// matched literal (lzma_packet_encoder.c:123-130): the tree follows the match
-					// byte for as long as the prefixes agree
-					const uint32_t extra = (0x100u + ((k.mb << (9 - e.lit_sh)) & 0x100u)) & e.treemask;
-					if ((k.mb >> e.lit_sh) == top) off += extra;
-					k.ctx = ctx < 10 ? ctx - 3 : ctx - 6;
-				} else {
-					k.ctx = ctx < 4 ? 0 : ctx - 3;
-				}
+				const uint32_t extra = (0x100u + ((k.mb << (9 - e.lit_sh)) & 0x100u)) & e.treemask;
+				if ((k.mb >> e.lit_sh) == top) off += extra;
+				k.ctx = ctx < 10 ? ctx - 3 : ctx - 6;
 				const uint32_t addr = e.lit_addr + 2 * off;
 				const uint32_t tr = lds_u32(e.trans_addr + ((lds_u16(addr) | bit11) << 2));
 				sts_u16(addr, tr);
@@ -514,8 +548,11 @@ struct ChainState {
 	uint32_t live_count;
 	uint32_t err;
 	uint32_t eval_index;  // successful evaluations since the chain's slab was last set
+	uint32_t journal_count;     // edits accepted since the best slab last equalled the current slab
+	uint32_t journal_overflow;  // != 0: the journal is incomplete, the next new best copies the whole slab
 	uint32_t pad;
 };
+constexpr uint32_t JOURNAL_CAP = 1024;
 
 struct ChainStats {
 	unsigned long long evals, attempts, accepted, new_best, packets, bits, slab_bytes, ck_bytes, finds, candidates,
@@ -541,6 +578,7 @@ struct AnnealArgs {
 	uint32_t* ck_pidx;   // [chains][2][nslots-1]
 	uint8_t* ck_live;    // [chains][nslots-1] which of the two buffers is current
 	Edit* logs;          // [chains][log_cap]
+	Edit* journal;       // [chains][JOURNAL_CAP] or null (no best tracking)
 	ChainState* state;   // [chains]
 	ChainStats* stats;   // [chains]
 	TraceRec* trace;     // [chains][trace_cap] or null
@@ -625,7 +663,7 @@ __global__ void __launch_bounds__(CTA_THREADS, MG_ANNEAL_MIN_CTAS) anneal_kernel
 		const uint32_t pos = k.pos;
 		if (pos - k.w.base >= 32u) {
 			tally_flush(k.t);
-			window_seek(lane, k.w, slab, a.data, n, pos);
+			window_seek(lane, k.w, slab, a.data, n, pos, e.wb_addr);
 		}
 		const uint32_t meta0 = window_meta(k.w, pos);
 		const uint32_t dist0 = window_dist(k.w, pos);
@@ -784,13 +822,67 @@ __global__ void __launch_bounds__(CTA_THREADS, MG_ANNEAL_MIN_CTAS) anneal_kernel
 			for (uint32_t j = j0 + lane; j < nck; j += 32) ck_live[j] ^= 1;
 			__syncwarp();
 			cs.accepted++;
+			// The best slab is kept in step with the current one through a journal of accepted
+			// edits (src/main.c:89-92 copies the whole slab on every new best; early in a run that
+			// is nearly every proposal).  Only a journal overflow falls back to a full copy.
+			Edit* jl = a.track_best ? a.journal + (size_t)c * JOURNAL_CAP : nullptr;
+			if (jl && !st.journal_overflow) {
+				if (st.journal_count + lg.stored <= JOURNAL_CAP) {
+					for (uint32_t i = lane; i < lg.stored; i += 32) jl[st.journal_count + i] = lg.e[i];
+					st.journal_count += lg.stored;
+				} else {
+					st.journal_overflow = 1;
+				}
+			}
 			if (st.best_cost == 0 || cost < st.best_cost) {
 				st.best_cost = cost;
 				flags |= 4;
 				cs.new_best++;
-				if (a.track_best) {
+				if (jl) {
 					uint64_t* best = a.bests + (size_t)c * n;
-					for (uint32_t i = lane; i < n; i += 32) best[i] = slab[i];
+					__syncwarp();
+					if (st.journal_overflow) {
+						if ((((uintptr_t)slab | (uintptr_t)best) & 15) == 0) {
+							const uint4* src4 = reinterpret_cast<const uint4*>(slab);
+							uint4* dst4 = reinterpret_cast<uint4*>(best);
+							const uint32_t n4 = n / 2;
+							uint32_t i = lane;
+							for (; i + 96 < n4; i += 128) {
+								const uint4 v0 = src4[i], v1 = src4[i + 32], v2 = src4[i + 64], v3 = src4[i + 96];
+								dst4[i] = v0;
+								dst4[i + 32] = v1;
+								dst4[i + 64] = v2;
+								dst4[i + 96] = v3;
+							}
+							for (; i < n4; i += 32) dst4[i] = src4[i];
+							if ((n & 1) && lane == 0) best[n - 1] = slab[n - 1];
+						} else {
+							uint32_t i = lane;
+							for (; i + 96 < n; i += 128) {
+								const uint64_t v0 = slab[i], v1 = slab[i + 32], v2 = slab[i + 64], v3 = slab[i + 96];
+								best[i] = v0;
+								best[i + 32] = v1;
+								best[i + 64] = v2;
+								best[i + 96] = v3;
+							}
+							for (; i < n; i += 32) best[i] = slab[i];
+						}
+						cs.slab_bytes += 16ull * n;
+					} else {
+						// later entries win: inside a step through match_any, across steps by order
+						for (uint32_t base = 0; base < st.journal_count; base += 32) {
+							const uint32_t i = base + lane;
+							const bool valid = i < st.journal_count;
+							const uint32_t jpos = valid ? jl[i].pos : 0xffffff00u + (uint32_t)lane;
+							const uint64_t jpk = valid ? jl[i].pk : 0;
+							const uint32_t peers = __match_any_sync(FULL, jpos);
+							if (valid && (peers >> lane) == 1u) best[jpos] = jpk;
+							__syncwarp();
+						}
+						cs.slab_bytes += 24ull * st.journal_count;
+					}
+					st.journal_count = 0;
+					st.journal_overflow = 0;
 				}
 			}
 		}
@@ -890,6 +982,7 @@ __global__ void __launch_bounds__(32) encode_kernel(EncodeArgs a)
 {
 	__shared__ __align__(16) Record rec;
 	__shared__ uint32_t ev[32];
+	__shared__ uint32_t wbytes[8];
 	const int lane = threadIdx.x;
 	Model m;
 	model_init(lane, rec.probs, m);
@@ -898,7 +991,7 @@ __global__ void __launch_bounds__(32) encode_kernel(EncodeArgs a)
 	w.base = WINDOW_NONE;
 	uint32_t err = 0;
 	while (m.pos < a.n) {
-		window_seek(lane, w, a.slab, a.data, a.n, m.pos);
+		window_seek(lane, w, a.slab, a.data, a.n, m.pos, smem_u32(wbytes));
 		const uint32_t meta = window_meta(w, m.pos);
 		const uint32_t type = meta_type(meta), len = meta_len(meta), dist = window_dist(w, m.pos);
 		const uint32_t byte = meta_byte(meta) & 0xff;
