@@ -357,7 +357,7 @@ def main() -> None:
     ap.add_argument("--impl", choices=["cuda", "reference"], default="cuda")
     ap.add_argument("--size", type=int, default=1 << 20)
     ap.add_argument("--chains", type=int, default=0, help="chains per GPU (default: SMs x --warps-per-sm)")
-    ap.add_argument("--warps-per-sm", type=int, default=16)
+    ap.add_argument("--warps-per-sm", type=int, default=32)
     ap.add_argument("--evals", type=int, default=1000, help="cap on successful evaluations per chain per step")
     ap.add_argument("--packet-budget", type=int, default=4_000_000,
                     help="a chain ends its step after the evaluation that brings its priced packets to this many "

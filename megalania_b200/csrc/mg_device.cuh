@@ -380,7 +380,7 @@ __device__ __forceinline__ uint32_t meta_len(uint32_t meta) { return (meta >> 3)
 __device__ __forceinline__ uint32_t meta_byte(uint32_t meta) { return meta >> 16; }
 
 struct Window {
-	uint32_t meta, dist, meta_next, dist_next;
+	uint32_t meta, dist, meta_next, dist_next, meta_next2, dist_next2;  // current + two prefetched windows
 	uint32_t base;     // multiple of 32; WINDOW_NONE = nothing loaded
 	uint32_t litmask;  // bit i: slot base+i is a canonical LITERAL
 };
@@ -407,17 +407,26 @@ __device__ __forceinline__ void window_seek(int lane, Window& w, const uint64_t*
 	const uint32_t want = pos & ~31u;
 	if (want == w.base) return;
 	if (want == w.base + 32) {
+		// the common case: slide by one window, fetch the one two ahead (HBM latency exceeds the
+		// time a warp spends on 32 packets)
 		w.meta = w.meta_next;
 		w.dist = w.dist_next;
+		w.meta_next = w.meta_next2;
+		w.dist_next = w.dist_next2;
+	} else if (want == w.base + 64) {
+		w.meta = w.meta_next2;
+		w.dist = w.dist_next2;
+		window_load(lane, slab, data, n, want + 32, w.meta_next, w.dist_next);
 	} else {
 		window_load(lane, slab, data, n, want, w.meta, w.dist);
+		window_load(lane, slab, data, n, want + 32, w.meta_next, w.dist_next);
 	}
 	w.base = want;
+	window_load(lane, slab, data, n, want + 64, w.meta_next2, w.dist_next2);
 	w.litmask = __ballot_sync(FULL, (w.meta & 0xffffu) == META_LITERAL);
 	__syncwarp();  // readers of the previous window's bytes are done
 	asm volatile("st.shared.u8 [%0], %1;" ::"r"(wbytes + (uint32_t)lane), "r"(w.meta >> 16) : "memory");
 	__syncwarp();
-	window_load(lane, slab, data, n, want + 32, w.meta_next, w.dist_next);
 }
 
 __device__ __forceinline__ uint32_t window_meta(const Window& w, uint32_t pos)

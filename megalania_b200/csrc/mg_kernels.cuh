@@ -5,9 +5,50 @@
 
 namespace mg {
 
-constexpr int WARPS_PER_CTA = 8;
+// One CTA of 32 warps per SM: the walk is bound by shared-memory latency, so occupancy is what
+// hides it; 32 models + the transition table fill the 227 KB of shared memory, and 64 registers
+// per thread fill the register file.
+#ifndef MG_WARPS_PER_CTA
+#define MG_WARPS_PER_CTA 32
+#endif
+constexpr int WARPS_PER_CTA = MG_WARPS_PER_CTA;
 constexpr int CTA_THREADS = WARPS_PER_CTA * 32;
 constexpr uint32_t RECIP_ENTRIES = 288;
+
+struct ChainStats {
+	unsigned long long evals, attempts, accepted, new_best, packets, bits, slab_bytes, ck_bytes, finds, candidates,
+	    edits, overflows;
+};
+
+struct ChainState {
+	uint64_t rng;
+	uint64_t cur_cost;
+	uint64_t best_cost;
+	uint32_t live_count;
+	uint32_t err;
+	uint32_t eval_index;  // successful evaluations since the chain's slab was last set
+	uint32_t journal_count;     // edits accepted since the best slab last equalled the current slab
+	uint32_t journal_overflow;  // != 0: the journal is incomplete, the next new best copies the whole slab
+	uint32_t pad;
+};
+constexpr uint32_t JOURNAL_CAP = 1024;
+
+// ---- the accept/reject buffer of one proposal (replaces packet_slab_undo_stack) -------------------
+struct Edit {
+	uint32_t pos;
+	uint32_t pad;
+	uint64_t pk;
+};
+
+struct EditLog {
+	Edit* e;
+	uint32_t cap;
+	uint32_t stored;    // physical entries
+	uint32_t count;     // logical edits (what the reference's undo stack would hold)
+	uint32_t dup_pos;   // position whose entry may be rewritten (pos+1 of a shrink), or ~0
+	uint32_t dup_index;
+	bool overflow;
+};
 
 // Dynamic shared memory of one CTA.
 struct WarpShared {
@@ -16,6 +57,7 @@ struct WarpShared {
 	uint64_t bar;
 	uint32_t wbytes[8];  // data bytes of the current slab window (see window_seek)
 	uint64_t pad;
+	ChainStats stats;    // counters of the running launch (kept out of the register file; lane 0 only)
 };
 struct CtaShared {
 	uint32_t trans[4096];  // see code_bit()
@@ -60,7 +102,7 @@ __device__ __forceinline__ bool packet_ok(const Model& m, uint32_t n, uint32_t t
 struct Tally {
 	uint64_t total;  // uniform: cost flushed so far
 	uint32_t acc;    // per lane: cost since the last flush
-	uint32_t packets, bits;  // bits: modelled bits in excess of 9 per packet (two's complement)
+	uint32_t bits;  // modelled bits in excess of 9 per packet (two's complement)
 };
 
 __device__ __forceinline__ void tally_flush(Tally& t)
@@ -80,22 +122,6 @@ __device__ __forceinline__ bool rep_matches(int lane, const uint8_t* __restrict_
 	return __all_sync(FULL, same);
 }
 
-// ---- the accept/reject buffer of one proposal (replaces packet_slab_undo_stack) -------------------
-struct Edit {
-	uint32_t pos;
-	uint32_t pad;
-	uint64_t pk;
-};
-
-struct EditLog {
-	Edit* e;
-	uint32_t cap;
-	uint32_t stored;    // physical entries
-	uint32_t count;     // logical edits (what the reference's undo stack would hold)
-	uint32_t dup_pos;   // position whose entry may be rewritten (pos+1 of a shrink), or ~0
-	uint32_t dup_index;
-	bool overflow;
-};
 
 __device__ __forceinline__ void log_put(int lane, EditLog& lg, uint32_t pos, uint64_t pk)
 {
@@ -212,7 +238,7 @@ __device__ __forceinline__ void walker_init(const WalkEnv& e, Walker& k)
 	if (e.lane == 0) e.probs[S_DUMMY] = 0;
 	__syncwarp();
 	k.pos = k.delta = k.ctx = k.mb = 0;
-	k.t = {0, 0, 0, 0};
+	k.t = {0, 0, 0};
 	k.w.base = WINDOW_NONE;
 }
 
@@ -224,7 +250,7 @@ __device__ __forceinline__ void walker_load(const WalkEnv& e, Walker& k, const R
 	k.pos = m.pos;
 	k.delta = m.pos - m.pidx;
 	k.ctx = m.ctx;
-	k.t = {cost, 0, 0, 0};
+	k.t = {cost, 0, 0};
 	k.w.base = WINDOW_NONE;
 	k.mb = 0;
 	if (k.ctx >= 7) walker_fetch_mb(e, k);
@@ -244,6 +270,7 @@ __device__ __forceinline__ void walker_apply(const WalkEnv& e, Walker& k, Model&
 		e.rec->rep[1] = m.rep1;
 		e.rec->rep[2] = m.rep2;
 		e.rec->rep[3] = m.rep3;
+		__syncwarp();  // lanes are not guaranteed to run in lockstep: order these stores before later reads
 	}
 	if (type != T_LITERAL) walker_fetch_mb(e, k);
 }
@@ -541,23 +568,7 @@ __global__ void __launch_bounds__(CTA_THREADS) topk_kernel(TopkArgs a)
 }
 
 // ---- K3/K4: the annealing loop ---------------------------------------------------------------------
-struct ChainState {
-	uint64_t rng;
-	uint64_t cur_cost;
-	uint64_t best_cost;
-	uint32_t live_count;
-	uint32_t err;
-	uint32_t eval_index;  // successful evaluations since the chain's slab was last set
-	uint32_t journal_count;     // edits accepted since the best slab last equalled the current slab
-	uint32_t journal_overflow;  // != 0: the journal is incomplete, the next new best copies the whole slab
-	uint32_t pad;
-};
-constexpr uint32_t JOURNAL_CAP = 1024;
 
-struct ChainStats {
-	unsigned long long evals, attempts, accepted, new_best, packets, bits, slab_bytes, ck_bytes, finds, candidates,
-	    edits, overflows;
-};
 
 struct TraceRec {
 	uint64_t cost;
@@ -591,7 +602,7 @@ struct AnnealArgs {
 };
 
 #ifndef MG_ANNEAL_MIN_CTAS
-#define MG_ANNEAL_MIN_CTAS 2
+#define MG_ANNEAL_MIN_CTAS 1
 #endif
 __global__ void __launch_bounds__(CTA_THREADS, MG_ANNEAL_MIN_CTAS) anneal_kernel(AnnealArgs a)
 {
@@ -611,7 +622,11 @@ __global__ void __launch_bounds__(CTA_THREADS, MG_ANNEAL_MIN_CTAS) anneal_kernel
 	ChainState st = a.state[c];
 	uint64_t rng = st.rng;
 	uint32_t parity = 0;
-	ChainStats cs = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+	// Counters live in shared memory and are touched by lane 0 only: lanes of a warp are not
+	// guaranteed to run in lockstep, so a read-modify-write by all of them could count twice.
+	ChainStats& cs = ws->stats;
+	if (lane == 0) cs = ChainStats{0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+	unsigned long long packets_done = 0;  // uniform copy of cs.packets for the budget test
 	EditLog lg;
 	lg.e = a.logs + (size_t)c * a.log_cap;
 	lg.cap = a.log_cap;
@@ -620,7 +635,7 @@ __global__ void __launch_bounds__(CTA_THREADS, MG_ANNEAL_MIN_CTAS) anneal_kernel
 	uint32_t done = 0, attempts = 0;
 	const uint32_t first_eval = a.first_eval == 0xffffffffu ? st.eval_index : a.first_eval;
 	while (done < a.evals && attempts < a.max_attempts && st.err == 0 &&
-	       (a.packet_budget == 0 || cs.packets < a.packet_budget)) {
+	       (a.packet_budget == 0 || packets_done < a.packet_budget)) {
 		attempts++;
 		lg.stored = lg.count = 0;
 		lg.dup_pos = 0xffffffffu;
@@ -637,7 +652,7 @@ __global__ void __launch_bounds__(CTA_THREADS, MG_ANNEAL_MIN_CTAS) anneal_kernel
 			walker_init(e, k);
 		} else {
 			walker_load(e, k, ck_base + (size_t)ck_live[j0 - 1] * nck + (j0 - 1), &ws->bar, parity);
-			cs.ck_bytes += sizeof(Record);
+			if (lane == 0) cs.ck_bytes += sizeof(Record);
 		}
 		const uint32_t start_pos = k.pos, start_pidx = walker_pidx(k);
 		CkSink ck;
@@ -705,10 +720,10 @@ __global__ void __launch_bounds__(CTA_THREADS, MG_ANNEAL_MIN_CTAS) anneal_kernel
 		bool failed = false;
 		while (phase < 3) {
 			if (want_find) {
-				cs.finds++;
+				if (lane == 0) cs.finds++;
 				const uint32_t count = warp_find(lane, e.probs, sh->trans, sh->recip, &ws->fs, a.data, n, a.occ_start, a.occ,
 				                                 walker_model(e, k), excluded, a.k);
-				cs.candidates += ws->fs.candidates;
+				if (lane == 0) cs.candidates += ws->fs.candidates;
 				uint64_t chosen = 0;
 				bool have = false;
 				if (count != 0) {
@@ -776,10 +791,13 @@ __global__ void __launch_bounds__(CTA_THREADS, MG_ANNEAL_MIN_CTAS) anneal_kernel
 		}
 		if (st.err) break;
 		tally_flush(k.t);
-		cs.packets += walker_pidx(k) - start_pidx;
-		cs.bits += walker_bits(k, start_pidx);
-		cs.slab_bytes += (uint64_t)(k.pos - start_pos) * 9;
-		cs.ck_bytes += (uint64_t)ck.written * sizeof(Record);
+		packets_done += walker_pidx(k) - start_pidx;
+		if (lane == 0) {
+			cs.packets += walker_pidx(k) - start_pidx;
+			cs.bits += walker_bits(k, start_pidx);
+			cs.slab_bytes += (uint64_t)(k.pos - start_pos) * 9;
+			cs.ck_bytes += (uint64_t)ck.written * sizeof(Record);
+		}
 		if (failed) {
 			if (a.trace && attempts <= a.trace_cap && lane == 0) {
 				TraceRec r = {0, 0, 0};
@@ -787,10 +805,10 @@ __global__ void __launch_bounds__(CTA_THREADS, MG_ANNEAL_MIN_CTAS) anneal_kernel
 			}
 			continue;
 		}
-		cs.edits += lg.count;
+		if (lane == 0) cs.edits += lg.count;
 		if (lg.overflow) {
 			// accept/reject buffer too small for this proposal: drop it, uncounted
-			cs.overflows++;
+			if (lane == 0) cs.overflows++;
 			if (a.trace && attempts <= a.trace_cap && lane == 0) {
 				TraceRec r = {0, 0, lg.count};
 				a.trace[(size_t)c * a.trace_cap + attempts - 1] = r;
@@ -821,7 +839,7 @@ __global__ void __launch_bounds__(CTA_THREADS, MG_ANNEAL_MIN_CTAS) anneal_kernel
 			for (uint32_t i = lane; i < lg.stored; i += 32) slab[lg.e[i].pos] = lg.e[i].pk;
 			for (uint32_t j = j0 + lane; j < nck; j += 32) ck_live[j] ^= 1;
 			__syncwarp();
-			cs.accepted++;
+			if (lane == 0) cs.accepted++;
 			// The best slab is kept in step with the current one through a journal of accepted
 			// edits (src/main.c:89-92 copies the whole slab on every new best; early in a run that
 			// is nearly every proposal).  Only a journal overflow falls back to a full copy.
@@ -837,7 +855,7 @@ __global__ void __launch_bounds__(CTA_THREADS, MG_ANNEAL_MIN_CTAS) anneal_kernel
 			if (st.best_cost == 0 || cost < st.best_cost) {
 				st.best_cost = cost;
 				flags |= 4;
-				cs.new_best++;
+				if (lane == 0) cs.new_best++;
 				if (jl) {
 					uint64_t* best = a.bests + (size_t)c * n;
 					__syncwarp();
@@ -867,7 +885,7 @@ __global__ void __launch_bounds__(CTA_THREADS, MG_ANNEAL_MIN_CTAS) anneal_kernel
 							}
 							for (; i < n; i += 32) best[i] = slab[i];
 						}
-						cs.slab_bytes += 16ull * n;
+						if (lane == 0) cs.slab_bytes += 16ull * n;
 					} else {
 						// later entries win: inside a step through match_any, across steps by order
 						for (uint32_t base = 0; base < st.journal_count; base += 32) {
@@ -879,7 +897,7 @@ __global__ void __launch_bounds__(CTA_THREADS, MG_ANNEAL_MIN_CTAS) anneal_kernel
 							if (valid && (peers >> lane) == 1u) best[jpos] = jpk;
 							__syncwarp();
 						}
-						cs.slab_bytes += 24ull * st.journal_count;
+						if (lane == 0) cs.slab_bytes += 24ull * st.journal_count;
 					}
 					st.journal_count = 0;
 					st.journal_overflow = 0;
@@ -894,13 +912,13 @@ __global__ void __launch_bounds__(CTA_THREADS, MG_ANNEAL_MIN_CTAS) anneal_kernel
 		__syncwarp();
 	}
 
-	cs.evals = done;
-	cs.attempts = attempts;
 	if (lane == 0) {
+		cs.evals = done;
+		cs.attempts = attempts;
 		st.rng = rng;
 		st.eval_index = first_eval + done;
 		a.state[c] = st;
-		a.stats[c] = cs;
+		a.stats[c] = ws->stats;
 		a.attempts_out[c] = attempts;
 	}
 }
