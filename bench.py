@@ -239,10 +239,14 @@ def run_cuda(args) -> None:
                            lambda buf: an.import_slab(int(cur.argmax()), buf.data_ptr(), adopt_cost=True),
                            import_buf)
 
+    step_no = [0]
+
     def step(first_eval):
         st = an.run(args.evals, schedule=mg.SCHEDULE_REFERENCE, step=0, first_eval=mg.CONTINUE_EVALS,
                     packet_budget=args.packet_budget)
-        exchange()
+        step_no[0] += 1
+        if step_no[0] % args.exchange_every == 0:
+            exchange()
         return st
 
     first_eval = 0
@@ -280,7 +284,10 @@ def run_cuda(args) -> None:
         total_evals, total_bits, total_packets, launches = (int(x) for x in w)
     else:
         total_evals, total_bits, total_packets, launches = agg["evals"], agg["bits_scored"], agg["packets_scored"], agg["launches"]
-    value = total_evals / device_s
+    # `value` uses the wall clock between the two barrier+synchronize brackets (launches, the
+    # between-step exchange and all host work included); the CUDA-event time of the kernels alone
+    # is reported beside it and feeds the roofline.
+    value = total_evals / wall
 
     # ---- roofline of the dominant kernel (anneal_kernel), this rank ---------------------------
     pk, pk_src = peaks()
@@ -329,15 +336,17 @@ def run_cuda(args) -> None:
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": 1e3 * device_s / args.steps, "higher_is_better": True,
+                "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "u16 probabilities / u64 cost (integer)",
                 "data": "synthetic",
                 "config": {"workload": WORKLOAD, "input_bytes": n, "chains_per_gpu": chains,
                            "step": f"each chain runs whole evaluations until it has priced {args.packet_budget} packets "
                                    f"(cap {args.evals} evaluations)", "top_k": 20, "l2": "inputs_exceed_l2",
                            "per_gpu_slab_bytes": chains * n * 8,
-                           "multi_gpu": "independent chains per rank; all-gather of best costs + NCCL broadcast of the best slab after each step"},
-                "wall_ms_per_step": 1e3 * wall / args.steps,
+                           "multi_gpu": f"independent chains per rank; all-gather of best costs + NCCL broadcast of the best slab every {args.exchange_every} steps"},
+                "device_ms_per_step": 1e3 * device_s / args.steps,
+                "timing": "value = evaluations / wall clock between barrier+cudaDeviceSynchronize brackets, max over ranks; "
+                          "device_ms_per_step = CUDA events around the kernel on the library's launch stream",
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
                 "roofline": roofline, "roofline_issue": roofline_issue, "cpu_baseline": cpu,
                 "stats": {"evals": total_evals, "modelled_bits": total_bits, "packets": total_packets,
@@ -363,6 +372,7 @@ def main() -> None:
                     help="a chain ends its step after the evaluation that brings its priced packets to this many "
                          "(time-boxed steps keep all warps busy; about 8 evaluations per chain per step at 1 MiB)")
     ap.add_argument("--seed", type=int, default=1673551)
+    ap.add_argument("--exchange-every", type=int, default=4, help="multi-GPU: best-slab broadcast every this many steps")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

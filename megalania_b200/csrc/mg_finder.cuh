@@ -247,6 +247,51 @@ __device__ __forceinline__ uint32_t warp_find(int lane, const uint16_t* probs, c
 				candidates += (L - 1) * (1 + __popc(rep_mask));
 			}
 			uint32_t pass = __ballot_sync(FULL, valid && cheapest <= root);
+			// the one candidate that is never offered (top_k_packet_finder.c:99-101) would break the
+			// shortcuts below if it were the cheap one; a step that contains it takes the full replay
+			const uint32_t ex_type = pk_type(excluded), ex_idx = pk_dist(excluded), ex_len = pk_len(excluded);
+			const bool ex_here = valid && ex_len >= 2 && ex_len <= L &&
+			                     ((ex_type == T_MATCH && ex_idx == dist) ||
+			                      (ex_type == T_LONG_REP && ex_idx < 4 && ((rep_mask >> ex_idx) & 1u)));
+			if (full && pass && !__any_sync(FULL, ex_here)) {
+				// With a full heap a candidate whose price EQUALS the root's only overwrites the root
+				// entry in place (strict comparisons in the sifts leave the heap order alone,
+				// max_heap.c:93-103), so of a stretch of ties only the last one survives, and a
+				// strictly cheaper candidate that follows evicts even that one.  Ties are the norm
+				// (integer cost/len over mostly untrained length/distance models), so: lanes in front
+				// of the first strictly cheaper lane are skipped, and a step holding nothing but ties
+				// collapses to one store by its last tying lane.
+				const uint32_t less = __ballot_sync(FULL, valid && cheapest < root);
+				if (less == 0) {
+					const int who = 31 - __clz((int)pass);
+					uint32_t done = 0;
+					if (lane == who) {
+						// last candidate of this lane, in enumeration order, that ties and is offered
+						uint64_t last = 0;
+						for (uint32_t len = 2; len <= L; len++) {
+							const uint32_t b = len == 2 ? base2 : len == 3 ? base3 : len == 4 ? base4 : base5;
+							if (per_byte(b + fs->len_price[0][len - 2], len, recip) == root && pk_pack(T_MATCH, dist, len) != excluded)
+								last = pk_pack(T_MATCH, dist, len);
+							if (rep_mask) {
+								const uint32_t lp = fs->len_price[1][len - 2];
+								if ((rep_mask & 1) && per_byte(hdr_r0 + lp, len, recip) == root && pk_pack(T_LONG_REP, 0, len) != excluded) last = pk_pack(T_LONG_REP, 0, len);
+								if ((rep_mask & 2) && per_byte(hdr_r1 + lp, len, recip) == root && pk_pack(T_LONG_REP, 1, len) != excluded) last = pk_pack(T_LONG_REP, 1, len);
+								if ((rep_mask & 4) && per_byte(hdr_r2 + lp, len, recip) == root && pk_pack(T_LONG_REP, 2, len) != excluded) last = pk_pack(T_LONG_REP, 2, len);
+								if ((rep_mask & 8) && per_byte(hdr_r3 + lp, len, recip) == root && pk_pack(T_LONG_REP, 3, len) != excluded) last = pk_pack(T_LONG_REP, 3, len);
+							}
+						}
+						if (last != 0) {
+							fs->ent_pk[fs->store[0]] = last;
+							done = 1;
+						}
+					}
+					// the only tie of that lane was the excluded packet: fall back to the full replay
+					if (__shfl_sync(FULL, done, who)) pass = 0;
+					__syncwarp();
+				} else {
+					pass &= ~((1u << (__ffs((int)less) - 1)) - 1u);
+				}
+			}
 			// replay survivors in enumeration order: occurrence-major, length ascending,
 			// MATCH before LONG_REP 0..3 (packet_enumerator.c:47-54)
 			while (pass) {
