@@ -69,8 +69,10 @@ __device__ __forceinline__ void heap_sift_up(FindScratch* fs, uint32_t node)
 	}
 }
 
-// src/top_k_packet_finder.c:72-93,99-101.  Called by exactly one lane at a time.
-__device__ __forceinline__ void heap_offer(FindScratch* fs, uint32_t k, uint64_t pk, uint32_t price, uint64_t excluded)
+// src/top_k_packet_finder.c:72-93,99-101.  Called by exactly one lane at a time.  Deliberately
+// out of line: it is reached from a dozen places in the finder, and one copy keeps the finder
+// (and the annealing kernel around it) inside the instruction cache.
+__device__ __noinline__ void heap_offer(FindScratch* fs, uint32_t k, uint64_t pk, uint32_t price, uint64_t excluded)
 {
 	if (pk == excluded) return;
 	uint32_t count = fs->count;
@@ -233,6 +235,7 @@ __device__ __forceinline__ uint32_t warp_find(int lane, const uint16_t* probs, c
 			const bool full = fs->count >= k;
 			const uint32_t root = full ? fs->ent_price[fs->store[0]] : 0xffffffffu;
 			uint32_t cheapest = 0xffffffffu;
+			uint32_t live_lens = 0;  // bit (len-2): some candidate of that length is at or below the root
 			if (valid) {
 				uint32_t rep_hdr_best = 0xffffffffu;
 				if (rep_mask & 1) rep_hdr_best = min(rep_hdr_best, hdr_r0);
@@ -241,8 +244,12 @@ __device__ __forceinline__ uint32_t warp_find(int lane, const uint16_t* probs, c
 				if (rep_mask & 8) rep_hdr_best = min(rep_hdr_best, hdr_r3);
 				for (uint32_t len = 2; len <= L; len++) {
 					const uint32_t b = len == 2 ? base2 : len == 3 ? base3 : len == 4 ? base4 : base5;
-					cheapest = min(cheapest, per_byte(b + fs->len_price[0][len - 2], len, recip));
-					if (rep_mask) cheapest = min(cheapest, per_byte(rep_hdr_best + fs->len_price[1][len - 2], len, recip));
+					const uint32_t pm = per_byte(b + fs->len_price[0][len - 2], len, recip);
+					uint32_t pr = 0xffffffffu;
+					if (rep_mask) pr = per_byte(rep_hdr_best + fs->len_price[1][len - 2], len, recip);
+					cheapest = min(cheapest, min(pm, pr));
+					// lengths worth replaying (only meaningful while L <= 33, see the replay below)
+					if (min(pm, pr) <= root) live_lens |= 1u << ((len - 2) & 31);
 				}
 				candidates += (L - 1) * (1 + __popc(rep_mask));
 			}
@@ -298,7 +305,16 @@ __device__ __forceinline__ uint32_t warp_find(int lane, const uint16_t* probs, c
 				const int who = __ffs(pass) - 1;
 				pass &= pass - 1;
 				if (lane == who) {
+					// The root only falls while this lane replays, so lengths that were above it when
+					// the lane was priced can be skipped; heap_offer re-tests the rest against the
+					// live root.  (The bit set covers lengths 2..33; longer matches replay in full.)
+					uint32_t todo = L <= 33 ? live_lens : 0xffffffffu;
 					for (uint32_t len = 2; len <= L; len++) {
+						if (L <= 33) {
+							if (todo == 0) break;
+							len = 2 + (uint32_t)__ffs((int)todo) - 1;
+							todo &= todo - 1;
+						}
 						const uint32_t b = len == 2 ? base2 : len == 3 ? base3 : len == 4 ? base4 : base5;
 						heap_offer(fs, k, pk_pack(T_MATCH, dist, len), per_byte(b + fs->len_price[0][len - 2], len, recip),
 						           excluded);

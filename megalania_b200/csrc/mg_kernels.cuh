@@ -306,20 +306,22 @@ enum WalkResult { WALK_DONE = 0, WALK_NEED_FIND = 1, WALK_ERROR = 2 };
 // Returns WALK_NEED_FIND with `pending` = the failed LONG_REP (index forced to 3, neighbour.c:99-108)
 // when the caller has to pick a replacement from the top-k at k.pos.
 // k.t.bits only accumulates the EXCESS over 9 bits per packet; see walker_bits().
-template <int MODE, bool CKPT>
-__device__ __forceinline__ uint32_t walk(const WalkEnv& e, Walker& k, uint32_t stop_pos, uint32_t stop_pidx, CkSink& ck,
+// MODE is a run-time argument on purpose: the annealing kernel calls this from ONE site for all
+// three phases, which keeps its code (and instruction-cache footprint) a third of the size of
+// three specialised copies.  A walk that writes no checkpoints passes ck.next = 0xffffffff.
+__device__ __forceinline__ uint32_t walk(const uint32_t MODE, const WalkEnv& e, Walker& k, uint32_t stop_pos, uint32_t stop_pidx, CkSink& ck,
                                          EditLog* lg, uint32_t override_pos, uint64_t override_pk, uint64_t& pending,
                                          uint64_t& pending_old, uint32_t& err)
 {
 	for (;;) {
 		if (k.pos >= stop_pos || k.pos - k.delta == stop_pidx) return WALK_DONE;
-		if (CKPT && k.pos >= ck.next) walker_checkpoint(e, k, ck);
+		if (k.pos >= ck.next) walker_checkpoint(e, k, ck);
 		if (k.pos - k.w.base >= 32u) {
 			tally_flush(k.t);
 			window_seek(e.lane, k.w, e.slab, e.data, e.n, k.pos, e.wb_addr);
 		}
 		uint32_t limit = k.w.base + 32 < stop_pos ? k.w.base + 32 : stop_pos;
-		if (CKPT) limit = ck.next < limit ? ck.next : limit;
+		limit = ck.next < limit ? ck.next : limit;
 		if (stop_pidx != 0xffffffffu) {
 			// the packet index only drifts from the position on multi-byte packets (slow path)
 			const uint32_t stop_at = stop_pidx + k.delta;
@@ -479,10 +481,8 @@ __global__ void __launch_bounds__(CTA_THREADS) score_kernel(ScoreArgs a)
 	ck.written = 0;
 	uint64_t pending = 0, pending_old = 0;
 	uint32_t err = 0;
-	if (a.ck)
-		walk<WALK_PLAIN, true>(e, k, a.stop_pos, 0xffffffffu, ck, nullptr, 0xffffffffu, 0, pending, pending_old, err);
-	else
-		walk<WALK_PLAIN, false>(e, k, a.stop_pos, 0xffffffffu, ck, nullptr, 0xffffffffu, 0, pending, pending_old, err);
+	if (!a.ck) ck.next = 0xffffffffu;
+	walk(WALK_PLAIN, e, k, a.stop_pos, 0xffffffffu, ck, nullptr, 0xffffffffu, 0, pending, pending_old, err);
 	tally_flush(k.t);
 	if (!err && k.pos != a.stop_pos) err = ERR_NOT_BOUNDARY;
 	if (a.final_model) walker_store(e, k, a.final_model + s);
@@ -543,8 +543,9 @@ __global__ void __launch_bounds__(CTA_THREADS) topk_kernel(TopkArgs a)
 			else
 				walker_load(e, k, a.ck + (below - 1), &ws->bar, parity);
 			CkSink ck = {};
+			ck.next = 0xffffffffu;
 			uint64_t pending = 0, pending_old = 0;
-			walk<WALK_PLAIN, false>(e, k, qpos, 0xffffffffu, ck, nullptr, 0xffffffffu, 0, pending, pending_old, err);
+			walk(WALK_PLAIN, e, k, qpos, 0xffffffffu, ck, nullptr, 0xffffffffu, 0, pending, pending_old, err);
 			if (!err && k.pos != qpos) err = ERR_NOT_BOUNDARY;
 		}
 		uint32_t pops = 0;
@@ -662,63 +663,84 @@ __global__ void __launch_bounds__(CTA_THREADS, MG_ANNEAL_MIN_CTAS) anneal_kernel
 		ck.live = ck_live;
 		ck.nck = nck;
 		ck.stride = a.stride;
-		ck.next = (j0 + 1) * a.stride;
+		ck.next = 0xffffffffu;  // no checkpoints while the prefix is priced
 		ck.written = 0;
 		uint64_t pending = 0, pending_old = 0;
 		uint32_t err = 0;
 
-		// ---- prefix: neighbour.c:22-32 from the checkpoint instead of from byte 0 ----------
-		walk<WALK_PLAIN, false>(e, k, n, target, ck, nullptr, 0xffffffffu, 0, pending, pending_old, err);
-		if (err || k.pos >= n) {
-			st.err = err ? err : ERR_NOT_BOUNDARY;
-			break;
-		}
-
-		// ---- mutate: neighbour.c:119-152 ---------------------------------------------------
-		const uint32_t pos = k.pos;
-		if (pos - k.w.base >= 32u) {
-			tally_flush(k.t);
-			window_seek(lane, k.w, slab, a.data, n, pos, e.wb_addr);
-		}
-		const uint32_t meta0 = window_meta(k.w, pos);
-		const uint32_t dist0 = window_dist(k.w, pos);
-		const uint64_t first = pk_pack(meta_type(meta0), dist0, meta_len(meta0));
-		const uint32_t byte0 = meta_byte(meta0) & 0xff;
-		uint64_t newpk = 0;
-		uint64_t override_pk = 0;
+		// One proposal = a small state machine around ONE walk call site, ONE finder call site and
+		// ONE place that prices a packet chosen outside the walk:
+		//   phase 0  price the prefix up to the target packet (neighbour.c:22-32, from the
+		//            checkpoint instead of from byte 0), then mutate it (neighbour.c:119-152)
+		//   phase 1  repair + price the next three packets (neighbour.c:82-98, count < 4)
+		//   phase 2  repair + price the rest, writing fresh checkpoints
+		uint32_t phase = 0, mode = WALK_PLAIN, stop_pidx = target;
+		uint32_t pos = 0, byte0 = 0;       // the mutated packet's position and data byte
+		uint64_t first = 0, newpk = 0, override_pk = 0, excluded = 0;
 		uint32_t override_pos = 0xffffffffu;
-		// what the single find site below is asked to do: 0 nothing, 1 mutation pick, 2 repair pick
-		uint32_t want_find = 1;
-		bool pick_best = false;
-		if (pos + 1 < n && rng31(rng) % 2 == 0) {
-			const uint64_t second = slab[pos + 1];
-			const uint32_t ft = pk_type(first), flen = pk_len(first);
-			const uint32_t stype = pk_type(second), slen = pk_len(second), sdist = pk_dist(second);
-			if ((ft == T_LONG_REP || ft == T_MATCH) && flen > 2) {
-				newpk = PK_LITERAL;
-				override_pos = pos + 1;
-				override_pk = pk_pack(ft, pk_dist(first), flen - 1);
-				log_put(lane, lg, pos, newpk);
-				lg.dup_index = lg.stored;
-				log_put(lane, lg, pos + 1, override_pk);
-				lg.dup_pos = pos + 1;  // a later repair of this slot rewrites the entry in place
-				want_find = 0;
-			} else if ((ft == T_LITERAL || ft == T_SHORT_REP) && (stype == T_MATCH || stype == T_LONG_REP)) {
-				const int64_t src = (int64_t)pos - (int64_t)(stype == T_LONG_REP ? model_rep(walker_model(e, k), sdist & 3) : sdist);
-				if (slen < MAX_MATCH && src > 0 && byte0 == a.data[src - 1]) {
-					newpk = pk_pack(stype, sdist, slen + 1);
-					log_put(lane, lg, pos, newpk);
-					want_find = 0;
-				}
+		uint32_t want_find = 0;            // 1 mutation pick, 2 repair pick
+		bool pick_best = false, failed = false;
+		for (;;) {
+			const uint32_t res = walk(mode, e, k, n, stop_pidx, ck, &lg, override_pos, override_pk, pending, pending_old, err);
+			if (res == WALK_ERROR) {
+				st.err = err;
+				break;
 			}
-		}
+			if (res == WALK_NEED_FIND) {
+				pick_best = rng31(rng) % 4 == 0;  // neighbour.c:107
+				excluded = pending;
+				want_find = 2;
+			} else if (phase == 0) {
+				if (k.pos >= n) {
+					st.err = ERR_NOT_BOUNDARY;
+					break;
+				}
+				// ---- mutate ----------------------------------------------------------------------
+				pos = k.pos;
+				if (pos - k.w.base >= 32u) {
+					tally_flush(k.t);
+					window_seek(lane, k.w, slab, a.data, n, pos, e.wb_addr);
+				}
+				const uint32_t meta0 = window_meta(k.w, pos);
+				const uint32_t dist0 = window_dist(k.w, pos);
+				first = pk_pack(meta_type(meta0), dist0, meta_len(meta0));
+				byte0 = meta_byte(meta0) & 0xff;
+				want_find = 1;
+				excluded = first;
+				pick_best = false;
+				if (pos + 1 < n && rng31(rng) % 2 == 0) {
+					const uint64_t second = slab[pos + 1];
+					const uint32_t ft = pk_type(first), flen = pk_len(first);
+					const uint32_t stype = pk_type(second), slen = pk_len(second), sdist = pk_dist(second);
+					if ((ft == T_LONG_REP || ft == T_MATCH) && flen > 2) {
+						newpk = PK_LITERAL;
+						override_pos = pos + 1;
+						override_pk = pk_pack(ft, pk_dist(first), flen - 1);
+						log_put(lane, lg, pos, newpk);
+						lg.dup_index = lg.stored;
+						log_put(lane, lg, pos + 1, override_pk);
+						lg.dup_pos = pos + 1;  // a later repair of this slot rewrites the entry in place
+						want_find = 0;
+					} else if ((ft == T_LITERAL || ft == T_SHORT_REP) && (stype == T_MATCH || stype == T_LONG_REP)) {
+						const int64_t src =
+						    (int64_t)pos - (int64_t)(stype == T_LONG_REP ? model_rep(walker_model(e, k), sdist & 3) : sdist);
+						if (slen < MAX_MATCH && src > 0 && byte0 == a.data[src - 1]) {
+							newpk = pk_pack(stype, sdist, slen + 1);
+							log_put(lane, lg, pos, newpk);
+							want_find = 0;
+						}
+					}
+				}
+				ck.next = (j0 + 1) * a.stride;  // from here on the walk refreshes the checkpoints it passes
+			} else if (phase == 1) {
+				phase = 2;
+				mode = WALK_REPAIR;
+				stop_pidx = 0xffffffffu;
+				continue;
+			} else {
+				break;  // reached the end of the slab
+			}
 
-		// ---- the proposal body: at most one find per pass, walks in between -------------------
-		uint64_t excluded = first;
-		uint32_t phase = 0;  // 0: mutated packet pending, 1: repair head, 2: repair tail, 3: done
-		uint32_t head_stop = 0;
-		bool failed = false;
-		while (phase < 3) {
 			if (want_find) {
 				if (lane == 0) cs.finds++;
 				const uint32_t count = warp_find(lane, e.probs, sh->trans, sh->recip, &ws->fs, a.data, n, a.occ_start, a.occ,
@@ -746,47 +768,27 @@ __global__ void __launch_bounds__(CTA_THREADS, MG_ANNEAL_MIN_CTAS) anneal_kernel
 					log_put(lane, lg, pos, newpk);
 				} else {
 					// repair pick: the slot keeps the forced LONG_REP(3) if the finder is empty
-					const uint64_t now = have ? chosen : pending;
-					if (now != pending_old) log_put(lane, lg, k.pos, now);
-					newpk = now;
+					newpk = have ? chosen : pending;
+					if (newpk != pending_old) log_put(lane, lg, k.pos, newpk);
 				}
 				want_find = 0;
 			}
-			if (phase == 0 || newpk != 0) {
-				// price a packet chosen outside the walk: the mutated one or a repair pick
+
+			// ---- price a packet chosen outside the walk: the mutated one or a repair pick --------
+			{
 				const uint32_t type = pk_type(newpk), len = pk_len(newpk), dist = pk_dist(newpk);
 				Model m = walker_model(e, k);
 				if (!packet_ok(m, n, type, len, dist)) {
 					st.err = ERR_BAD_PACKET;
 					break;
 				}
-				if (k.pos >= ck.next) walker_checkpoint(e, k, ck);
 				const uint32_t byte = phase == 0 ? byte0 : a.data[k.pos];
 				walker_apply(e, k, m, type, len, dist, byte);
-				newpk = 0;
-				if (phase == 0) {
-					phase = 1;
-					head_stop = walker_pidx(k) + 3;
-				}
 			}
-			uint32_t res;
-			if (phase == 1) {
-				res = walk<WALK_REPAIR_HEAD, true>(e, k, n, head_stop, ck, &lg, override_pos, override_pk, pending, pending_old, err);
-				if (res == WALK_DONE) {
-					phase = 2;
-					continue;
-				}
-			} else {
-				res = walk<WALK_REPAIR, true>(e, k, n, 0xffffffffu, ck, &lg, 0xffffffffu, 0, pending, pending_old, err);
-				if (res == WALK_DONE) phase = 3;
-			}
-			if (res == WALK_NEED_FIND) {
-				pick_best = rng31(rng) % 4 == 0;  // neighbour.c:107
-				excluded = pending;
-				want_find = 2;
-			} else if (res == WALK_ERROR) {
-				st.err = err;
-				break;
+			if (phase == 0) {
+				phase = 1;
+				mode = WALK_REPAIR_HEAD;
+				stop_pidx = walker_pidx(k) + 3;
 			}
 		}
 		if (st.err) break;
