@@ -368,9 +368,9 @@ def main() -> None:
     ap.add_argument("--chains", type=int, default=0, help="chains per GPU (default: SMs x --warps-per-sm)")
     ap.add_argument("--warps-per-sm", type=int, default=32)
     ap.add_argument("--evals", type=int, default=1000, help="cap on successful evaluations per chain per step")
-    ap.add_argument("--packet-budget", type=int, default=4_000_000,
+    ap.add_argument("--packet-budget", type=int, default=8_000_000,
                     help="a chain ends its step after the evaluation that brings its priced packets to this many "
-                         "(time-boxed steps keep all warps busy; about 8 evaluations per chain per step at 1 MiB)")
+                         "(time-boxed steps keep all warps busy; about 16 evaluations per chain per step at 1 MiB)")
     ap.add_argument("--seed", type=int, default=1673551)
     ap.add_argument("--exchange-every", type=int, default=4, help="multi-GPU: best-slab broadcast every this many steps")
     ap.add_argument("--e2e-steps", type=int, default=2)

@@ -679,6 +679,24 @@ extern "C" MG_API int mg_anneal_create(mg_ctx* ctx, const mg_anneal_params* para
 	return MG_OK;
 }
 
+// dst[c * stride_bytes + ...] = src[...] for c in [0, copies): one kernel when everything is
+// 16-byte aligned, a memcpy per copy otherwise.
+static int replicate(mg_ctx* ctx, const void* src, void* dst, size_t bytes, size_t stride_bytes, uint32_t copies)
+{
+	if (copies == 0 || bytes == 0) return 0;
+	const bool aligned = (((uintptr_t)src | (uintptr_t)dst | bytes | stride_bytes) & 15) == 0;
+	if (aligned) {
+		const size_t words = bytes / 16;
+		replicate_kernel<<<grid_for(words, 256, ctx->sm_count * 16), 256, 0, ctx->stream>>>(
+		    static_cast<const uint4*>(src), static_cast<uint4*>(dst), words, stride_bytes / 16, copies);
+		CU(cudaGetLastError());
+		return 0;
+	}
+	for (uint32_t c = 0; c < copies; c++)
+		CU(cudaMemcpyAsync(static_cast<char*>(dst) + (size_t)c * stride_bytes, src, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+	return 0;
+}
+
 // Rescore + checkpoint chains [first, first+count) from their current device slabs.
 static int refresh_chains(mg_anneal* an, uint32_t first, uint32_t count, int adopt_cost, int reset_best)
 {
@@ -755,20 +773,19 @@ extern "C" MG_API int mg_anneal_set_slab(mg_anneal* an, uint32_t first, uint32_t
 		fill_literal_kernel<<<grid_for(n, 256, ctx->sm_count * 8), 256, 0, ctx->stream>>>(dst0, n);
 		CU(cudaGetLastError());
 	}
-	for (uint32_t c = 1; c < count; c++)
-		CU(cudaMemcpyAsync(dst0 + (size_t)c * n, dst0, n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+	if (int rc = replicate(ctx, dst0, dst0 + n, n * 8, n * 8, count - 1)) return rc;
 	if (an->d_bests && reset_best)
-		CU(cudaMemcpyAsync(an->d_bests + (size_t)first * n, dst0, (size_t)count * n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+		if (int rc = replicate(ctx, dst0, an->d_bests + (size_t)first * n, n * 8, n * 8, count)) return rc;
 	// identical slabs: score the first, replicate its checkpoints
 	if (int rc = refresh_chains(an, first, 1, adopt_cost, reset_best)) return rc;
 	if (count > 1) {
 		const size_t nck = an->nck;
-		for (uint32_t c = 1; c < count; c++) {
-			CU(cudaMemcpyAsync(an->d_ck + (size_t)(first + c) * 2 * nck, an->d_ck + (size_t)first * 2 * nck,
-			                   nck * sizeof(Record), cudaMemcpyDeviceToDevice, ctx->stream));
-			CU(cudaMemcpyAsync(an->d_ck_pidx + (size_t)(first + c) * 2 * nck, an->d_ck_pidx + (size_t)first * 2 * nck,
-			                   nck * 4, cudaMemcpyDeviceToDevice, ctx->stream));
-		}
+		if (int rc = replicate(ctx, an->d_ck + (size_t)first * 2 * nck, an->d_ck + (size_t)(first + 1) * 2 * nck,
+		                       nck * sizeof(Record), 2 * nck * sizeof(Record), count - 1))
+			return rc;
+		if (int rc = replicate(ctx, an->d_ck_pidx + (size_t)first * 2 * nck, an->d_ck_pidx + (size_t)(first + 1) * 2 * nck,
+		                       nck * 4, 2 * nck * 4, count - 1))
+			return rc;
 		CU(cudaMemsetAsync(an->d_ck_live + (size_t)first * nck, 0, (size_t)count * nck, ctx->stream));
 		std::vector<ChainState> st(count);
 		CU(cudaMemcpyAsync(st.data(), an->d_state + first, count * sizeof(ChainState), cudaMemcpyDeviceToHost, ctx->stream));

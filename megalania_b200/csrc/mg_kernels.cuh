@@ -1087,6 +1087,18 @@ __global__ void fill_literal_kernel(uint64_t* __restrict__ packed, size_t count)
 		packed[i] = PK_LITERAL;
 }
 
+// Copies one block of `words` 16-byte words to `copies` destinations `stride` words apart (slab,
+// checkpoint and index replication when many chains start from the same slab): one launch
+// instead of one cudaMemcpyAsync per chain.
+__global__ void replicate_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, size_t words, size_t stride,
+                                 uint32_t copies)
+{
+	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < words; i += (size_t)gridDim.x * blockDim.x) {
+		const uint4 v = src[i];
+		for (uint32_t c = 0; c < copies; c++) dst[(size_t)c * stride + i] = v;
+	}
+}
+
 // Every slot of a slab a chain may walk must be decodable on its own terms
 // (type, length, extent, absolute match distance).
 __global__ void validate_kernel(const uint64_t* __restrict__ packed, uint32_t n, uint32_t* bad)
