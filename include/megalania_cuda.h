@@ -148,6 +148,12 @@ typedef struct {
 	uint64_t packet_budget; /* 0 = none; else a chain also stops after the evaluation that brings the
 	                           packets it priced in this call to this many (time-boxed steps: every
 	                           warp then finishes at about the same moment whatever its suffix lengths) */
+	uint32_t no_early_exit; /* != 0: always price a proposal to the end of the slab.  By default a
+	                           proposal stops at the first checkpoint where its whole model (every
+	                           probability, automaton state, rep distances, position) is bit-identical
+	                           to the checkpoint the current slab left there: the rest is priced
+	                           exactly as for the current slab, so the full cost is still exact */
+	uint32_t reserved;
 } mg_anneal_run_params;
 #define MG_CONTINUE_EVALS 0xffffffffu
 
@@ -164,6 +170,7 @@ typedef struct {
 	uint64_t finder_candidates; /* candidates enumerated and priced */
 	uint64_t edits;            /* slab edits logged */
 	uint64_t log_overflows;    /* proposals abandoned because the edit log was full */
+	uint64_t rejoined;         /* proposals that stopped early at a re-joined checkpoint */
 	double kernel_ms;          /* device time of the launch(es), CUDA events */
 	uint32_t launches;         /* kernels launched by this call */
 } mg_anneal_stats;

@@ -52,13 +52,14 @@ class AnnealParams(C.Structure):
 class AnnealRunParams(C.Structure):
     _fields_ = [("evals", C.c_uint32), ("max_attempts", C.c_uint32), ("schedule", C.c_uint32),
                 ("step", C.c_uint32), ("num_iters", C.c_uint32), ("first_eval", C.c_uint32),
-                ("temperatures", C.POINTER(C.c_float)), ("packet_budget", C.c_uint64)]
+                ("temperatures", C.POINTER(C.c_float)), ("packet_budget", C.c_uint64), ("no_early_exit", C.c_uint32),
+                ("reserved", C.c_uint32)]
 
 
 class AnnealStats(C.Structure):
     _fields_ = [(name, C.c_uint64) for name in (
         "evals", "attempts", "accepted", "new_best", "packets_scored", "bits_scored", "slab_bytes_read",
-        "checkpoint_bytes", "finder_calls", "finder_candidates", "edits", "log_overflows")] + [
+        "checkpoint_bytes", "finder_calls", "finder_candidates", "edits", "log_overflows", "rejoined")] + [
         ("kernel_ms", C.c_double), ("launches", C.c_uint32)]
 
     def as_dict(self) -> dict:
@@ -280,7 +281,8 @@ class Annealer:
         _check(self._lib.mg_anneal_set_slab(self._h, first, count, ptr, int(adopt_cost), int(reset_best)))
 
     def run(self, evals: int, *, schedule: int = SCHEDULE_REFERENCE, step: int = 0, num_iters: int = 0,
-            first_eval: int = 0, max_attempts: int = 0, temperatures=None, packet_budget: int = 0) -> dict:
+            first_eval: int = 0, max_attempts: int = 0, temperatures=None, packet_budget: int = 0,
+            early_exit: bool = True) -> dict:
         temps = None
         tptr = None
         if temperatures is not None:
@@ -288,7 +290,8 @@ class Annealer:
             if temps.size != self.chains:
                 raise ValueError("one temperature per chain")
             tptr = temps.ctypes.data_as(C.POINTER(C.c_float))
-        rp = AnnealRunParams(evals, max_attempts, schedule, step, num_iters, first_eval, tptr, packet_budget)
+        rp = AnnealRunParams(evals, max_attempts, schedule, step, num_iters, first_eval, tptr, packet_budget,
+                             0 if early_exit else 1, 0)
         st = AnnealStats()
         _check(self._lib.mg_anneal_run(self._h, C.byref(rp), C.byref(st)))
         return st.as_dict()
@@ -336,7 +339,7 @@ def anneal_oneshot(ctx: Context, *, chains: int, evals: int, init: np.ndarray | 
     """Host buffers in, host buffers out: the call the end-to-end benchmark times."""
     lib = ctx._lib
     p = AnnealParams(chains, top_k, 0, 0, 1, 0, seed)
-    rp = AnnealRunParams(evals, 0, schedule, step, num_iters, 0, None, packet_budget)
+    rp = AnnealRunParams(evals, 0, schedule, step, num_iters, 0, None, packet_budget, 0, 0)
     st = AnnealStats()
     best = np.zeros(ctx.n, dtype=PACKET_DTYPE)
     cost = C.c_uint64(0)

@@ -251,7 +251,7 @@ static uint32_t default_stride(uint32_t n)
 
 // ---- cost -------------------------------------------------------------------------------------------
 static int score_device(mg_ctx* ctx, const uint64_t* d_slabs, uint32_t nslabs, uint32_t stop_pos, uint64_t* d_cost,
-                        uint32_t* d_count, uint32_t* d_err, Record* ck, uint32_t* ck_pos, uint32_t* ck_pidx,
+                        uint32_t* d_count, uint32_t* d_err, Record* ck, uint32_t* ck_pos, CkMeta* ck_meta,
                         uint32_t stride, uint32_t nslots, Record* final_model)
 {
 	ScoreArgs a;
@@ -265,7 +265,7 @@ static int score_device(mg_ctx* ctx, const uint64_t* d_slabs, uint32_t nslabs, u
 	a.out_err = d_err;
 	a.ck = ck;
 	a.ck_pos = ck_pos;
-	a.ck_pidx = ck_pidx;
+	a.ck_meta = ck_meta;
 	a.stride = stride;
 	a.nslots = nslots ? nslots : 1;
 	a.ck_chain_stride = a.nslots - 1;
@@ -538,7 +538,7 @@ struct mg_anneal {
 	uint64_t* d_slabs = nullptr;
 	uint64_t* d_bests = nullptr;
 	Record* d_ck = nullptr;
-	uint32_t* d_ck_pidx = nullptr;
+	CkMeta* d_ck_meta = nullptr;
 	uint8_t* d_ck_live = nullptr;
 	Edit* d_logs = nullptr;
 	Edit* d_journal = nullptr;
@@ -576,7 +576,7 @@ extern "C" MG_API size_t mg_anneal_chain_bytes(const mg_ctx* ctx, const mg_annea
 	const size_t nck = nslots > 1 ? nslots - 1 : 1;
 	size_t b = n * 8;
 	if (p.track_best) b += n * 8 + (size_t)JOURNAL_CAP * sizeof(Edit);
-	b += nck * 2 * (sizeof(Record) + 4) + nck;
+	b += nck * 2 * (sizeof(Record) + sizeof(CkMeta)) + nck;
 	b += (size_t)p.edit_log_capacity * sizeof(Edit);
 	b += sizeof(ChainState) + sizeof(ChainStats) + 4 + 4 + 8 + 4 + 4;
 	b += (size_t)p.trace_capacity * sizeof(TraceRec);
@@ -591,7 +591,7 @@ extern "C" MG_API void mg_anneal_destroy(mg_anneal* an)
 	cudaFree(an->d_slabs);
 	cudaFree(an->d_bests);
 	cudaFree(an->d_ck);
-	cudaFree(an->d_ck_pidx);
+	cudaFree(an->d_ck_meta);
 	cudaFree(an->d_ck_live);
 	cudaFree(an->d_logs);
 	cudaFree(an->d_journal);
@@ -636,7 +636,7 @@ extern "C" MG_API int mg_anneal_create(mg_ctx* ctx, const mg_anneal_params* para
 	A(an->d_slabs, C * n * 8);
 	if (p.track_best) A(an->d_bests, C * n * 8);
 	A(an->d_ck, C * 2 * nck * sizeof(Record));
-	A(an->d_ck_pidx, C * 2 * nck * 4);
+	A(an->d_ck_meta, C * 2 * nck * sizeof(CkMeta));
 	A(an->d_ck_live, C * nck);
 	A(an->d_logs, C * (size_t)p.edit_log_capacity * sizeof(Edit));
 	if (p.track_best) A(an->d_journal, C * (size_t)JOURNAL_CAP * sizeof(Edit));
@@ -720,7 +720,7 @@ static int refresh_chains(mg_anneal* an, uint32_t first, uint32_t count, int ado
 		a.out_err = an->d_err + c;
 		a.ck = an->d_ck + (size_t)c * 2 * nck;
 		a.ck_pos = nullptr;
-		a.ck_pidx = an->d_ck_pidx + (size_t)c * 2 * nck;
+		a.ck_meta = an->d_ck_meta + (size_t)c * 2 * nck;
 		a.stride = an->stride;
 		a.nslots = an->nslots;
 		a.ck_chain_stride = 0;
@@ -744,6 +744,7 @@ static int refresh_chains(mg_anneal* an, uint32_t first, uint32_t count, int ado
 	for (uint32_t i = 0; i < count; i++) {
 		if (err[i]) return fail(MG_ESLAB, "chain %u: %s", first + i, walk_error(err[i]));
 		st[i].cur_cost = adopt_cost ? cost[i] : 0;
+		st[i].slab_cost = cost[i];
 		st[i].live_count = live[i];
 		st[i].err = 0;
 		st[i].eval_index = 0;
@@ -783,8 +784,8 @@ extern "C" MG_API int mg_anneal_set_slab(mg_anneal* an, uint32_t first, uint32_t
 		if (int rc = replicate(ctx, an->d_ck + (size_t)first * 2 * nck, an->d_ck + (size_t)(first + 1) * 2 * nck,
 		                       nck * sizeof(Record), 2 * nck * sizeof(Record), count - 1))
 			return rc;
-		if (int rc = replicate(ctx, an->d_ck_pidx + (size_t)first * 2 * nck, an->d_ck_pidx + (size_t)(first + 1) * 2 * nck,
-		                       nck * 4, 2 * nck * 4, count - 1))
+		if (int rc = replicate(ctx, an->d_ck_meta + (size_t)first * 2 * nck, an->d_ck_meta + (size_t)(first + 1) * 2 * nck,
+		                       nck * sizeof(CkMeta), 2 * nck * sizeof(CkMeta), count - 1))
 			return rc;
 		CU(cudaMemsetAsync(an->d_ck_live + (size_t)first * nck, 0, (size_t)count * nck, ctx->stream));
 		std::vector<ChainState> st(count);
@@ -792,6 +793,7 @@ extern "C" MG_API int mg_anneal_set_slab(mg_anneal* an, uint32_t first, uint32_t
 		CU(cudaStreamSynchronize(ctx->stream));
 		for (uint32_t i = 1; i < count; i++) {
 			st[i].cur_cost = st[0].cur_cost;
+			st[i].slab_cost = st[0].slab_cost;
 			st[i].live_count = st[0].live_count;
 			st[i].err = 0;
 			st[i].eval_index = 0;
@@ -841,7 +843,7 @@ extern "C" MG_API int mg_anneal_run(mg_anneal* an, const mg_anneal_run_params* r
 	a.slabs = an->d_slabs;
 	a.bests = an->d_bests;
 	a.ck = an->d_ck;
-	a.ck_pidx = an->d_ck_pidx;
+	a.ck_meta = an->d_ck_meta;
 	a.ck_live = an->d_ck_live;
 	a.logs = an->d_logs;
 	a.journal = an->d_journal;
@@ -857,6 +859,7 @@ extern "C" MG_API int mg_anneal_run(mg_anneal* an, const mg_anneal_run_params* r
 	a.num_iters = run->num_iters ? run->num_iters : ctx->n;
 	a.first_eval = run->first_eval;
 	a.packet_budget = run->packet_budget;
+	a.early_exit = run->no_early_exit ? 0u : 1u;
 	a.temps = run->temperatures ? an->d_temps : nullptr;
 	if (an->nslots <= 1) {
 		// a single slot has no checkpoints: the kernel's nck is 0
@@ -891,6 +894,7 @@ extern "C" MG_API int mg_anneal_run(mg_anneal* an, const mg_anneal_run_params* r
 			stats->finder_candidates += cs[c].candidates;
 			stats->edits += cs[c].edits;
 			stats->log_overflows += cs[c].overflows;
+			stats->rejoined += cs[c].rejoined;
 		}
 		stats->kernel_ms = ms;
 		stats->launches = 1;
@@ -991,7 +995,7 @@ extern "C" MG_API int mg_anneal_swap_chains(mg_anneal* an, uint32_t x, uint32_t 
 	};
 	CU(swap_region(an->d_slabs + (size_t)x * n, an->d_slabs + (size_t)y * n, n * 8));
 	CU(swap_region(an->d_ck + (size_t)x * 2 * nck, an->d_ck + (size_t)y * 2 * nck, 2 * nck * sizeof(Record)));
-	CU(swap_region(an->d_ck_pidx + (size_t)x * 2 * nck, an->d_ck_pidx + (size_t)y * 2 * nck, 2 * nck * 4));
+	CU(swap_region(an->d_ck_meta + (size_t)x * 2 * nck, an->d_ck_meta + (size_t)y * 2 * nck, 2 * nck * sizeof(CkMeta)));
 	CU(swap_region(an->d_ck_live + (size_t)x * nck, an->d_ck_live + (size_t)y * nck, nck));
 	ChainState sx, sy;
 	CU(cudaStreamSynchronize(ctx->stream));
@@ -1000,8 +1004,10 @@ extern "C" MG_API int mg_anneal_swap_chains(mg_anneal* an, uint32_t x, uint32_t 
 	// the slab, its cost and live count move; generators and best records stay with the chain id
 	ChainState nx = sx, ny = sy;
 	nx.cur_cost = sy.cur_cost;
+	nx.slab_cost = sy.slab_cost;
 	nx.live_count = sy.live_count;
 	ny.cur_cost = sx.cur_cost;
+	ny.slab_cost = sx.slab_cost;
 	ny.live_count = sx.live_count;
 	nx.journal_count = ny.journal_count = 0;
 	nx.journal_overflow = ny.journal_overflow = 1;  // the best slabs stayed, the current ones moved

@@ -17,19 +17,19 @@ constexpr uint32_t RECIP_ENTRIES = 288;
 
 struct ChainStats {
 	unsigned long long evals, attempts, accepted, new_best, packets, bits, slab_bytes, ck_bytes, finds, candidates,
-	    edits, overflows;
+	    edits, overflows, rejoined;
 };
 
 struct ChainState {
 	uint64_t rng;
 	uint64_t cur_cost;
 	uint64_t best_cost;
+	uint64_t slab_cost;   // exact cost of the current slab (cur_cost may be 0 = "accept the first proposal")
 	uint32_t live_count;
 	uint32_t err;
 	uint32_t eval_index;  // successful evaluations since the chain's slab was last set
 	uint32_t journal_count;     // edits accepted since the best slab last equalled the current slab
 	uint32_t journal_overflow;  // != 0: the journal is incomplete, the next new best copies the whole slab
-	uint32_t pad;
 };
 constexpr uint32_t JOURNAL_CAP = 1024;
 
@@ -186,16 +186,29 @@ __device__ __forceinline__ WalkEnv make_env(int lane, WarpShared* ws, const CtaS
 	return e;
 }
 
+// Per-checkpoint bookkeeping kept beside the records, in DELTA form: cost and packets between the
+// previous checkpoint (or the start of the file) and this one.  Deltas stay valid for the
+// untouched tail when a proposal stops early (see walker_checkpoint), absolutes would not.
+struct CkMeta {
+	uint64_t dcost;
+	uint32_t dpidx;
+	uint32_t pos;
+};
+
 // Where checkpoints of the walk go (all null when the walk writes none)
 struct CkSink {
 	Record* ck;          // indexed by slot-1
-	uint32_t* ck_pos;    // optional
-	uint32_t* ck_pidx;   // optional
+	uint32_t* ck_pos;    // optional: absolute positions (top-k queries)
+	CkMeta* meta;        // optional
 	const uint8_t* live; // anneal: which of the two buffers is current per slot-1 (write the other); null = buffer 0
 	uint32_t nck;        // anneal: records per buffer
 	uint32_t stride;
 	uint32_t next;       // next position that triggers a checkpoint
 	uint32_t written;    // count, for stats
+	uint32_t last_pidx;  // packet index / cost at the previous checkpoint of this walk
+	uint64_t last_cost;
+	uint32_t test;       // != 0: compare each crossing with the chain's current checkpoint there
+	uint32_t converged;  // slot at which the model re-joined the current slab's trajectory (0 = not)
 };
 
 // The state a walk keeps in registers.  The rep distances stay in e.rec->rep[] (shared memory):
@@ -281,22 +294,76 @@ __device__ __forceinline__ void walker_store(const WalkEnv& e, const Walker& k, 
 	record_store(e.lane, e.rec, m, k.t.total, dst);
 }
 
+// Is the walking model, at a checkpoint crossing, bit-identical to the checkpoint the chain's
+// CURRENT slab left at the same slot (same position, automaton state, rep distances and all
+// probabilities)?  If so everything after this point is priced exactly as it was for the current
+// slab, and the proposal can stop here: an exact early exit, no approximation.
+__device__ __forceinline__ bool walker_rejoined(const WalkEnv& e, const Walker& k, const Record* old, uint32_t old_pos)
+{
+	if (old_pos != k.pos) return false;
+	if (old->ctx != k.ctx || old->rep[0] != e.rec->rep[0] || old->rep[1] != e.rec->rep[1] || old->rep[2] != e.rec->rep[2] ||
+	    old->rep[3] != e.rec->rep[3])
+		return false;
+	const uint32_t* mine = reinterpret_cast<const uint32_t*>(e.probs);
+	const uint32_t* theirs = reinterpret_cast<const uint32_t*>(old->probs);
+	constexpr uint32_t WORDS = (S_TOTAL + 1) / 2;
+	for (uint32_t base = 0; base < WORDS; base += 32) {  // uniform trip count: the vote needs every lane
+		const uint32_t i = base + (uint32_t)e.lane;
+		const bool differs = i < WORDS && mine[i] != theirs[i];
+		if (__any_sync(FULL, differs)) return false;
+	}
+	return true;
+}
+
 __device__ __forceinline__ void walker_checkpoint(const WalkEnv& e, Walker& k, CkSink& ck)
 {
 	tally_flush(k.t);
 	const uint32_t slot = k.pos / ck.stride;
-	const uint32_t buf = ck.live ? (ck.live[slot - 1] ^ 1u) : 0u;
+	const uint32_t cur = ck.live ? ck.live[slot - 1] : 0u;
+	const uint32_t buf = ck.live ? cur ^ 1u : 0u;
+	bool same = false;
+	if (ck.test) same = walker_rejoined(e, k, ck.ck + (size_t)cur * ck.nck + (slot - 1), ck.meta[(size_t)cur * ck.nck + (slot - 1)].pos);
 	walker_store(e, k, ck.ck + (size_t)buf * ck.nck + (slot - 1));
+	const uint32_t pidx = walker_pidx(k);
 	if (e.lane == 0) {
 		if (ck.ck_pos) ck.ck_pos[(size_t)buf * ck.nck + (slot - 1)] = k.pos;
-		if (ck.ck_pidx) ck.ck_pidx[(size_t)buf * ck.nck + (slot - 1)] = walker_pidx(k);
+		if (ck.meta) {
+			CkMeta m;
+			m.dcost = k.t.total - ck.last_cost;
+			m.dpidx = pidx - ck.last_pidx;
+			m.pos = k.pos;
+			ck.meta[(size_t)buf * ck.nck + (slot - 1)] = m;
+		}
 	}
+	ck.last_cost = k.t.total;
+	ck.last_pidx = pidx;
 	ck.next = (slot + 1) * ck.stride;
 	ck.written++;
+	if (same) ck.converged = slot;
+}
+
+// Sum of the deltas of the chain's CURRENT checkpoints 1..upto: absolute packet index and cost at
+// checkpoint `upto` (upto = 0: start of file).
+__device__ __forceinline__ void ck_absolute(int lane, const CkMeta* meta, const uint8_t* live, uint32_t nck, uint32_t upto,
+                                            uint32_t& pidx, uint64_t& cost)
+{
+	uint32_t p = 0;
+	uint64_t c = 0;
+	for (uint32_t i = (uint32_t)lane; i < upto; i += 32) {
+		const CkMeta m = meta[(size_t)live[i] * nck + i];
+		p += m.dpidx;
+		c += m.dcost;
+	}
+	for (int o = 16; o > 0; o >>= 1) {
+		p += __shfl_xor_sync(FULL, p, o);
+		c += __shfl_xor_sync(FULL, c, o);
+	}
+	pidx = p;
+	cost = c;
 }
 
 enum WalkMode { WALK_PLAIN = 0, WALK_REPAIR_HEAD = 1, WALK_REPAIR = 2 };
-enum WalkResult { WALK_DONE = 0, WALK_NEED_FIND = 1, WALK_ERROR = 2 };
+enum WalkResult { WALK_DONE = 0, WALK_NEED_FIND = 1, WALK_ERROR = 2, WALK_REJOINED = 3 };
 
 // Prices packets from k.pos until stop_pos bytes or packet index stop_pidx is reached.
 //   WALK_PLAIN        the slab as it is (neighbour.c:22-32, main.c:116-118)
@@ -315,7 +382,10 @@ __device__ __forceinline__ uint32_t walk(const uint32_t MODE, const WalkEnv& e, 
 {
 	for (;;) {
 		if (k.pos >= stop_pos || k.pos - k.delta == stop_pidx) return WALK_DONE;
-		if (k.pos >= ck.next) walker_checkpoint(e, k, ck);
+		if (k.pos >= ck.next) {
+			walker_checkpoint(e, k, ck);
+			if (ck.converged) return WALK_REJOINED;
+		}
 		if (k.pos - k.w.base >= 32u) {
 			tally_flush(k.t);
 			window_seek(e.lane, k.w, e.slab, e.data, e.n, k.pos, e.wb_addr);
@@ -450,7 +520,7 @@ struct ScoreArgs {
 	uint32_t* out_err;       // [nslabs]
 	Record* ck;              // [nslabs][nslots-1] or null
 	uint32_t* ck_pos;        // [nslabs][nslots-1] or null
-	uint32_t* ck_pidx;       // [nslabs][nslots-1] or null
+	CkMeta* ck_meta;         // [nslabs][nslots-1] or null
 	uint32_t stride, nslots;
 	uint32_t ck_chain_stride;  // records between consecutive slabs' checkpoint blocks
 	Record* final_model;     // [nslabs] model after the walk, or null
@@ -473,12 +543,16 @@ __global__ void __launch_bounds__(CTA_THREADS) score_kernel(ScoreArgs a)
 	CkSink ck;
 	ck.ck = a.ck ? a.ck + ckoff : nullptr;
 	ck.ck_pos = a.ck_pos ? a.ck_pos + ckoff : nullptr;
-	ck.ck_pidx = a.ck_pidx ? a.ck_pidx + ckoff : nullptr;
+	ck.meta = a.ck_meta ? a.ck_meta + ckoff : nullptr;
 	ck.live = nullptr;
 	ck.nck = 0;
 	ck.stride = a.stride;
 	ck.next = a.stride;
 	ck.written = 0;
+	ck.last_pidx = 0;
+	ck.last_cost = 0;
+	ck.test = 0;
+	ck.converged = 0;
 	uint64_t pending = 0, pending_old = 0;
 	uint32_t err = 0;
 	if (!a.ck) ck.next = 0xffffffffu;
@@ -587,7 +661,7 @@ struct AnnealArgs {
 	uint64_t* slabs;     // [chains][n]
 	uint64_t* bests;     // [chains][n] or null
 	Record* ck;          // [chains][2][nslots-1]
-	uint32_t* ck_pidx;   // [chains][2][nslots-1]
+	CkMeta* ck_meta;     // [chains][2][nslots-1]
 	uint8_t* ck_live;    // [chains][nslots-1] which of the two buffers is current
 	Edit* logs;          // [chains][log_cap]
 	Edit* journal;       // [chains][JOURNAL_CAP] or null (no best tracking)
@@ -599,6 +673,7 @@ struct AnnealArgs {
 	// run parameters
 	uint32_t evals, max_attempts, schedule, step, num_iters, first_eval;
 	unsigned long long packet_budget;
+	uint32_t early_exit;  // stop a proposal where its model re-joins the current slab's checkpoints
 	const float* temps;
 };
 
@@ -618,7 +693,7 @@ __global__ void __launch_bounds__(CTA_THREADS, MG_ANNEAL_MIN_CTAS) anneal_kernel
 	uint64_t* slab = a.slabs + (size_t)c * n;
 	const WalkEnv e = make_env(lane, ws, sh, slab, a.data, n);
 	Record* ck_base = a.ck + (size_t)c * 2 * nck;
-	uint32_t* ck_pidx = a.ck_pidx + (size_t)c * 2 * nck;
+	CkMeta* ck_meta = a.ck_meta + (size_t)c * 2 * nck;
 	uint8_t* ck_live = a.ck_live + (size_t)c * nck;
 	ChainState st = a.state[c];
 	uint64_t rng = st.rng;
@@ -626,7 +701,7 @@ __global__ void __launch_bounds__(CTA_THREADS, MG_ANNEAL_MIN_CTAS) anneal_kernel
 	// Counters live in shared memory and are touched by lane 0 only: lanes of a warp are not
 	// guaranteed to run in lockstep, so a read-modify-write by all of them could count twice.
 	ChainStats& cs = ws->stats;
-	if (lane == 0) cs = ChainStats{0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+	if (lane == 0) cs = ChainStats{0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 	unsigned long long packets_done = 0;  // uniform copy of cs.packets for the budget test
 	EditLog lg;
 	lg.e = a.logs + (size_t)c * a.log_cap;
@@ -645,26 +720,63 @@ __global__ void __launch_bounds__(CTA_THREADS, MG_ANNEAL_MIN_CTAS) anneal_kernel
 
 		// ---- pick the packet to mutate and the checkpoint to start from ------------------
 		const uint32_t target = rng31(rng) % st.live_count;  // neighbour.c:163
-		uint32_t below = 0;
-		for (uint32_t j = lane; j < nck; j += 32) below += ck_pidx[(size_t)ck_live[j] * nck + j] <= target ? 1u : 0u;
-		const uint32_t j0 = __reduce_add_sync(FULL, below);  // checkpoint slot to resume from (0 = start of file)
+		// last checkpoint whose packet index is <= target: running sums of the delta records
+		uint32_t j0 = 0, pidx0 = 0;
+		uint64_t cost0 = 0;
+		{
+			uint32_t carry_p = 0;
+			uint64_t carry_c = 0;
+			for (uint32_t base = 0; base < nck; base += 32) {
+				const uint32_t i = base + lane;
+				CkMeta mt = {0, 0, 0};
+				if (i < nck) mt = ck_meta[(size_t)ck_live[i] * nck + i];
+				uint32_t p = mt.dpidx;
+				uint64_t cc = mt.dcost;
+				for (int o = 1; o < 32; o <<= 1) {
+					const uint32_t tp = __shfl_up_sync(FULL, p, o);
+					const uint64_t tc = __shfl_up_sync(FULL, cc, o);
+					if (lane >= o) {
+						p += tp;
+						cc += tc;
+					}
+				}
+				p += carry_p;
+				cc += carry_c;
+				const uint32_t cnt = __popc(__ballot_sync(FULL, i < nck && p <= target));
+				if (cnt) {
+					j0 = base + cnt;
+					pidx0 = __shfl_sync(FULL, p, (int)cnt - 1);
+					cost0 = __shfl_sync(FULL, cc, (int)cnt - 1);
+				}
+				carry_p = __shfl_sync(FULL, p, 31);
+				carry_c = __shfl_sync(FULL, cc, 31);
+				if (cnt < 32) break;
+			}
+		}
 		Walker k;
 		if (j0 == 0) {
 			walker_init(e, k);
 		} else {
 			walker_load(e, k, ck_base + (size_t)ck_live[j0 - 1] * nck + (j0 - 1), &ws->bar, parity);
+			// the record's own counters date from the proposal that wrote it; the running sums are current
+			k.delta = k.pos - pidx0;
+			k.t.total = cost0;
 			if (lane == 0) cs.ck_bytes += sizeof(Record);
 		}
 		const uint32_t start_pos = k.pos, start_pidx = walker_pidx(k);
 		CkSink ck;
 		ck.ck = ck_base;
 		ck.ck_pos = nullptr;
-		ck.ck_pidx = ck_pidx;
+		ck.meta = ck_meta;
 		ck.live = ck_live;
 		ck.nck = nck;
 		ck.stride = a.stride;
 		ck.next = 0xffffffffu;  // no checkpoints while the prefix is priced
 		ck.written = 0;
+		ck.last_pidx = pidx0;
+		ck.last_cost = cost0;
+		ck.test = 0;
+		ck.converged = 0;
 		uint64_t pending = 0, pending_old = 0;
 		uint32_t err = 0;
 
@@ -686,6 +798,7 @@ __global__ void __launch_bounds__(CTA_THREADS, MG_ANNEAL_MIN_CTAS) anneal_kernel
 				st.err = err;
 				break;
 			}
+			if (res == WALK_REJOINED) break;
 			if (res == WALK_NEED_FIND) {
 				pick_best = rng31(rng) % 4 == 0;  // neighbour.c:107
 				excluded = pending;
@@ -736,6 +849,7 @@ __global__ void __launch_bounds__(CTA_THREADS, MG_ANNEAL_MIN_CTAS) anneal_kernel
 				phase = 2;
 				mode = WALK_REPAIR;
 				stop_pidx = 0xffffffffu;
+				ck.test = a.early_exit;  // from the fourth packet on the walk may re-join the current slab's trajectory
 				continue;
 			} else {
 				break;  // reached the end of the slab
@@ -818,8 +932,24 @@ __global__ void __launch_bounds__(CTA_THREADS, MG_ANNEAL_MIN_CTAS) anneal_kernel
 			continue;
 		}
 
+		// ---- the proposal's full cost ---------------------------------------------------------
+		// A walk that re-joined the current slab's trajectory at checkpoint `converged` prices the
+		// rest exactly as the current slab does: its cost and packet count are the current totals
+		// minus what the current slab had spent up to that checkpoint.
+		uint64_t cost = k.t.total;
+		uint32_t live_new = walker_pidx(k);
+		uint32_t flip_end = nck;  // checkpoints j0+1 .. flip_end were rewritten by this proposal
+		if (ck.converged) {
+			uint32_t old_pidx;
+			uint64_t old_cost;
+			ck_absolute(lane, ck_meta, ck_live, nck, ck.converged, old_pidx, old_cost);
+			cost += st.slab_cost - old_cost;
+			live_new += st.live_count - old_pidx;
+			flip_end = ck.converged;
+			if (lane == 0) cs.rejoined++;
+		}
+
 		// ---- accept / reject: main.c:86-96 ---------------------------------------------------
-		const uint64_t cost = k.t.total;
 		const uint32_t r = rng31(rng);
 		bool uphill;
 		if (a.schedule == 0) {
@@ -835,11 +965,12 @@ __global__ void __launch_bounds__(CTA_THREADS, MG_ANNEAL_MIN_CTAS) anneal_kernel
 		if (st.cur_cost == 0 || cost < st.cur_cost || uphill) {
 			flags |= 2;
 			st.cur_cost = cost;
-			st.live_count = walker_pidx(k);
+			st.slab_cost = cost;
+			st.live_count = live_new;
 			// commit the accept/reject buffer and the checkpoints written on the way
 			__syncwarp();
 			for (uint32_t i = lane; i < lg.stored; i += 32) slab[lg.e[i].pos] = lg.e[i].pk;
-			for (uint32_t j = j0 + lane; j < nck; j += 32) ck_live[j] ^= 1;
+			for (uint32_t j = j0 + lane; j < flip_end; j += 32) ck_live[j] ^= 1;
 			__syncwarp();
 			if (lane == 0) cs.accepted++;
 			// The best slab is kept in step with the current one through a journal of accepted

@@ -12,5 +12,5 @@ t=time.time(); an=mg.Annealer(ctx, chains, seed=5); an.set_slab(None); print("cr
 for it in range(3):
     t=time.time(); st=an.run(evals, packet_budget=budget, first_eval=mg.CONTINUE_EVALS); dt=time.time()-t
     print(it, "wall",round(dt,3),"kernel_ms",round(st['kernel_ms'],1),"evals/s",round(st['evals']/(st['kernel_ms']/1e3),1),
-      "bits/s %.3g"%(st['bits_scored']/(st['kernel_ms']/1e3)), "pk/eval",st['packets_scored']//max(1,st['attempts']), "att",st['attempts'],"acc",st['accepted'],"cand/find",st['finder_candidates']//max(1,st['finder_calls']), "finds", st['finder_calls'])
+      "bits/s %.3g"%(st['bits_scored']/(st['kernel_ms']/1e3)), "pk/eval",st['packets_scored']//max(1,st['attempts']), "att",st['attempts'],"acc",st['accepted'],"cand/find",st['finder_candidates']//max(1,st['finder_calls']), "finds", st["finder_calls"], "rejoined", st["rejoined"])
 cur,best=an.costs(); print("best", best.min(), "cur mean", cur.mean())
