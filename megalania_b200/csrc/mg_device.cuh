@@ -121,52 +121,106 @@ __device__ __forceinline__ uint32_t next_ctx(uint32_t ctx, uint32_t type)
 	return ctx < 7 ? 8 : 11;
 }
 
+// Shared-memory accessors with 32-bit shared addresses (LDS/STS without generic-address math).
+__device__ __forceinline__ uint32_t lds_u16(uint32_t addr)
+{
+	uint16_t v;
+	asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr) : "memory");
+	return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr)
+{
+	uint32_t v;
+	asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+	return v;
+}
+__device__ __forceinline__ uint32_t lds_u8(uint32_t addr)
+{
+	uint32_t v;
+	asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+	return v;
+}
+__device__ __forceinline__ void sts_u16(uint32_t addr, uint32_t v)
+{
+	asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((uint16_t)v) : "memory");
+}
+__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v)
+{
+	asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
+// Arrays in shared memory addressed by their 32-bit shared address.  Going through generic
+// pointers kept in structs made the compiler re-derive the shared window for every access
+// (8 % of the instructions executed on match-heavy slabs were cvta sequences).
+struct SmemU16 {
+	uint32_t a;
+	__device__ __forceinline__ uint32_t get(uint32_t i) const { return lds_u16(a + 2 * i); }
+	__device__ __forceinline__ void set(uint32_t i, uint32_t v) const { sts_u16(a + 2 * i, v); }
+};
+struct SmemU32 {
+	uint32_t a;
+	__device__ __forceinline__ uint32_t get(uint32_t i) const { return lds_u32(a + 4 * i); }
+	__device__ __forceinline__ void set(uint32_t i, uint32_t v) const { sts_u32(a + 4 * i, v); }
+};
+
 // Transition table, 4096 x u32, indexed by (bit << 11) | p:
 //   low 16 bits  = the adapted probability  (src/probability_model.c:5-15)
 //   high 16 bits = the price of coding `bit` at probability p (src/perplexity_encoder.c:6-10)
 // One shared-memory load replaces the price lookup plus the shift/add/select update.
-__device__ __forceinline__ void code_bit(uint16_t* probs, const uint32_t* trans, uint32_t slot, uint32_t bit11,
-                                         uint32_t& acc)
+__device__ __forceinline__ void code_bit(SmemU16 probs, SmemU32 trans, uint32_t slot, uint32_t bit11, uint32_t& acc)
 {
-	const uint32_t t = trans[probs[slot] | bit11];
+	const uint32_t t = trans.get(probs.get(slot) | bit11);
 	acc += t >> 16;
-	probs[slot] = (uint16_t)t;
+	probs.set(slot, t);
 }
 
-__device__ __forceinline__ uint32_t bit_price(const uint16_t* probs, const uint32_t* trans, uint32_t slot,
-                                              uint32_t bit)
+__device__ __forceinline__ uint32_t bit_price(SmemU16 probs, SmemU32 trans, uint32_t slot, uint32_t bit)
 {
-	return trans[probs[slot] | (bit << 11)] >> 16;
+	return trans.get(probs.get(slot) | (bit << 11)) >> 16;
 }
 
 // ---- lane -> (slot, bit) maps ----------------------------------------------------------------
-// Length coder (src/lzma_packet_encoder.c:42-63): rel 0 choice_1, rel 1 choice_2, rel 2..9 tree.
-__device__ __forceinline__ bool len_event(int rel, uint32_t base, uint32_t len, uint32_t& slot, uint32_t& bit)
+// Every lane has ONE role per packet kind, fixed at kernel start, and the maps below are pure
+// select arithmetic (no divergent branches): all lanes run the same instructions and the one
+// probability update that follows is issued once for the whole warp.  Lane order == the
+// reference's coding order, which the range-coder kernel relies on.
+//   LITERAL   : 0 is_match | 1..8 literal tree depth 0..7
+//   otherwise : 0 is_match | 1 is_rep | 2 is_rep_g0 | 3 is_rep0_long or is_rep_g1 | 4 is_rep_g2
+//               | 5 len choice_1 | 6 len choice_2 | 7..14 length tree | 15..20 pos-slot tree
+//               | 21..25 reverse tree (pos_coder or align; direct bits sit just before lane 21)
+// A slot is only ever touched from one lane: is_match 0, is_rep 1, ... length trees 5..14 (the match
+// and rep length coders are different slots), distance 15..25, literal tree 1..8.
+enum LaneGroup { G_HEADER = 0, G_CHOICE = 1, G_LENTREE = 2, G_SLOTTREE = 3, G_REVTREE = 4, G_NONE = 5 };
+constexpr int FIRST_REVTREE_LANE = 21;
+
+struct LaneRole {
+	uint32_t grp;  // LaneGroup for non-literal packets
+	uint32_t t;    // index inside the group
+};
+
+__device__ __forceinline__ LaneRole lane_role(int lane)
 {
-	uint32_t v = len - 2;
-	if (rel == 0) {
-		slot = base;
-		bit = v >= 8;
-		return true;
+	LaneRole r;
+	if (lane < 5) {
+		r.grp = G_HEADER;
+		r.t = (uint32_t)lane;
+	} else if (lane < 7) {
+		r.grp = G_CHOICE;
+		r.t = (uint32_t)lane - 5;
+	} else if (lane < 15) {
+		r.grp = G_LENTREE;
+		r.t = (uint32_t)lane - 7;
+	} else if (lane < 21) {
+		r.grp = G_SLOTTREE;
+		r.t = (uint32_t)lane - 15;
+	} else if (lane < 26) {
+		r.grp = G_REVTREE;
+		r.t = (uint32_t)lane - 21;
+	} else {
+		r.grp = G_NONE;
+		r.t = 0;
 	}
-	if (rel == 1) {
-		slot = base + 1;
-		bit = v >= 16;
-		return v >= 8;
-	}
-	if (rel < 2 || rel > 9) return false;
-	uint32_t t = (uint32_t)rel - 2;
-	if (v < 16) {
-		if (t >= 3) return false;
-		uint32_t w = v & 7;
-		slot = base + (v < 8 ? LEN_LOW : LEN_MID) + ((1u << t) | (w >> (3 - t)));
-		bit = (w >> (2 - t)) & 1;
-		return true;
-	}
-	uint32_t w = v - 16;
-	slot = base + LEN_HIGH + ((1u << t) | (w >> (8 - t)));
-	bit = (w >> (7 - t)) & 1;
-	return true;
+	return r;
 }
 
 struct DistParts {
@@ -200,25 +254,7 @@ __device__ __forceinline__ DistParts dist_parts(uint32_t dist)
 	return d;
 }
 
-// Distance coder: rel 0..5 pos-slot tree, rel 6..10 reverse tree (pos_coder or align).
-__device__ __forceinline__ bool dist_event(int rel, const DistParts& d, uint32_t lctx, uint32_t& slot, uint32_t& bit)
-{
-	if (rel < 0 || rel > 10) return false;
-	if (rel < 6) {
-		uint32_t t = (uint32_t)rel;
-		slot = S_POSSLOT + lctx * 64 + ((1u << t) | (d.pslot >> (6 - t)));
-		bit = (d.pslot >> (5 - t)) & 1;
-		return true;
-	}
-	uint32_t i = (uint32_t)rel - 6;
-	if (i >= d.rbits) return false;
-	uint32_t prefix = i ? (__brev(d.low & ((1u << i) - 1)) >> (32 - i)) : 0;
-	slot = d.rbase + ((1u << i) | prefix);
-	bit = (d.low >> i) & 1;
-	return true;
-}
-
-// Literal tree (src/lzma_packet_encoder.c:106-136): depth 0..7 on lanes 1..8.
+// Literal tree (src/lzma_packet_encoder.c:106-136): depth 0..7.
 __device__ __forceinline__ void lit_event(uint32_t depth, uint32_t byte, bool matched_mode, uint32_t mbyte,
                                           uint32_t& slot, uint32_t& bit)
 {
@@ -229,71 +265,96 @@ __device__ __forceinline__ void lit_event(uint32_t depth, uint32_t byte, bool ma
 	slot = S_LIT + node;
 }
 
-// Lane's event for a whole packet.  Lane order == the reference's coding order, which the
-// range-coder kernel relies on (direct bits sit between lanes 17 and 18 of a MATCH).
-//   LITERAL   : 0 is_match | 1..8 literal tree
-//   MATCH     : 0 is_match | 1 is_rep | 2..11 length | 12..17 pos slot | 18..22 reverse/align
-//   SHORT_REP : 0 is_match | 1 is_rep | 2 is_rep_g0 | 3 is_rep0_long
-//   LONG_REP  : 0 is_match | 1 is_rep | 2 g0 | 3 rep0_long or g1 | 4 g2 | 5..14 length
-__device__ __forceinline__ bool packet_event(int lane, uint32_t type, uint32_t len, uint32_t dist, uint32_t ctx,
-                                             uint32_t byte, uint32_t mbyte, const DistParts& dp, uint32_t& slot,
-                                             uint32_t& bit)
+// The length coder's three trees (src/lzma_packet_encoder.c:42-63) as one: nb bits of value w
+// under `tree`, after choice_1 / choice_2.
+struct LenParts {
+	uint32_t v, nb, w, tree;
+};
+__device__ __forceinline__ LenParts len_parts(uint32_t base, uint32_t len)
 {
+	LenParts l;
+	l.v = len - 2;
+	l.nb = l.v < 16 ? 3u : 8u;
+	l.w = l.v < 8 ? l.v : (l.v < 16 ? l.v - 8 : l.v - 16);
+	l.tree = base + (l.v < 8 ? LEN_LOW : l.v < 16 ? LEN_MID : LEN_HIGH);
+	return l;
+}
+
+// MATCH (src/lzma_packet_encoder.c:138-146): header, length, distance.
+__device__ __forceinline__ bool match_event(const LaneRole r, uint32_t ctx, uint32_t len, const DistParts& d,
+                                            uint32_t& slot, uint32_t& bit)
+{
+	const LenParts l = len_parts(S_LEN, len);
+	const uint32_t t = r.t;
+	// header: is_match = 1, is_rep = 0 (lanes 2..4 idle)
+	const uint32_t s_h = (t == 0 ? S_ISMATCH : S_ISREP) + ctx;
+	const uint32_t b_h = t == 0;
+	const bool a_h = t < 2;
+	// choice_1 / choice_2
+	const uint32_t s_c = S_LEN + t;
+	const uint32_t b_c = t == 0 ? l.v >= 8 : l.v >= 16;
+	const bool a_c = t == 0 || l.v >= 8;
+	// length tree
+	const uint32_t sh = l.nb > t ? l.nb - t : 0;
+	const uint32_t s_l = l.tree + ((1u << t) | (l.w >> sh));
+	const uint32_t b_l = (l.w >> (sh ? sh - 1 : 0)) & 1;
+	const bool a_l = t < l.nb;
+	// pos-slot tree under the length context
+	const uint32_t lctx = l.v < 3 ? l.v : 3;
+	const uint32_t ts = t < 5 ? t : 5;
+	const uint32_t s_s = S_POSSLOT + lctx * 64 + ((1u << ts) | (d.pslot >> (6 - ts)));
+	const uint32_t b_s = (d.pslot >> (5 - ts)) & 1;
+	// reverse tree: pos_coder for short distances, align for long ones
+	const uint32_t prefix = t ? (__brev(d.low & ((1u << t) - 1)) >> (32 - t)) : 0;
+	const uint32_t s_r = d.rbase + ((1u << t) | prefix);
+	const uint32_t b_r = (d.low >> t) & 1;
+	const bool a_r = t < d.rbits;
+	const uint32_t g = r.grp;
+	slot = g == G_HEADER ? s_h : g == G_CHOICE ? s_c : g == G_LENTREE ? s_l : g == G_SLOTTREE ? s_s : s_r;
+	bit = g == G_HEADER ? b_h : g == G_CHOICE ? b_c : g == G_LENTREE ? b_l : g == G_SLOTTREE ? b_s : b_r;
+	return g == G_HEADER ? a_h : g == G_CHOICE ? a_c : g == G_LENTREE ? a_l : g == G_SLOTTREE ? true : g == G_REVTREE ? a_r : false;
+}
+
+// SHORT_REP / LONG_REP (src/lzma_packet_encoder.c:148-167): header bits, then the rep length coder.
+__device__ __forceinline__ bool rep_event(const LaneRole r, uint32_t type, uint32_t ctx, uint32_t len, uint32_t idx,
+                                          uint32_t& slot, uint32_t& bit)
+{
+	const bool is_long = type == T_LONG_REP;
+	const LenParts l = len_parts(S_REPLEN, is_long ? len : 2);
+	const uint32_t t = r.t;
+	// header lanes: is_match 1 | is_rep 1 | g0 | rep0_long (short rep, long rep 0) or g1 | g2
+	const bool rep0 = !is_long || idx == 0;
+	const uint32_t base_h = t == 0 ? S_ISMATCH : t == 1 ? S_ISREP : t == 2 ? S_ISREPG0 : t == 3 ? (rep0 ? S_ISREP0LONG : S_ISREPG1) : S_ISREPG2;
+	const uint32_t s_h = base_h + ctx;
+	const uint32_t b_h = t < 2 ? 1u : t == 2 ? (is_long && idx != 0) : t == 3 ? (is_long && idx != 1) : idx != 2;
+	const bool a_h = t < 4 ? true : (is_long && idx >= 2);
+	const uint32_t s_c = S_REPLEN + t;
+	const uint32_t b_c = t == 0 ? l.v >= 8 : l.v >= 16;
+	const bool a_c = is_long && (t == 0 || l.v >= 8);
+	const uint32_t sh = l.nb > t ? l.nb - t : 0;
+	const uint32_t s_l = l.tree + ((1u << t) | (l.w >> sh));
+	const uint32_t b_l = (l.w >> (sh ? sh - 1 : 0)) & 1;
+	const bool a_l = is_long && t < l.nb;
+	const uint32_t g = r.grp;
+	slot = g == G_HEADER ? s_h : g == G_CHOICE ? s_c : s_l;
+	bit = g == G_HEADER ? b_h : g == G_CHOICE ? b_c : b_l;
+	return g == G_HEADER ? a_h : g == G_CHOICE ? a_c : g == G_LENTREE ? a_l : false;
+}
+
+// Lane's event for a whole packet of any type (the walk's general path, the range coder).
+__device__ __forceinline__ bool packet_event(int lane, const LaneRole r, uint32_t type, uint32_t len, uint32_t dist,
+                                             uint32_t ctx, uint32_t byte, uint32_t mbyte, const DistParts& dp,
+                                             uint32_t& slot, uint32_t& bit)
+{
+	if (type == T_MATCH) return match_event(r, ctx, len, dp, slot, bit);  // uniform branches: the type is
+	if (type != T_LITERAL) return rep_event(r, type, ctx, len, dist, slot, bit);  // the same on every lane
+	const uint32_t depth = lane >= 1 && lane <= 8 ? (uint32_t)lane - 1 : 0;
+	lit_event(depth, byte, ctx >= 7, mbyte, slot, bit);
 	if (lane == 0) {
 		slot = S_ISMATCH + ctx;
-		bit = type != T_LITERAL;
-		return true;
+		bit = 0;
 	}
-	if (type == T_LITERAL) {
-		if (lane > 8) return false;
-		lit_event((uint32_t)lane - 1, byte, ctx >= 7, mbyte, slot, bit);
-		return true;
-	}
-	if (lane == 1) {
-		slot = S_ISREP + ctx;
-		bit = type != T_MATCH;
-		return true;
-	}
-	if (type == T_MATCH) {
-		if (lane < 12) return len_event(lane - 2, S_LEN, len, slot, bit);
-		uint32_t lctx = len - 2 < 3 ? len - 2 : 3;
-		return dist_event(lane - 12, dp, lctx, slot, bit);
-	}
-	if (type == T_SHORT_REP) {
-		if (lane == 2) {
-			slot = S_ISREPG0 + ctx;
-			bit = 0;
-			return true;
-		}
-		if (lane == 3) {
-			slot = S_ISREP0LONG + ctx;
-			bit = 0;
-			return true;
-		}
-		return false;
-	}
-	// LONG_REP, dist = rep index
-	if (lane == 2) {
-		slot = S_ISREPG0 + ctx;
-		bit = dist != 0;
-		return true;
-	}
-	if (lane == 3) {
-		if (dist == 0) {
-			slot = S_ISREP0LONG + ctx;
-			bit = 1;
-		} else {
-			slot = S_ISREPG1 + ctx;
-			bit = dist != 1;
-		}
-		return true;
-	}
-	if (lane == 4) {
-		slot = S_ISREPG2 + ctx;
-		bit = dist != 2;
-		return dist >= 2;
-	}
-	return len_event(lane - 5, S_REPLEN, len, slot, bit);
+	return lane <= 8;
 }
 
 // src/lzma_state.c:59-81 + src/lzma_packet_encoder.c:192-193
@@ -323,7 +384,7 @@ __device__ __forceinline__ uint32_t model_rep(const Model& m, uint32_t idx)
 
 // Price + adapt one packet across the warp.  `byte` = data[pos]; mbyte only read when the packet
 // is a literal in matched mode.  Returns the number of modelled bits (uniform).
-__device__ __forceinline__ uint32_t apply_packet(int lane, uint16_t* probs, const uint32_t* trans, Model& m,
+__device__ __forceinline__ uint32_t apply_packet(int lane, SmemU16 probs, SmemU32 trans, Model& m,
                                                  uint32_t type, uint32_t len, uint32_t dist, uint32_t byte,
                                                  uint32_t mbyte, uint32_t& acc)
 {
@@ -331,43 +392,23 @@ __device__ __forceinline__ uint32_t apply_packet(int lane, uint16_t* probs, cons
 	dp.pslot = dp.nlow = dp.low = dp.rbase = dp.rbits = dp.direct = 0;
 	if (type == T_MATCH) dp = dist_parts(dist);
 	uint32_t slot = 0, bit = 0;
-	bool active = packet_event(lane, type, len, dist, m.ctx, byte, mbyte, dp, slot, bit);
+	bool active = packet_event(lane, lane_role(lane), type, len, dist, m.ctx, byte, mbyte, dp, slot, bit);
+	// Re-converge before the shared tail: without this the compiler clones the probability
+	// update and the model bookkeeping into every divergent lane group (measured: that tail ran
+	// with ~3 active lanes, about ten times per packet).
+	__syncwarp();
 	if (active) code_bit(probs, trans, slot, bit << 11, acc);
 	if (lane == 0) acc += dp.direct << 11;  // src/perplexity_encoder.c:12-17
 	model_advance(m, type, len, dist);
 	return __popc(__ballot_sync(FULL, active));
 }
 
-__device__ __forceinline__ void model_init(int lane, uint16_t* probs, Model& m)
+__device__ __forceinline__ void model_init(int lane, SmemU16 probs, Model& m)
 {
-	for (uint32_t i = (uint32_t)lane; i <= S_TOTAL; i += 32) probs[i] = 1024;
+	for (uint32_t i = (uint32_t)lane; i <= S_TOTAL; i += 32) probs.set(i, 1024);
 	m.pos = m.pidx = m.ctx = 0;
 	m.rep0 = m.rep1 = m.rep2 = m.rep3 = 0;
 	__syncwarp();
-}
-
-// Shared-memory accessors with 32-bit shared addresses (LDS/STS without generic-address math).
-__device__ __forceinline__ uint32_t lds_u16(uint32_t addr)
-{
-	uint16_t v;
-	asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr) : "memory");
-	return v;
-}
-__device__ __forceinline__ uint32_t lds_u32(uint32_t addr)
-{
-	uint32_t v;
-	asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
-	return v;
-}
-__device__ __forceinline__ uint32_t lds_u8(uint32_t addr)
-{
-	uint32_t v;
-	asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
-	return v;
-}
-__device__ __forceinline__ void sts_u16(uint32_t addr, uint32_t v)
-{
-	asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((uint16_t)v) : "memory");
 }
 
 // Window of 32 consecutive slab slots + data bytes held across the warp's registers, with the

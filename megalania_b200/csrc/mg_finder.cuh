@@ -29,9 +29,9 @@ struct FindScratch {
 };
 
 // floor(c / len) for c*len < 2^32 via one multiply: recip[len] = floor((2^32-1)/len) + 1
-__device__ __forceinline__ uint32_t per_byte(uint32_t cost, uint32_t len, const uint32_t* recip)
+__device__ __forceinline__ uint32_t per_byte(uint32_t cost, uint32_t len, SmemU32 recip)
 {
-	return len == 1 ? cost : __umulhi(cost, recip[len]);
+	return len == 1 ? cost : __umulhi(cost, recip.get(len));
 }
 
 __device__ __forceinline__ bool heap_gt(const FindScratch* fs, uint32_t a, uint32_t b)
@@ -92,7 +92,7 @@ __device__ __noinline__ void heap_offer(FindScratch* fs, uint32_t k, uint64_t pk
 	}
 }
 
-__device__ __forceinline__ uint32_t tree_price(const uint16_t* probs, const uint32_t* price, uint32_t base,
+__device__ __forceinline__ uint32_t tree_price(SmemU16 probs, SmemU32 price, uint32_t base,
                                                uint32_t nbits, uint32_t value)
 {
 	uint32_t c = 0, node = 1;
@@ -105,7 +105,7 @@ __device__ __forceinline__ uint32_t tree_price(const uint16_t* probs, const uint
 }
 
 // src/lzma_packet_encoder.c:42-63 priced from the pre-state
-__device__ __forceinline__ uint32_t length_price(const uint16_t* probs, const uint32_t* price, uint32_t base,
+__device__ __forceinline__ uint32_t length_price(SmemU16 probs, SmemU32 price, uint32_t base,
                                                  uint32_t len)
 {
 	uint32_t v = len - 2;
@@ -116,7 +116,7 @@ __device__ __forceinline__ uint32_t length_price(const uint16_t* probs, const ui
 }
 
 // Literal price at the model's position (src/lzma_packet_encoder.c:106-136)
-__device__ __forceinline__ uint32_t literal_price(const uint16_t* probs, const uint32_t* price, uint32_t ctx,
+__device__ __forceinline__ uint32_t literal_price(SmemU16 probs, SmemU32 price, uint32_t ctx,
                                                   uint32_t byte, uint32_t mbyte)
 {
 	uint32_t c = bit_price(probs, price, S_ISMATCH + ctx, 0);
@@ -129,7 +129,7 @@ __device__ __forceinline__ uint32_t literal_price(const uint16_t* probs, const u
 }
 
 // Distance price without the pos-slot tree: reverse/align tree + direct bits
-__device__ __forceinline__ uint32_t dist_tail_price(const uint16_t* probs, const uint32_t* price, const DistParts& d)
+__device__ __forceinline__ uint32_t dist_tail_price(SmemU16 probs, SmemU32 price, const DistParts& d)
 {
 	uint32_t c = d.direct << 11, node = 1, v = d.low;
 	for (uint32_t i = 0; i < d.rbits; i++) {
@@ -145,8 +145,8 @@ __device__ __forceinline__ uint32_t dist_tail_price(const uint16_t* probs, const
 // probs: the warp's live model (read only here).  Returns the candidate count kept;
 // fs->candidates receives how many candidates were enumerated.  The model is taken by value so
 // that the caller's copy stays in registers across this (deliberately out-of-line) call.
-__device__ __forceinline__ uint32_t warp_find(int lane, const uint16_t* probs, const uint32_t* price,
-                                           const uint32_t* recip, FindScratch* fs, const uint8_t* __restrict__ data,
+__device__ __forceinline__ uint32_t warp_find(int lane, SmemU16 probs, SmemU32 price,
+                                           SmemU32 recip, FindScratch* fs, const uint8_t* __restrict__ data,
                                            uint32_t n, const uint32_t* __restrict__ occ_start,
                                            const uint32_t* __restrict__ occ, const Model m, uint64_t excluded,
                                            uint32_t k)

@@ -148,8 +148,11 @@ __device__ __forceinline__ void log_put(int lane, EditLog& lg, uint32_t pos, uin
 // is branch-free across the warp.
 struct WalkEnv {
 	int lane;
-	uint16_t* probs;
-	const uint32_t* trans;
+	SmemU16 probs;        // the model's probabilities
+	SmemU32 trans;        // the CTA's transition table
+	SmemU32 recip;        // the CTA's reciprocal table
+	SmemU32 reps;         // rec->rep[4]
+	uint16_t* probs_ptr;  // generic pointer to the same probabilities (bulk compares only)
 	Record* rec;
 	const uint64_t* __restrict__ slab;
 	const uint8_t* __restrict__ data;
@@ -168,8 +171,11 @@ __device__ __forceinline__ WalkEnv make_env(int lane, WarpShared* ws, const CtaS
 {
 	WalkEnv e;
 	e.lane = lane;
-	e.probs = ws->rec.probs;
-	e.trans = sh->trans;
+	e.probs.a = smem_u32(ws->rec.probs);
+	e.trans.a = smem_u32(sh->trans);
+	e.recip.a = smem_u32(sh->recip);
+	e.reps.a = smem_u32(ws->rec.rep);
+	e.probs_ptr = ws->rec.probs;
 	e.rec = &ws->rec;
 	e.slab = slab;
 	e.data = data;
@@ -230,16 +236,16 @@ __device__ __forceinline__ Model walker_model(const WalkEnv& e, const Walker& k)
 	m.pos = k.pos;
 	m.pidx = k.pos - k.delta;
 	m.ctx = k.ctx;
-	m.rep0 = e.rec->rep[0];
-	m.rep1 = e.rec->rep[1];
-	m.rep2 = e.rec->rep[2];
-	m.rep3 = e.rec->rep[3];
+	m.rep0 = e.reps.get(0);
+	m.rep1 = e.reps.get(1);
+	m.rep2 = e.reps.get(2);
+	m.rep3 = e.reps.get(3);
 	return m;
 }
 
 __device__ __forceinline__ void walker_fetch_mb(const WalkEnv& e, Walker& k)
 {
-	const uint32_t rep0 = e.rec->rep[0];
+	const uint32_t rep0 = e.reps.get(0);
 	k.mb = (k.pos < e.n && rep0 < k.pos) ? e.data[k.pos - rep0 - 1] : 0;
 }
 
@@ -247,8 +253,8 @@ __device__ __forceinline__ void walker_init(const WalkEnv& e, Walker& k)
 {
 	Model m;
 	model_init(e.lane, e.probs, m);
-	if (e.lane < 4) e.rec->rep[e.lane] = 0;
-	if (e.lane == 0) e.probs[S_DUMMY] = 0;
+	if (e.lane < 4) e.reps.set(e.lane, 0);
+	if (e.lane == 0) e.probs.set(S_DUMMY, 0);
 	__syncwarp();
 	k.pos = k.delta = k.ctx = k.mb = 0;
 	k.t = {0, 0, 0};
@@ -279,10 +285,10 @@ __device__ __forceinline__ void walker_apply(const WalkEnv& e, Walker& k, Model&
 	k.ctx = m.ctx;
 	if (type == T_MATCH || type == T_LONG_REP) {
 		// every lane holds the same values; each writes them so that it can read them back unsynchronised
-		e.rec->rep[0] = m.rep0;
-		e.rec->rep[1] = m.rep1;
-		e.rec->rep[2] = m.rep2;
-		e.rec->rep[3] = m.rep3;
+		e.reps.set(0, m.rep0);
+		e.reps.set(1, m.rep1);
+		e.reps.set(2, m.rep2);
+		e.reps.set(3, m.rep3);
 		__syncwarp();  // lanes are not guaranteed to run in lockstep: order these stores before later reads
 	}
 	if (type != T_LITERAL) walker_fetch_mb(e, k);
@@ -304,7 +310,7 @@ __device__ __forceinline__ bool walker_rejoined(const WalkEnv& e, const Walker& 
 	if (old->ctx != k.ctx || old->rep[0] != e.rec->rep[0] || old->rep[1] != e.rec->rep[1] || old->rep[2] != e.rec->rep[2] ||
 	    old->rep[3] != e.rec->rep[3])
 		return false;
-	const uint32_t* mine = reinterpret_cast<const uint32_t*>(e.probs);
+	const uint32_t* mine = reinterpret_cast<const uint32_t*>(e.probs_ptr);
 	const uint32_t* theirs = reinterpret_cast<const uint32_t*>(old->probs);
 	constexpr uint32_t WORDS = (S_TOTAL + 1) / 2;
 	for (uint32_t base = 0; base < WORDS; base += 32) {  // uniform trip count: the vote needs every lane
@@ -624,7 +630,7 @@ __global__ void __launch_bounds__(CTA_THREADS) topk_kernel(TopkArgs a)
 		}
 		uint32_t pops = 0;
 		if (!err) {
-			pops = warp_find(lane, e.probs, sh->trans, sh->recip, &ws->fs, a.data, a.n, a.occ_start, a.occ,
+			pops = warp_find(lane, e.probs, e.trans, e.recip, &ws->fs, a.data, a.n, a.occ_start, a.occ,
 			                 walker_model(e, k), a.slab[qpos], a.k);
 			cand += ws->fs.candidates;
 			for (uint32_t i = lane; i < pops; i += 32) {
@@ -857,7 +863,7 @@ __global__ void __launch_bounds__(CTA_THREADS, MG_ANNEAL_MIN_CTAS) anneal_kernel
 
 			if (want_find) {
 				if (lane == 0) cs.finds++;
-				const uint32_t count = warp_find(lane, e.probs, sh->trans, sh->recip, &ws->fs, a.data, n, a.occ_start, a.occ,
+				const uint32_t count = warp_find(lane, e.probs, e.trans, e.recip, &ws->fs, a.data, n, a.occ_start, a.occ,
 				                                 walker_model(e, k), excluded, a.k);
 				if (lane == 0) cs.candidates += ws->fs.candidates;
 				uint64_t chosen = 0;
@@ -1136,7 +1142,7 @@ __global__ void __launch_bounds__(32) encode_kernel(EncodeArgs a)
 	__shared__ uint32_t wbytes[8];
 	const int lane = threadIdx.x;
 	Model m;
-	model_init(lane, rec.probs, m);
+	model_init(lane, SmemU16{smem_u32(rec.probs)}, m);
 	RangeCoder rc = {0, 0xFFFFFFFFu, 0, 1, a.out, a.cap, 0};
 	Window w;
 	w.base = WINDOW_NONE;
@@ -1156,7 +1162,7 @@ __global__ void __launch_bounds__(32) encode_kernel(EncodeArgs a)
 		dp.pslot = dp.nlow = dp.low = dp.rbase = dp.rbits = dp.direct = 0;
 		if (type == T_MATCH) dp = dist_parts(dist);
 		uint32_t slot = 0, bit = 0;
-		const bool active = packet_event(lane, type, len, dist, m.ctx, byte, mbyte, dp, slot, bit);
+		const bool active = packet_event(lane, lane_role(lane), type, len, dist, m.ctx, byte, mbyte, dp, slot, bit);
 		uint32_t word = 0;
 		if (active) {
 			uint32_t p = rec.probs[slot];
@@ -1168,13 +1174,13 @@ __global__ void __launch_bounds__(32) encode_kernel(EncodeArgs a)
 		uint32_t mask = __ballot_sync(FULL, active);
 		__syncwarp();
 		if (lane == 0) {
-			// lanes are in coding order; the direct bits of a far match sit before lane 18
+			// lanes are in coding order; the direct bits of a far match sit before the reverse-tree lanes
 			const uint32_t direct_val = dp.direct ? (dist & ((1u << dp.nlow) - 1)) >> 4 : 0;
 			bool direct_done = dp.direct == 0;
 			while (mask) {
 				const int l = __ffs(mask) - 1;
 				mask &= mask - 1;
-				if (!direct_done && l >= 18) {
+				if (!direct_done && l >= FIRST_REVTREE_LANE) {
 					rc_direct(rc, direct_val, dp.direct);
 					direct_done = true;
 				}
