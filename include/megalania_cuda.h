@@ -153,7 +153,15 @@ typedef struct {
 	                           probability, automaton state, rep distances, position) is bit-identical
 	                           to the checkpoint the current slab left there: the rest is priced
 	                           exactly as for the current slab, so the full cost is still exact */
-	uint32_t reserved;
+	uint32_t suspend;       /* != 0 (needs packet_budget): the budget is exact.  A proposal that crosses it is
+	                           suspended at the next checkpoint it writes and carried on by the next
+	                           mg_anneal_run on the same chains, so every warp ends a step at the same
+	                           moment even when one evaluation is a large part of the step (1 MiB slabs).
+	                           Trajectories do not depend on where proposals are suspended.  Replacing a
+	                           chain's slab (set_slab, swap, broadcast) drops its suspended proposal */
+	uint64_t cycle_budget;  /* 0 = none; else SM clocks after which the chains stop: at the end of the evaluation
+	                           in flight, or (with suspend) at the next checkpoint it writes.  A wall-clock box:
+	                           how many evaluations fit is not reproducible, each chain's trajectory still is */
 } mg_anneal_run_params;
 #define MG_CONTINUE_EVALS 0xffffffffu
 
@@ -171,6 +179,10 @@ typedef struct {
 	uint64_t edits;            /* slab edits logged */
 	uint64_t log_overflows;    /* proposals abandoned because the edit log was full */
 	uint64_t rejoined;         /* proposals that stopped early at a re-joined checkpoint */
+	uint64_t finder_cycles;    /* SM clocks spent inside the match finder, summed over chains */
+	uint64_t chain_cycles;     /* SM clocks each chain's warp was busy, summed over chains */
+	uint64_t finder_chunks;    /* 32-occurrence steps of the match finder */
+	uint64_t max_chain_cycles; /* the longest-running chain: chain_cycles / (chains * this) = how evenly the step ended */
 	double kernel_ms;          /* device time of the launch(es), CUDA events */
 	uint32_t launches;         /* kernels launched by this call */
 } mg_anneal_stats;

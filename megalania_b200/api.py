@@ -53,13 +53,14 @@ class AnnealRunParams(C.Structure):
     _fields_ = [("evals", C.c_uint32), ("max_attempts", C.c_uint32), ("schedule", C.c_uint32),
                 ("step", C.c_uint32), ("num_iters", C.c_uint32), ("first_eval", C.c_uint32),
                 ("temperatures", C.POINTER(C.c_float)), ("packet_budget", C.c_uint64), ("no_early_exit", C.c_uint32),
-                ("reserved", C.c_uint32)]
+                ("suspend", C.c_uint32), ("cycle_budget", C.c_uint64)]
 
 
 class AnnealStats(C.Structure):
     _fields_ = [(name, C.c_uint64) for name in (
         "evals", "attempts", "accepted", "new_best", "packets_scored", "bits_scored", "slab_bytes_read",
-        "checkpoint_bytes", "finder_calls", "finder_candidates", "edits", "log_overflows", "rejoined")] + [
+        "checkpoint_bytes", "finder_calls", "finder_candidates", "edits", "log_overflows", "rejoined", "finder_cycles", "chain_cycles",
+        "finder_chunks", "max_chain_cycles")] + [
         ("kernel_ms", C.c_double), ("launches", C.c_uint32)]
 
     def as_dict(self) -> dict:
@@ -282,7 +283,7 @@ class Annealer:
 
     def run(self, evals: int, *, schedule: int = SCHEDULE_REFERENCE, step: int = 0, num_iters: int = 0,
             first_eval: int = 0, max_attempts: int = 0, temperatures=None, packet_budget: int = 0,
-            early_exit: bool = True) -> dict:
+            early_exit: bool = True, suspend: bool = False, cycle_budget: int = 0) -> dict:
         temps = None
         tptr = None
         if temperatures is not None:
@@ -291,7 +292,7 @@ class Annealer:
                 raise ValueError("one temperature per chain")
             tptr = temps.ctypes.data_as(C.POINTER(C.c_float))
         rp = AnnealRunParams(evals, max_attempts, schedule, step, num_iters, first_eval, tptr, packet_budget,
-                             0 if early_exit else 1, 0)
+                             0 if early_exit else 1, int(suspend), cycle_budget)
         st = AnnealStats()
         _check(self._lib.mg_anneal_run(self._h, C.byref(rp), C.byref(st)))
         return st.as_dict()
@@ -339,7 +340,7 @@ def anneal_oneshot(ctx: Context, *, chains: int, evals: int, init: np.ndarray | 
     """Host buffers in, host buffers out: the call the end-to-end benchmark times."""
     lib = ctx._lib
     p = AnnealParams(chains, top_k, 0, 0, 1, 0, seed)
-    rp = AnnealRunParams(evals, 0, schedule, step, num_iters, 0, None, packet_budget, 0, 0)
+    rp = AnnealRunParams(evals, 0, schedule, step, num_iters, 0, None, packet_budget, 0, 0, 0)
     st = AnnealStats()
     best = np.zeros(ctx.n, dtype=PACKET_DTYPE)
     cost = C.c_uint64(0)

@@ -748,6 +748,7 @@ static int refresh_chains(mg_anneal* an, uint32_t first, uint32_t count, int ado
 		st[i].live_count = live[i];
 		st[i].err = 0;
 		st[i].eval_index = 0;
+		st[i].susp_slot = 0;  // a suspended proposal belongs to the slab that was replaced
 		st[i].journal_count = 0;
 		st[i].journal_overflow = reset_best ? 0 : 1;  // best slab == current slab only right after a reset
 		if (reset_best) st[i].best_cost = 0;
@@ -797,6 +798,8 @@ extern "C" MG_API int mg_anneal_set_slab(mg_anneal* an, uint32_t first, uint32_t
 			st[i].live_count = st[0].live_count;
 			st[i].err = 0;
 			st[i].eval_index = 0;
+			st[i].susp_slot = 0;
+		st[i].susp_slot = 0;  // a suspended proposal belongs to the slab that was replaced
 			st[i].journal_count = 0;
 			st[i].journal_overflow = reset_best ? 0 : 1;
 			if (reset_best) st[i].best_cost = 0;
@@ -860,6 +863,8 @@ extern "C" MG_API int mg_anneal_run(mg_anneal* an, const mg_anneal_run_params* r
 	a.first_eval = run->first_eval;
 	a.packet_budget = run->packet_budget;
 	a.early_exit = run->no_early_exit ? 0u : 1u;
+	a.suspend = run->suspend ? 1u : 0u;
+	a.cycle_budget = run->cycle_budget;
 	a.temps = run->temperatures ? an->d_temps : nullptr;
 	if (an->nslots <= 1) {
 		// a single slot has no checkpoints: the kernel's nck is 0
@@ -895,6 +900,10 @@ extern "C" MG_API int mg_anneal_run(mg_anneal* an, const mg_anneal_run_params* r
 			stats->edits += cs[c].edits;
 			stats->log_overflows += cs[c].overflows;
 			stats->rejoined += cs[c].rejoined;
+			stats->finder_cycles += cs[c].find_cycles;
+			stats->finder_chunks += cs[c].chunks;
+			stats->chain_cycles += cs[c].chain_cycles;
+			if (cs[c].chain_cycles > stats->max_chain_cycles) stats->max_chain_cycles = cs[c].chain_cycles;
 		}
 		stats->kernel_ms = ms;
 		stats->launches = 1;
@@ -1010,6 +1019,7 @@ extern "C" MG_API int mg_anneal_swap_chains(mg_anneal* an, uint32_t x, uint32_t 
 	ny.slab_cost = sx.slab_cost;
 	ny.live_count = sx.live_count;
 	nx.journal_count = ny.journal_count = 0;
+	nx.susp_slot = ny.susp_slot = 0;  // suspended proposals do not move with the slabs: dropped
 	nx.journal_overflow = ny.journal_overflow = 1;  // the best slabs stayed, the current ones moved
 	CU(cudaMemcpy(an->d_state + x, &nx, sizeof(ChainState), cudaMemcpyHostToDevice));
 	CU(cudaMemcpy(an->d_state + y, &ny, sizeof(ChainState), cudaMemcpyHostToDevice));

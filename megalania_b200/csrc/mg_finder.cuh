@@ -21,11 +21,12 @@ struct FindScratch {
 	uint64_t ent_pk[MAX_K];
 	uint32_t ent_price[MAX_K];
 	uint32_t len_price[2][MAX_MATCH - 1];  // [0] match lengths, [1] rep lengths; index len-2
-	uint8_t store[MAX_K];                  // heap order -> entry index
+	uint32_t hkey[MAX_K];                  // heap order -> price << 5 | entry index
 	uint8_t pop_order[MAX_K];              // entry indices, worst first
 	uint32_t count;
 	uint32_t pops;
 	uint32_t candidates;  // candidates enumerated by the last find
+	uint32_t chunks;      // 32-occurrence steps the last find took (its cost in the step budget)
 };
 
 // floor(c / len) for c*len < 2^32 via one multiply: recip[len] = floor((2^32-1)/len) + 1
@@ -34,39 +35,43 @@ __device__ __forceinline__ uint32_t per_byte(uint32_t cost, uint32_t len, SmemU3
 	return len == 1 ? cost : __umulhi(cost, recip.get(len));
 }
 
-__device__ __forceinline__ bool heap_gt(const FindScratch* fs, uint32_t a, uint32_t b)
-{
-	return fs->ent_price[a] > fs->ent_price[b];
-}
+// The heap order lives in hkey[]: heap position -> (price << 5) | entry index, so a sift compares
+// one word per node (prices are below 2^20: a packet costs at most ~5.5e5).
+// "Hole" form of the reference's swap loops: the moving element is written once, at its final place.
 
-// src/max_heap.c:82-105
-__device__ __forceinline__ void heap_sift_down(FindScratch* fs, uint32_t parent)
+// src/max_heap.c:82-105 (left child preferred on ties, strict comparisons)
+__device__ __forceinline__ void heap_sink(FindScratch* fs, uint32_t p, uint32_t key, uint32_t count)
 {
-	uint32_t count = fs->count;
+	const uint32_t price = key >> 5;
 	for (;;) {
-		uint32_t l = parent * 2 + 1, r = l + 1;
+		const uint32_t l = 2 * p + 1;
 		if (l >= count) break;
-		uint32_t big = l;
-		if (r < count && heap_gt(fs, fs->store[r], fs->store[l])) big = r;
-		if (!heap_gt(fs, fs->store[big], fs->store[parent])) break;
-		uint8_t t = fs->store[big];
-		fs->store[big] = fs->store[parent];
-		fs->store[parent] = t;
-		parent = big;
+		const uint32_t kl = fs->hkey[l];
+		const uint32_t kr = l + 1 < count ? fs->hkey[l + 1] : 0u;
+		uint32_t big = l, kb = kl;
+		if ((kr >> 5) > (kl >> 5)) {
+			big = l + 1;
+			kb = kr;
+		}
+		if ((kb >> 5) <= price) break;
+		fs->hkey[p] = kb;
+		p = big;
 	}
+	fs->hkey[p] = key;
 }
 
 // src/max_heap.c:107-121
-__device__ __forceinline__ void heap_sift_up(FindScratch* fs, uint32_t node)
+__device__ __forceinline__ void heap_rise(FindScratch* fs, uint32_t p, uint32_t key)
 {
-	while (node > 0) {
-		uint32_t parent = (node - 1) / 2;
-		if (!heap_gt(fs, fs->store[node], fs->store[parent])) break;
-		uint8_t t = fs->store[node];
-		fs->store[node] = fs->store[parent];
-		fs->store[parent] = t;
-		node = parent;
+	const uint32_t price = key >> 5;
+	while (p > 0) {
+		const uint32_t parent = (p - 1) / 2;
+		const uint32_t kp = fs->hkey[parent];
+		if (price <= (kp >> 5)) break;
+		fs->hkey[p] = kp;
+		p = parent;
 	}
+	fs->hkey[p] = key;
 }
 
 // src/top_k_packet_finder.c:72-93,99-101.  Called by exactly one lane at a time.  Deliberately
@@ -75,20 +80,20 @@ __device__ __forceinline__ void heap_sift_up(FindScratch* fs, uint32_t node)
 __device__ __noinline__ void heap_offer(FindScratch* fs, uint32_t k, uint64_t pk, uint32_t price, uint64_t excluded)
 {
 	if (pk == excluded) return;
-	uint32_t count = fs->count;
+	const uint32_t count = fs->count;
 	if (count < k) {
 		fs->ent_pk[count] = pk;
 		fs->ent_price[count] = price;
-		fs->store[count] = (uint8_t)count;
 		fs->count = count + 1;
-		heap_sift_up(fs, count);
+		heap_rise(fs, count, (price << 5) | count);
 		return;
 	}
-	uint32_t top = fs->store[0];
-	if (price <= fs->ent_price[top]) {
-		fs->ent_pk[top] = pk;
-		fs->ent_price[top] = price;
-		heap_sift_down(fs, 0);
+	const uint32_t top = fs->hkey[0];
+	if (price <= (top >> 5)) {
+		const uint32_t en = top & 31u;
+		fs->ent_pk[en] = pk;
+		fs->ent_price[en] = price;
+		heap_sink(fs, 0, (price << 5) | en, count);
 	}
 }
 
@@ -141,17 +146,26 @@ __device__ __forceinline__ uint32_t dist_tail_price(SmemU16 probs, SmemU32 price
 	return c;
 }
 
+// Four bytes at any address, from the two aligned words around it (the input is padded, see
+// mg_ctx_create): match extension compares a word per step instead of a byte.
+__device__ __forceinline__ uint32_t load_u32_unaligned(const uint8_t* __restrict__ p)
+{
+	const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+	const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+	return __funnelshift_r(w[0], w[1], (uint32_t)(a & 3) * 8);
+}
+
 // Fills fs with the top-k of position m.pos and pops them (fs->pop_order, worst first).
 // probs: the warp's live model (read only here).  Returns the candidate count kept;
 // fs->candidates receives how many candidates were enumerated.  The model is taken by value so
 // that the caller's copy stays in registers across this (deliberately out-of-line) call.
-__device__ __forceinline__ uint32_t warp_find(int lane, SmemU16 probs, SmemU32 price,
+__device__ __noinline__ uint32_t warp_find(int lane, SmemU16 probs, SmemU32 price,
                                            SmemU32 recip, FindScratch* fs, const uint8_t* __restrict__ data,
                                            uint32_t n, const uint32_t* __restrict__ occ_start,
                                            const uint32_t* __restrict__ occ, const Model m, uint64_t excluded,
                                            uint32_t k)
 {
-	uint32_t candidates = 0;
+	uint32_t candidates = 0, chunks = 0;
 	__syncwarp();
 	const uint32_t pos = m.pos, ctx = m.ctx;
 	if (lane == 0) {
@@ -189,16 +203,38 @@ __device__ __forceinline__ uint32_t warp_find(int lane, SmemU16 probs, SmemU32 p
 		const uint32_t begin = occ_start[key], end = occ_start[key + 1];
 		const uint32_t max_len = n - pos < MAX_MATCH ? n - pos : MAX_MATCH;
 		uint32_t have_len[2] = {1, 1};  // len_price filled for lengths 2..have_len
+		uint32_t min_lp[2] = {0xffffffffu, 0xffffffffu};  // cheapest length price filled so far
+		uint32_t slot_cached = 0xffffffffu, slot_price2 = 0, slot_price3 = 0, slot_price4 = 0, slot_price5 = 0;
+		// align tree prices (src/lzma_packet_encoder.c:97-102): value i on lane i
+		DistParts ap;
+		ap.pslot = 14;
+		ap.nlow = 4;
+		ap.low = (uint32_t)lane & 15;
+		ap.rbase = S_ALIGN;
+		ap.rbits = 4;
+		ap.direct = 0;
+		const uint32_t align_tab = dist_tail_price(probs, price, ap);
 		for (uint32_t chunk = begin; chunk < end; chunk += 32) {
 			const uint32_t idx = chunk + (uint32_t)lane;
 			const uint32_t o = idx < end ? occ[idx] : 0xffffffffu;
 			const bool valid = o < pos;  // ascending bucket: stop at the first occurrence >= pos
 			const uint32_t valid_mask = __ballot_sync(FULL, valid);
 			if (valid_mask == 0) break;
+			chunks++;
 			uint32_t L = 0;
 			if (valid) {
 				L = 2;
-				while (L < max_len && data[pos + L] == data[o + L]) L++;
+				const uint8_t* q = data + pos;
+				const uint8_t* r = data + o;
+				while (L < max_len) {
+					const uint32_t x = load_u32_unaligned(q + L) ^ load_u32_unaligned(r + L);
+					if (x) {
+						L += ((uint32_t)__ffs((int)x) - 1u) >> 3;
+						break;
+					}
+					L += 4;
+				}
+				L = L < max_len ? L : max_len;
 			}
 			const uint32_t dist = pos - o - 1;
 			uint32_t rep_mask = 0;
@@ -210,30 +246,54 @@ __device__ __forceinline__ uint32_t warp_find(int lane, SmemU16 probs, SmemU32 p
 			const uint32_t need0 = __reduce_max_sync(FULL, L);
 			const uint32_t need1 = __reduce_max_sync(FULL, rep_mask ? L : 0u);
 			if (need0 > have_len[0]) {
-				for (uint32_t l = have_len[0] + 1 + (uint32_t)lane; l <= need0; l += 32)
-					fs->len_price[0][l - 2] = length_price(probs, price, S_LEN, l);
+				uint32_t mn = 0xffffffffu;
+				for (uint32_t l = have_len[0] + 1 + (uint32_t)lane; l <= need0; l += 32) {
+					const uint32_t v = length_price(probs, price, S_LEN, l);
+					fs->len_price[0][l - 2] = v;
+					mn = min(mn, v);
+				}
+				min_lp[0] = min(min_lp[0], __reduce_min_sync(FULL, mn));
 				have_len[0] = need0;
 			}
 			if (need1 > have_len[1]) {
-				for (uint32_t l = have_len[1] + 1 + (uint32_t)lane; l <= need1; l += 32)
-					fs->len_price[1][l - 2] = length_price(probs, price, S_REPLEN, l);
+				uint32_t mn = 0xffffffffu;
+				for (uint32_t l = have_len[1] + 1 + (uint32_t)lane; l <= need1; l += 32) {
+					const uint32_t v = length_price(probs, price, S_REPLEN, l);
+					fs->len_price[1][l - 2] = v;
+					mn = min(mn, v);
+				}
+				min_lp[1] = min(min_lp[1], __reduce_min_sync(FULL, mn));
 				have_len[1] = need1;
 			}
 			__syncwarp();
-			// per-occurrence distance prices: tail once, pos-slot tree per length context
+			// per-occurrence distance prices: tail once, pos-slot tree per length context.  The model
+			// does not change during a find and a bucket is walked in ascending position order, so a
+			// lane sees long stretches of one pos slot: its four tree prices are kept in registers.
+			const DistParts dp = dist_parts(valid ? dist : 0);
+			const uint32_t align_price = __shfl_sync(FULL, align_tab, (int)(dp.low & 15));
 			uint32_t base2 = 0, base3 = 0, base4 = 0, base5 = 0;
 			if (valid) {
-				const DistParts dp = dist_parts(dist);
-				const uint32_t tail = hdr_match + dist_tail_price(probs, price, dp);
-				base2 = tail + tree_price(probs, price, S_POSSLOT, 6, dp.pslot);
-				if (L > 2) base3 = tail + tree_price(probs, price, S_POSSLOT + 64, 6, dp.pslot);
-				if (L > 3) base4 = tail + tree_price(probs, price, S_POSSLOT + 128, 6, dp.pslot);
-				if (L > 4) base5 = tail + tree_price(probs, price, S_POSSLOT + 192, 6, dp.pslot);
+				uint32_t tail = hdr_match;
+				if (dp.pslot >= 14)
+					tail += (dp.direct << 11) + align_price;
+				else
+					tail += dist_tail_price(probs, price, dp);
+				if (dp.pslot != slot_cached) {
+					slot_cached = dp.pslot;
+					slot_price2 = tree_price(probs, price, S_POSSLOT, 6, dp.pslot);
+					slot_price3 = tree_price(probs, price, S_POSSLOT + 64, 6, dp.pslot);
+					slot_price4 = tree_price(probs, price, S_POSSLOT + 128, 6, dp.pslot);
+					slot_price5 = tree_price(probs, price, S_POSSLOT + 192, 6, dp.pslot);
+				}
+				base2 = tail + slot_price2;
+				base3 = tail + slot_price3;
+				base4 = tail + slot_price4;
+				base5 = tail + slot_price5;
 			}
 			const uint32_t hdr_r0 = hdr_lrep0, hdr_r1 = hdr_lrep1, hdr_r2 = hdr_lrep2, hdr_r3 = hdr_lrep3;
 			// cheapest candidate of this lane (lower bound test against the heap root)
 			const bool full = fs->count >= k;
-			const uint32_t root = full ? fs->ent_price[fs->store[0]] : 0xffffffffu;
+			const uint32_t root = full ? fs->hkey[0] >> 5 : 0xffffffffu;
 			uint32_t cheapest = 0xffffffffu;
 			uint32_t live_lens = 0;  // bit (len-2): some candidate of that length is at or below the root
 			if (valid) {
@@ -242,14 +302,29 @@ __device__ __forceinline__ uint32_t warp_find(int lane, SmemU16 probs, SmemU32 p
 				if (rep_mask & 2) rep_hdr_best = min(rep_hdr_best, hdr_r1);
 				if (rep_mask & 4) rep_hdr_best = min(rep_hdr_best, hdr_r2);
 				if (rep_mask & 8) rep_hdr_best = min(rep_hdr_best, hdr_r3);
-				for (uint32_t len = 2; len <= L; len++) {
-					const uint32_t b = len == 2 ? base2 : len == 3 ? base3 : len == 4 ? base4 : base5;
-					const uint32_t pm = per_byte(b + fs->len_price[0][len - 2], len, recip);
-					uint32_t pr = 0xffffffffu;
-					if (rep_mask) pr = per_byte(rep_hdr_best + fs->len_price[1][len - 2], len, recip);
-					cheapest = min(cheapest, min(pm, pr));
-					// lengths worth replaying (only meaningful while L <= 33, see the replay below)
-					if (min(pm, pr) <= root) live_lens |= 1u << ((len - 2) & 31);
+				// No candidate of this occurrence is cheaper per byte than its cheapest header + distance
+				// plus the cheapest length price, spread over its longest length.  Once the heap is full
+				// that bound is above the root for nearly every occurrence, which then costs O(1)
+				// instead of one pricing per length.
+				uint32_t lo = base2;
+				if (L > 2) lo = min(lo, base3);
+				if (L > 3) lo = min(lo, base4);
+				if (L > 4) lo = min(lo, base5);
+				uint32_t bound = per_byte(lo + min_lp[0], L, recip);
+				if (rep_mask) bound = min(bound, per_byte(rep_hdr_best + min_lp[1], L, recip));
+				if (!full) {
+					cheapest = 0;
+					live_lens = 0xffffffffu;
+				} else if (bound <= root) {
+					for (uint32_t len = 2; len <= L; len++) {
+						const uint32_t b = len == 2 ? base2 : len == 3 ? base3 : len == 4 ? base4 : base5;
+						const uint32_t pm = per_byte(b + fs->len_price[0][len - 2], len, recip);
+						uint32_t pr = 0xffffffffu;
+						if (rep_mask) pr = per_byte(rep_hdr_best + fs->len_price[1][len - 2], len, recip);
+						cheapest = min(cheapest, min(pm, pr));
+						// lengths worth replaying (only meaningful while L <= 33, see the replay below)
+						if (min(pm, pr) <= root) live_lens |= 1u << ((len - 2) & 31);
+					}
 				}
 				candidates += (L - 1) * (1 + __popc(rep_mask));
 			}
@@ -288,7 +363,7 @@ __device__ __forceinline__ uint32_t warp_find(int lane, SmemU16 probs, SmemU32 p
 							}
 						}
 						if (last != 0) {
-							fs->ent_pk[fs->store[0]] = last;
+							fs->ent_pk[fs->hkey[0] & 31u] = last;
 							done = 1;
 						}
 					}
@@ -337,12 +412,15 @@ __device__ __forceinline__ uint32_t warp_find(int lane, SmemU16 probs, SmemU32 p
 	// pop everything, worst first (top_k_packet_finder.c:127-138)
 	if (lane == 0) {
 		fs->candidates = candidates;
+		fs->chunks = chunks;
 		uint32_t pops = 0;
-		while (fs->count > 0) {
-			fs->pop_order[pops++] = fs->store[0];
-			fs->store[0] = fs->store[--fs->count];
-			heap_sift_down(fs, 0);
+		uint32_t count = fs->count;
+		while (count > 0) {
+			fs->pop_order[pops++] = (uint8_t)(fs->hkey[0] & 31u);
+			count--;
+			if (count) heap_sink(fs, 0, fs->hkey[count], count);
 		}
+		fs->count = 0;
 		fs->pops = pops;
 	}
 	__syncwarp();

@@ -17,7 +17,7 @@ constexpr uint32_t RECIP_ENTRIES = 288;
 
 struct ChainStats {
 	unsigned long long evals, attempts, accepted, new_best, packets, bits, slab_bytes, ck_bytes, finds, candidates,
-	    edits, overflows, rejoined;
+	    edits, overflows, rejoined, find_cycles, chain_cycles, chunks;
 };
 
 struct ChainState {
@@ -30,6 +30,13 @@ struct ChainState {
 	uint32_t eval_index;  // successful evaluations since the chain's slab was last set
 	uint32_t journal_count;     // edits accepted since the best slab last equalled the current slab
 	uint32_t journal_overflow;  // != 0: the journal is incomplete, the next new best copies the whole slab
+	// A proposal suspended at a checkpoint crossing when the launch's packet budget ran out (see
+	// AnnealArgs::suspend).  Its model is the record it had just written into the non-live buffer
+	// of slot susp_slot-1, its edits so far sit in the chain's accept/reject buffer.
+	uint32_t susp_slot;      // 0 = nothing suspended
+	uint32_t susp_j0;        // first checkpoint index the proposal rewrites
+	uint32_t susp_stored, susp_count, susp_overflow;  // EditLog counters
+	uint32_t pad;
 };
 constexpr uint32_t JOURNAL_CAP = 1024;
 
@@ -215,6 +222,8 @@ struct CkSink {
 	uint64_t last_cost;
 	uint32_t test;       // != 0: compare each crossing with the chain's current checkpoint there
 	uint32_t converged;  // slot at which the model re-joined the current slab's trajectory (0 = not)
+	uint32_t suspend_pidx;  // WALK_REPAIR: stop at the first checkpoint at or past this packet index (~0 = never)
+	long long deadline;     // WALK_REPAIR: ... or at the first checkpoint after this clock64() value (0 = none)
 };
 
 // The state a walk keeps in registers.  The rep distances stay in e.rec->rep[] (shared memory):
@@ -369,7 +378,7 @@ __device__ __forceinline__ void ck_absolute(int lane, const CkMeta* meta, const 
 }
 
 enum WalkMode { WALK_PLAIN = 0, WALK_REPAIR_HEAD = 1, WALK_REPAIR = 2 };
-enum WalkResult { WALK_DONE = 0, WALK_NEED_FIND = 1, WALK_ERROR = 2, WALK_REJOINED = 3 };
+enum WalkResult { WALK_DONE = 0, WALK_NEED_FIND = 1, WALK_ERROR = 2, WALK_REJOINED = 3, WALK_SUSPENDED = 4 };
 
 // Prices packets from k.pos until stop_pos bytes or packet index stop_pidx is reached.
 //   WALK_PLAIN        the slab as it is (neighbour.c:22-32, main.c:116-118)
@@ -391,6 +400,9 @@ __device__ __forceinline__ uint32_t walk(const uint32_t MODE, const WalkEnv& e, 
 		if (k.pos >= ck.next) {
 			walker_checkpoint(e, k, ck);
 			if (ck.converged) return WALK_REJOINED;
+			if (MODE == WALK_REPAIR && k.pos < stop_pos &&
+			    (k.pos - k.delta >= ck.suspend_pidx || (ck.deadline != 0 && clock64() >= ck.deadline)))
+				return WALK_SUSPENDED;
 		}
 		if (k.pos - k.w.base >= 32u) {
 			tally_flush(k.t);
@@ -559,6 +571,8 @@ __global__ void __launch_bounds__(CTA_THREADS) score_kernel(ScoreArgs a)
 	ck.last_cost = 0;
 	ck.test = 0;
 	ck.converged = 0;
+	ck.suspend_pidx = 0xffffffffu;
+	ck.deadline = 0;
 	uint64_t pending = 0, pending_old = 0;
 	uint32_t err = 0;
 	if (!a.ck) ck.next = 0xffffffffu;
@@ -624,6 +638,8 @@ __global__ void __launch_bounds__(CTA_THREADS) topk_kernel(TopkArgs a)
 				walker_load(e, k, a.ck + (below - 1), &ws->bar, parity);
 			CkSink ck = {};
 			ck.next = 0xffffffffu;
+			ck.suspend_pidx = 0xffffffffu;
+			ck.deadline = 0;
 			uint64_t pending = 0, pending_old = 0;
 			walk(WALK_PLAIN, e, k, qpos, 0xffffffffu, ck, nullptr, 0xffffffffu, 0, pending, pending_old, err);
 			if (!err && k.pos != qpos) err = ERR_NOT_BOUNDARY;
@@ -679,7 +695,10 @@ struct AnnealArgs {
 	// run parameters
 	uint32_t evals, max_attempts, schedule, step, num_iters, first_eval;
 	unsigned long long packet_budget;
+	unsigned long long cycle_budget;  // SM clocks: chains stop (suspending their proposal) once the launch has run this long
 	uint32_t early_exit;  // stop a proposal where its model re-joins the current slab's checkpoints
+	uint32_t suspend;     // packet_budget is exact: a proposal that crosses it is suspended at its next
+	                      // checkpoint and carried on by the next launch, so all warps end together
 	const float* temps;
 };
 
@@ -707,7 +726,8 @@ __global__ void __launch_bounds__(CTA_THREADS, MG_ANNEAL_MIN_CTAS) anneal_kernel
 	// Counters live in shared memory and are touched by lane 0 only: lanes of a warp are not
 	// guaranteed to run in lockstep, so a read-modify-write by all of them could count twice.
 	ChainStats& cs = ws->stats;
-	if (lane == 0) cs = ChainStats{0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+	if (lane == 0) cs = ChainStats{0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+	const long long t_start = clock64();
 	unsigned long long packets_done = 0;  // uniform copy of cs.packets for the budget test
 	EditLog lg;
 	lg.e = a.logs + (size_t)c * a.log_cap;
@@ -716,60 +736,11 @@ __global__ void __launch_bounds__(CTA_THREADS, MG_ANNEAL_MIN_CTAS) anneal_kernel
 
 	uint32_t done = 0, attempts = 0;
 	const uint32_t first_eval = a.first_eval == 0xffffffffu ? st.eval_index : a.first_eval;
+	const long long deadline = a.cycle_budget ? t_start + (long long)a.cycle_budget : 0;
 	while (done < a.evals && attempts < a.max_attempts && st.err == 0 &&
-	       (a.packet_budget == 0 || packets_done < a.packet_budget)) {
+	       (a.packet_budget == 0 || packets_done < a.packet_budget) && (deadline == 0 || clock64() < deadline)) {
 		attempts++;
-		lg.stored = lg.count = 0;
-		lg.dup_pos = 0xffffffffu;
-		lg.dup_index = 0;
-		lg.overflow = false;
-
-		// ---- pick the packet to mutate and the checkpoint to start from ------------------
-		const uint32_t target = rng31(rng) % st.live_count;  // neighbour.c:163
-		// last checkpoint whose packet index is <= target: running sums of the delta records
-		uint32_t j0 = 0, pidx0 = 0;
-		uint64_t cost0 = 0;
-		{
-			uint32_t carry_p = 0;
-			uint64_t carry_c = 0;
-			for (uint32_t base = 0; base < nck; base += 32) {
-				const uint32_t i = base + lane;
-				CkMeta mt = {0, 0, 0};
-				if (i < nck) mt = ck_meta[(size_t)ck_live[i] * nck + i];
-				uint32_t p = mt.dpidx;
-				uint64_t cc = mt.dcost;
-				for (int o = 1; o < 32; o <<= 1) {
-					const uint32_t tp = __shfl_up_sync(FULL, p, o);
-					const uint64_t tc = __shfl_up_sync(FULL, cc, o);
-					if (lane >= o) {
-						p += tp;
-						cc += tc;
-					}
-				}
-				p += carry_p;
-				cc += carry_c;
-				const uint32_t cnt = __popc(__ballot_sync(FULL, i < nck && p <= target));
-				if (cnt) {
-					j0 = base + cnt;
-					pidx0 = __shfl_sync(FULL, p, (int)cnt - 1);
-					cost0 = __shfl_sync(FULL, cc, (int)cnt - 1);
-				}
-				carry_p = __shfl_sync(FULL, p, 31);
-				carry_c = __shfl_sync(FULL, cc, 31);
-				if (cnt < 32) break;
-			}
-		}
 		Walker k;
-		if (j0 == 0) {
-			walker_init(e, k);
-		} else {
-			walker_load(e, k, ck_base + (size_t)ck_live[j0 - 1] * nck + (j0 - 1), &ws->bar, parity);
-			// the record's own counters date from the proposal that wrote it; the running sums are current
-			k.delta = k.pos - pidx0;
-			k.t.total = cost0;
-			if (lane == 0) cs.ck_bytes += sizeof(Record);
-		}
-		const uint32_t start_pos = k.pos, start_pidx = walker_pidx(k);
 		CkSink ck;
 		ck.ck = ck_base;
 		ck.ck_pos = nullptr;
@@ -777,12 +748,91 @@ __global__ void __launch_bounds__(CTA_THREADS, MG_ANNEAL_MIN_CTAS) anneal_kernel
 		ck.live = ck_live;
 		ck.nck = nck;
 		ck.stride = a.stride;
-		ck.next = 0xffffffffu;  // no checkpoints while the prefix is priced
 		ck.written = 0;
-		ck.last_pidx = pidx0;
-		ck.last_cost = cost0;
-		ck.test = 0;
 		ck.converged = 0;
+		uint32_t j0 = 0, target = 0;
+		uint32_t phase = 0, mode = WALK_PLAIN;
+		const bool resumed = st.susp_slot != 0;
+		if (resumed) {
+			// ---- carry on the proposal the previous launch suspended (phase 2, at a checkpoint) ----
+			const uint32_t slot = st.susp_slot;
+			j0 = st.susp_j0;
+			lg.stored = st.susp_stored;
+			lg.count = st.susp_count;
+			lg.overflow = st.susp_overflow != 0;
+			lg.dup_pos = 0xffffffffu;  // only the first three repaired packets can rewrite an entry
+			lg.dup_index = 0;
+			st.susp_slot = 0;
+			walker_load(e, k, ck_base + (size_t)(ck_live[slot - 1] ^ 1u) * nck + (slot - 1), &ws->bar, parity);
+			if (lane == 0) cs.ck_bytes += sizeof(Record);
+			ck.next = (slot + 1) * a.stride;
+			ck.last_pidx = walker_pidx(k);
+			ck.last_cost = k.t.total;
+			ck.test = a.early_exit;
+			phase = 2;
+			mode = WALK_REPAIR;
+		} else {
+			lg.stored = lg.count = 0;
+			lg.dup_pos = 0xffffffffu;
+			lg.dup_index = 0;
+			lg.overflow = false;
+
+			// ---- pick the packet to mutate and the checkpoint to start from ------------------
+			target = rng31(rng) % st.live_count;  // neighbour.c:163
+			// last checkpoint whose packet index is <= target: running sums of the delta records
+			uint32_t pidx0 = 0;
+			uint64_t cost0 = 0;
+			{
+				uint32_t carry_p = 0;
+				uint64_t carry_c = 0;
+				for (uint32_t base = 0; base < nck; base += 32) {
+					const uint32_t i = base + lane;
+					CkMeta mt = {0, 0, 0};
+					if (i < nck) mt = ck_meta[(size_t)ck_live[i] * nck + i];
+					uint32_t p = mt.dpidx;
+					uint64_t cc = mt.dcost;
+					for (int o = 1; o < 32; o <<= 1) {
+						const uint32_t tp = __shfl_up_sync(FULL, p, o);
+						const uint64_t tc = __shfl_up_sync(FULL, cc, o);
+						if (lane >= o) {
+							p += tp;
+							cc += tc;
+						}
+					}
+					p += carry_p;
+					cc += carry_c;
+					const uint32_t cnt = __popc(__ballot_sync(FULL, i < nck && p <= target));
+					if (cnt) {
+						j0 = base + cnt;
+						pidx0 = __shfl_sync(FULL, p, (int)cnt - 1);
+						cost0 = __shfl_sync(FULL, cc, (int)cnt - 1);
+					}
+					carry_p = __shfl_sync(FULL, p, 31);
+					carry_c = __shfl_sync(FULL, cc, 31);
+					if (cnt < 32) break;
+				}
+			}
+			if (j0 == 0) {
+				walker_init(e, k);
+			} else {
+				walker_load(e, k, ck_base + (size_t)ck_live[j0 - 1] * nck + (j0 - 1), &ws->bar, parity);
+				// the record's own counters date from the proposal that wrote it; the running sums are current
+				k.delta = k.pos - pidx0;
+				k.t.total = cost0;
+				if (lane == 0) cs.ck_bytes += sizeof(Record);
+			}
+			ck.next = 0xffffffffu;  // no checkpoints while the prefix is priced
+			ck.last_pidx = pidx0;
+			ck.last_cost = cost0;
+			ck.test = 0;
+		}
+		const uint32_t start_pos = k.pos, start_pidx = walker_pidx(k);
+		ck.suspend_pidx = 0xffffffffu;
+		ck.deadline = a.suspend ? deadline : 0;
+		if (a.suspend && a.packet_budget) {
+			const unsigned long long lim = (unsigned long long)start_pidx + (a.packet_budget - packets_done);
+			ck.suspend_pidx = lim < 0xffffffffull ? (uint32_t)lim : 0xffffffffu;
+		}
 		uint64_t pending = 0, pending_old = 0;
 		uint32_t err = 0;
 
@@ -792,12 +842,12 @@ __global__ void __launch_bounds__(CTA_THREADS, MG_ANNEAL_MIN_CTAS) anneal_kernel
 		//            checkpoint instead of from byte 0), then mutate it (neighbour.c:119-152)
 		//   phase 1  repair + price the next three packets (neighbour.c:82-98, count < 4)
 		//   phase 2  repair + price the rest, writing fresh checkpoints
-		uint32_t phase = 0, mode = WALK_PLAIN, stop_pidx = target;
+		uint32_t stop_pidx = resumed ? 0xffffffffu : target;
 		uint32_t pos = 0, byte0 = 0;       // the mutated packet's position and data byte
 		uint64_t first = 0, newpk = 0, override_pk = 0, excluded = 0;
 		uint32_t override_pos = 0xffffffffu;
 		uint32_t want_find = 0;            // 1 mutation pick, 2 repair pick
-		bool pick_best = false, failed = false;
+		bool pick_best = false, failed = false, suspended = false;
 		for (;;) {
 			const uint32_t res = walk(mode, e, k, n, stop_pidx, ck, &lg, override_pos, override_pk, pending, pending_old, err);
 			if (res == WALK_ERROR) {
@@ -805,6 +855,10 @@ __global__ void __launch_bounds__(CTA_THREADS, MG_ANNEAL_MIN_CTAS) anneal_kernel
 				break;
 			}
 			if (res == WALK_REJOINED) break;
+			if (res == WALK_SUSPENDED) {
+				suspended = true;
+				break;
+			}
 			if (res == WALK_NEED_FIND) {
 				pick_best = rng31(rng) % 4 == 0;  // neighbour.c:107
 				excluded = pending;
@@ -863,9 +917,14 @@ __global__ void __launch_bounds__(CTA_THREADS, MG_ANNEAL_MIN_CTAS) anneal_kernel
 
 			if (want_find) {
 				if (lane == 0) cs.finds++;
+				const long long t_find = clock64();
 				const uint32_t count = warp_find(lane, e.probs, e.trans, e.recip, &ws->fs, a.data, n, a.occ_start, a.occ,
 				                                 walker_model(e, k), excluded, a.k);
-				if (lane == 0) cs.candidates += ws->fs.candidates;
+				if (lane == 0) {
+					cs.candidates += ws->fs.candidates;
+					cs.chunks += ws->fs.chunks;
+					cs.find_cycles += (unsigned long long)(clock64() - t_find);
+				}
 				uint64_t chosen = 0;
 				bool have = false;
 				if (count != 0) {
@@ -919,6 +978,16 @@ __global__ void __launch_bounds__(CTA_THREADS, MG_ANNEAL_MIN_CTAS) anneal_kernel
 			cs.bits += walker_bits(k, start_pidx);
 			cs.slab_bytes += (uint64_t)(k.pos - start_pos) * 9;
 			cs.ck_bytes += (uint64_t)ck.written * sizeof(Record);
+		}
+		if (suspended) {
+			// out of budget in the middle of the suffix: the checkpoint just written is the resume point
+			st.susp_slot = k.pos / a.stride;
+			st.susp_j0 = j0;
+			st.susp_stored = lg.stored;
+			st.susp_count = lg.count;
+			st.susp_overflow = lg.overflow ? 1u : 0u;
+			attempts--;  // counted by the launch that finishes it
+			break;
 		}
 		if (failed) {
 			if (a.trace && attempts <= a.trace_cap && lane == 0) {
@@ -1054,6 +1123,7 @@ __global__ void __launch_bounds__(CTA_THREADS, MG_ANNEAL_MIN_CTAS) anneal_kernel
 	if (lane == 0) {
 		cs.evals = done;
 		cs.attempts = attempts;
+		cs.chain_cycles = (unsigned long long)(clock64() - t_start);
 		st.rng = rng;
 		st.eval_index = first_eval + done;
 		a.state[c] = st;

@@ -110,3 +110,41 @@ def test_anneal_trace_matches_oracle(mg, port, corpora, kind, n, step):
             assert same_packets(an.get_slab(c, best=True), bslab)
             assert ctx.score_slab(an.get_slab(c)) == cc
         an.close()
+
+
+@pytest.mark.parametrize("kind,n,step,budget", [("text", 8192, 0, 3000), ("mixed", 8192, 1, 1500), ("binary", 4096, 1, 700)])
+def test_suspended_proposals_do_not_change_trajectories(mg, port, corpora, kind, n, step, budget):
+    """Exact packet budgets: a proposal cut at a checkpoint and carried on by the next launch must
+    leave every chain on the trajectory the oracle follows without any cuts."""
+    data = corpora(kind, n)
+    chains, seed, launches = 4, 31, 40
+    init = mg.literal_slab(n) if step == 0 else port.greedy_slab(data)
+    with mg.Context(data) as ctx:
+        an = mg.Annealer(ctx, chains, trace_capacity=4096, seed=seed, checkpoint_stride=512)
+        an.set_slab(init if step else None, adopt_cost=False)
+        got = [[] for _ in range(chains)]
+        packets = 0
+        for _ in range(launches):
+            st = an.run(1000, step=step, packet_budget=budget, suspend=True, first_eval=mg.CONTINUE_EVALS)
+            packets += st["packets_scored"]
+            for c in range(chains):
+                got[c].append(an.trace(c))
+        # the budget is exact to within the distance to the next checkpoint
+        assert packets <= chains * launches * (budget + 2 * 512 + 8)
+        assert packets >= chains * launches * budget
+        cur, best = an.costs()
+        for c in range(chains):
+            g = np.concatenate(got[c])
+            evals = int((g["flags"] & 1).sum())
+            assert evals >= 10
+            slab, bslab = init.copy(), init.copy()
+            attempts, bc, cc, _, trace = port.anneal_epoch(data, slab, bslab, 0, 0, rng_mode=1,
+                                                           rng_state=port.chain_seed(seed, c), step=step, evals=evals)
+            # the GPU may have drawn failed proposals after its last success
+            assert len(g) >= attempts
+            assert (g["flags"][:attempts] == trace["flags"]).all()
+            assert (g["cost"][:attempts] == trace["cost"]).all()
+            assert (g["undo_count"][:attempts] == trace["undo_count"]).all()
+            assert (g["flags"][attempts:] == 0).all()
+            assert int(best[c]) == bc
+        an.close()
