@@ -357,6 +357,79 @@ __device__ __forceinline__ bool packet_event(int lane, const LaneRole r, uint32_
 	return lane <= 8;
 }
 
+// ---- MATCH fast path ---------------------------------------------------------------------------
+// The events of a MATCH (src/lzma_packet_encoder.c:138-146) from two packed words that are the same
+// on every lane and four per-lane constants (a 512-byte table in shared memory):
+//   F  tree fields, each left-aligned in its byte (most significant bit first, the order the trees
+//      consume them): byte3 length tree, byte2 pos slot, byte1 reverse tree (bit-reversed low bits),
+//      byte0 bit0 is_match=1, bit1 is_rep=0, bit2 choice_1, bit3 choice_2
+//   G  the variable part of each group's slot base: byte0 ctx, byte1 length tree offset,
+//      byte2 64 * length context, byte3 reverse-tree base - S_ALIGN
+// A lane at depth t of its tree reads the top t+1 bits of its field: prefix and bit in one shift.
+struct LaneConst {
+	uint32_t shb;    // F >> shb puts the lane's bit at bit 0 and its prefix above it
+	uint32_t mask2;  // (2 << t) - 1
+	uint32_t base;   // fixed part of the slot index, tree root offset (1 << t) included
+	uint32_t sel;    // __byte_perm selector of the lane's byte of G (0x4444 = none)
+};
+
+__host__ __device__ inline LaneConst match_lane_const(int lane)
+{
+	LaneConst c = {0, 0, S_DUMMY, 0x4444};
+	if (lane == 0) c = {0, 1, S_ISMATCH, 0x4440};
+	else if (lane == 1) c = {1, 1, S_ISREP, 0x4440};
+	else if (lane == 5) c = {2, 1, S_LEN, 0x4444};
+	else if (lane == 6) c = {3, 1, S_LEN + 1, 0x4444};
+	else if (lane >= 7 && lane < 15) {
+		const uint32_t t = (uint32_t)lane - 7;
+		c = {24 + 7 - t, (2u << t) - 1, S_LEN + (1u << t), 0x4441};
+	} else if (lane >= 15 && lane < 21) {
+		const uint32_t t = (uint32_t)lane - 15;
+		c = {16 + 7 - t, (2u << t) - 1, S_POSSLOT + (1u << t), 0x4442};
+	} else if (lane >= 21 && lane < 26) {
+		const uint32_t t = (uint32_t)lane - 21;
+		c = {8 + 7 - t, (2u << t) - 1, S_ALIGN + (1u << t), 0x4443};
+	}
+	return c;
+}
+
+struct MatchDesc {
+	uint32_t F, G, amask, direct;
+};
+
+__device__ __forceinline__ MatchDesc match_desc(uint32_t ctx, uint32_t len, uint32_t dist)
+{
+	MatchDesc d;
+	const uint32_t v = len - 2;
+	const uint32_t cls = (v >= 8 ? 1u : 0u) + (v >= 16 ? 1u : 0u);      // low / mid / high tree
+	const uint32_t w = v - (cls == 0 ? 0u : cls == 1 ? 8u : 16u);
+	const uint32_t fieldL = cls == 2 ? w : w << 5;
+	const uint32_t lenoff = LEN_LOW + 8 * cls;
+	const uint32_t lctx = v < 3 ? v : 3;
+	// src/lzma_packet_encoder.c:71-104
+	uint32_t pslot = dist, low = 0, rbase = S_ALIGN, rbits = 0, direct = 0;
+	if (dist >= 4) {
+		const uint32_t nlow = 30u - (uint32_t)__clz(dist);
+		const uint32_t high = dist >> nlow;
+		low = dist & ((1u << nlow) - 1);
+		pslot = nlow * 2 + high;
+		if (pslot < 14) {
+			rbase = S_POSCODER + (high << nlow) - pslot;
+			rbits = nlow;
+		} else {
+			rbits = 4;
+			direct = nlow - 4;
+			low &= 15;
+		}
+	}
+	const uint32_t fieldR = __brev(low) >> 24;
+	d.F = (fieldL << 24) | (pslot << 18) | (fieldR << 8) | 1u | (cls >= 1 ? 4u : 0u) | (cls == 2 ? 8u : 0u);
+	d.G = ctx | (lenoff << 8) | (lctx << 22) | ((rbase - S_ALIGN) << 24);
+	d.amask = 0x23u | (cls >= 1 ? 0x40u : 0u) | ((cls == 2 ? 0xffu : 0x7u) << 7) | (0x3fu << 15) | (((1u << rbits) - 1u) << 21);
+	d.direct = direct;
+	return d;
+}
+
 // src/lzma_state.c:59-81 + src/lzma_packet_encoder.c:192-193
 __device__ __forceinline__ void model_advance(Model& m, uint32_t type, uint32_t len, uint32_t dist)
 {

@@ -69,6 +69,7 @@ struct WarpShared {
 struct CtaShared {
 	uint32_t trans[4096];  // see code_bit()
 	uint32_t recip[RECIP_ENTRIES];
+	uint4 lane_tab[32];    // match_lane_const() per lane
 	WarpShared warp[WARPS_PER_CTA];
 };
 static_assert(sizeof(WarpShared) % 16 == 0, "per-warp shared block must keep the record 16-byte aligned");
@@ -83,6 +84,10 @@ __device__ __forceinline__ void cta_tables_load(CtaShared* sh, const Tables& t)
 {
 	for (int i = threadIdx.x; i < 4096; i += blockDim.x) sh->trans[i] = t.trans[i];
 	for (int i = threadIdx.x; i < (int)RECIP_ENTRIES; i += blockDim.x) sh->recip[i] = t.recip[i];
+	if (threadIdx.x < 32) {
+		const LaneConst c = match_lane_const((int)threadIdx.x);
+		sh->lane_tab[threadIdx.x] = make_uint4(c.shb, c.mask2, c.base, c.sel);
+	}
 	if ((threadIdx.x & 31) == 0) mbar_init(&sh->warp[threadIdx.x >> 5].bar, 1);
 	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	__syncthreads();
@@ -166,6 +171,7 @@ struct WalkEnv {
 	uint32_t n;
 	uint32_t trans_addr;  // shared address of trans[]
 	uint32_t wb_addr;     // shared address of the window byte mirror
+	uint32_t lane_tab_addr;  // shared address of this lane's match_lane_const() entry
 	uint32_t lit_addr;    // shared address of this lane's first slot
 	uint32_t lit_sh;      // byte >> lit_sh = tree prefix at this lane's depth
 	uint32_t bitmask;     // 0x800 on tree lanes
@@ -178,20 +184,26 @@ __device__ __forceinline__ WalkEnv make_env(int lane, WarpShared* ws, const CtaS
 {
 	WalkEnv e;
 	e.lane = lane;
-	e.probs.a = smem_u32(ws->rec.probs);
-	e.trans.a = smem_u32(sh->trans);
-	e.recip.a = smem_u32(sh->recip);
-	e.reps.a = smem_u32(ws->rec.rep);
+	// Two opaque base addresses, everything else a compile-time offset from them: left to itself the
+	// compiler re-derives each shared address from the generic pointer (S2R SR_CgaCtaId + LEA + IMAD)
+	// wherever it is short of registers, which was ~10 % of the instructions of a non-literal packet.
+	uint32_t cta_base = smem_u32(sh), warp_base = smem_u32(ws);
+	asm volatile("" : "+r"(cta_base), "+r"(warp_base));
+	e.probs.a = warp_base + (uint32_t)offsetof(WarpShared, rec) + (uint32_t)offsetof(Record, probs);
+	e.trans.a = cta_base + (uint32_t)offsetof(CtaShared, trans);
+	e.recip.a = cta_base + (uint32_t)offsetof(CtaShared, recip);
+	e.reps.a = warp_base + (uint32_t)offsetof(WarpShared, rec) + (uint32_t)offsetof(Record, rep);
 	e.probs_ptr = ws->rec.probs;
 	e.rec = &ws->rec;
 	e.slab = slab;
 	e.data = data;
 	e.n = n;
-	e.trans_addr = smem_u32(sh->trans);
-	e.wb_addr = smem_u32(ws->wbytes);
+	e.trans_addr = e.trans.a;
+	e.wb_addr = warp_base + (uint32_t)offsetof(WarpShared, wbytes);
+	e.lane_tab_addr = cta_base + (uint32_t)offsetof(CtaShared, lane_tab) + 16u * (uint32_t)lane;
 	const bool tree = lane >= 1 && lane <= 8;
 	const uint32_t first = lane == 0 ? S_ISMATCH : tree ? S_LIT + (1u << (lane - 1)) : S_DUMMY;
-	e.lit_addr = smem_u32(ws->rec.probs) + 2 * first;
+	e.lit_addr = e.probs.a + 2 * first;
 	e.lit_sh = tree ? 9u - (uint32_t)lane : 8u;
 	e.bitmask = tree ? 0x800u : 0u;
 	e.ctxmask = lane == 0 ? 0xffffffffu : 0u;
@@ -252,10 +264,16 @@ __device__ __forceinline__ Model walker_model(const WalkEnv& e, const Walker& k)
 	return m;
 }
 
-__device__ __forceinline__ void walker_fetch_mb(const WalkEnv& e, Walker& k)
+// The match byte is fetched on demand: only a literal that directly follows a non-literal packet
+// reads it (the automaton is below 7 after any literal, src/lzma_state.c:34-40).
+constexpr uint32_t MB_UNKNOWN = 0xffffffffu;
+__device__ __forceinline__ uint32_t walker_mb(const WalkEnv& e, Walker& k)
 {
-	const uint32_t rep0 = e.reps.get(0);
-	k.mb = (k.pos < e.n && rep0 < k.pos) ? e.data[k.pos - rep0 - 1] : 0;
+	if (k.mb == MB_UNKNOWN) {
+		const uint32_t rep0 = e.reps.get(0);
+		k.mb = (k.pos < e.n && rep0 < k.pos) ? e.data[k.pos - rep0 - 1] : 0;
+	}
+	return k.mb;
 }
 
 __device__ __forceinline__ void walker_init(const WalkEnv& e, Walker& k)
@@ -280,15 +298,15 @@ __device__ __forceinline__ void walker_load(const WalkEnv& e, Walker& k, const R
 	k.ctx = m.ctx;
 	k.t = {cost, 0, 0};
 	k.w.base = WINDOW_NONE;
-	k.mb = 0;
-	if (k.ctx >= 7) walker_fetch_mb(e, k);
+	k.mb = MB_UNKNOWN;
 }
 
 // Generic (any packet type) price + adapt: the slow path of the walk.
 __device__ __forceinline__ void walker_apply(const WalkEnv& e, Walker& k, Model& m, uint32_t type, uint32_t len,
                                              uint32_t dist, uint32_t byte)
 {
-	k.t.bits += apply_packet(e.lane, e.probs, e.trans, m, type, len, dist, byte, k.mb, k.t.acc) - 9u;
+	const uint32_t mbyte = (type == T_LITERAL && k.ctx >= 7) ? walker_mb(e, k) : 0u;
+	k.t.bits += apply_packet(e.lane, e.probs, e.trans, m, type, len, dist, byte, mbyte, k.t.acc) - 9u;
 	k.pos = m.pos;
 	k.delta = m.pos - m.pidx;
 	k.ctx = m.ctx;
@@ -300,7 +318,7 @@ __device__ __forceinline__ void walker_apply(const WalkEnv& e, Walker& k, Model&
 		e.reps.set(3, m.rep3);
 		__syncwarp();  // lanes are not guaranteed to run in lockstep: order these stores before later reads
 	}
-	if (type != T_LITERAL) walker_fetch_mb(e, k);
+	if (type != T_LITERAL) k.mb = MB_UNKNOWN;
 }
 
 __device__ __forceinline__ void walker_store(const WalkEnv& e, const Walker& k, Record* dst)
@@ -460,8 +478,9 @@ __device__ __forceinline__ uint32_t walk(const uint32_t MODE, const WalkEnv& e, 
 				const uint32_t top = byte >> e.lit_sh;
 				const uint32_t bit11 = (byte << (12 - e.lit_sh)) & e.bitmask;
 				uint32_t off = top + (ctx & e.ctxmask);
-				const uint32_t extra = (0x100u + ((k.mb << (9 - e.lit_sh)) & 0x100u)) & e.treemask;
-				if ((k.mb >> e.lit_sh) == top) off += extra;
+				const uint32_t mb = walker_mb(e, k);
+				const uint32_t extra = (0x100u + ((mb << (9 - e.lit_sh)) & 0x100u)) & e.treemask;
+				if ((mb >> e.lit_sh) == top) off += extra;
 				k.ctx = ctx < 10 ? ctx - 3 : ctx - 6;
 				const uint32_t addr = e.lit_addr + 2 * off;
 				const uint32_t tr = lds_u32(e.trans_addr + ((lds_u16(addr) | bit11) << 2));
@@ -469,6 +488,37 @@ __device__ __forceinline__ uint32_t walk(const uint32_t MODE, const WalkEnv& e, 
 				k.t.acc += tr >> 16;
 				k.pos++;
 				continue;
+			}
+			// ---- a MATCH outside the repair head: repair never touches it (neighbour.c:82-117), so it
+			// is priced straight from the slab.  One warp step: F/G/amask are the same on every lane,
+			// the lane's four constants turn them into its slot and bit ----------------------------
+			if (MODE != WALK_REPAIR_HEAD && meta_type(meta) == T_MATCH) {
+				const uint32_t len = meta_len(meta);
+				const uint32_t dist = window_dist(k.w, k.pos);
+				if (len - 2 <= MAX_MATCH - 2 && len <= e.n - k.pos && dist < k.pos) {
+					const MatchDesc d = match_desc(k.ctx, len, dist);
+					uint32_t shb, mask2, base, sel;
+					asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+					             : "=r"(shb), "=r"(mask2), "=r"(base), "=r"(sel)
+					             : "r"(e.lane_tab_addr));
+					const uint32_t nwb = (d.F >> shb) & mask2;
+					const uint32_t slot = base + __byte_perm(d.G, 0, sel) + (nwb >> 1);
+					if ((d.amask >> e.lane) & 1u) code_bit(e.probs, e.trans, slot, (nwb & 1u) << 11, k.t.acc);
+					if (e.lane == 0) k.t.acc += d.direct << 11;  // src/perplexity_encoder.c:12-17
+					k.t.bits += (uint32_t)__popc(d.amask) - 9u;
+					// src/lzma_state.c:59-65, 29-57
+					const uint32_t r0 = e.reps.get(0), r1 = e.reps.get(1), r2 = e.reps.get(2);
+					e.reps.set(0, dist);
+					e.reps.set(1, r0);
+					e.reps.set(2, r1);
+					e.reps.set(3, r2);
+					__syncwarp();
+					k.ctx = k.ctx < 7 ? 7 : 10;
+					k.pos += len;
+					k.delta += len - 1;
+					k.mb = MB_UNKNOWN;
+					continue;
+				}
 			}
 			// ---- every other packet ---------------------------------------------------------------
 			Model m = walker_model(e, k);
