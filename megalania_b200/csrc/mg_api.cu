@@ -312,7 +312,8 @@ static void export_model(const Record& r, mg_model_dump* out)
 {
 	for (int i = 0; i < 2615; i++) out->probs[i] = 1024;
 	auto put = [&](uint32_t ref_index, uint32_t slot) { out->probs[ref_index] = r.probs[slot]; };
-	for (uint32_t i = 0; i < 768; i++) put(i, S_LIT + i);
+	for (uint32_t node = 0; node < 768; node++)
+		if (node & 0xff) put(node, lit_slot(node));  // node 0 of each tree is never coded
 	const uint32_t ref_len[2] = {768, 768 + 514};
 	const uint32_t dev_len[2] = {S_LEN, S_REPLEN};
 	for (int t = 0; t < 2; t++) {

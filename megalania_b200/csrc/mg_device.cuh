@@ -21,25 +21,51 @@ constexpr uint32_t FULL = 0xffffffffu;
 constexpr uint32_t T_INVALID = 0, T_LITERAL = 1, T_MATCH = 2, T_SHORT_REP = 3, T_LONG_REP = 4;
 
 // ---- slot map at lc = lp = pb = 0 (only the reachable slots of src/lzma_state.h:15-55) ----
+//
+// Literal trees (plain, matched with match bit 0, matched with match bit 1; src/lzma_state.h:47-50):
+// a literal is priced by nine lanes at once (is_match + one lane per tree depth), so the layout is
+// chosen for shared-memory banks, not for the reference's node order.  Each tree is cut by the top
+// two bits of the byte into four 64-node sub-trees, one per 128-byte row, stored in heap order:
+// depth d (2..7) of every row then lives in words [2^(d-3), 2^(d-2)) of the row - the six depth
+// lanes always hit six different banks.  Depths 0 and 1 (9 slots) sit in a small block placed
+// over the deepest level's banks (that lane covers 16 banks, so a clash is a 1-in-16 event).
+// The natural layout measured 1.84 wavefronts per probability access on the 1 MiB corpus.
 constexpr uint32_t LEN_LOW = 2, LEN_MID = 10, LEN_HIGH = 18, LEN_SLOTS = 274;
-constexpr uint32_t S_LIT = 0;                       // [0x300]
-constexpr uint32_t S_LEN = 768;                     // choice1, choice2, low[8], mid[8], high[256]
-constexpr uint32_t S_REPLEN = S_LEN + LEN_SLOTS;    // 1042
-constexpr uint32_t S_POSSLOT = S_REPLEN + LEN_SLOTS;  // 1316, [4][64]
-constexpr uint32_t S_ALIGN = S_POSSLOT + 256;       // 1572, [16]
-constexpr uint32_t S_POSCODER = S_ALIGN + 16;       // 1588, [115]
-constexpr uint32_t S_ISMATCH = S_POSCODER + 115;    // 1703, [12]
-constexpr uint32_t S_ISREP = S_ISMATCH + 12;        // 1715
-constexpr uint32_t S_ISREPG0 = S_ISREP + 12;        // 1727
-constexpr uint32_t S_ISREPG1 = S_ISREPG0 + 12;      // 1739
-constexpr uint32_t S_ISREPG2 = S_ISREPG1 + 12;      // 1751
-constexpr uint32_t S_ISREP0LONG = S_ISREPG2 + 12;   // 1763
-constexpr uint32_t S_TOTAL = S_ISREP0LONG + 12;     // 1775
+constexpr uint32_t S_LIT = 0;                       // [3 trees][4 rows][64]: slot 0 of each row unused
+constexpr uint32_t S_LIT01 = 768 + 32;              // depth 0: [3], depth 1 (+4): [3][2]; over banks 16..21
+constexpr uint32_t S_ISMATCH = S_LIT01 + 12;        // [12]; is_match[0] is touched by every literal of a run
+constexpr uint32_t S_ISREP = S_ISMATCH + 12;
+constexpr uint32_t S_ISREPG0 = S_ISREP + 12;
+constexpr uint32_t S_ISREPG1 = S_ISREPG0 + 12;
+constexpr uint32_t S_ISREPG2 = S_ISREPG1 + 12;
+constexpr uint32_t S_ISREP0LONG = S_ISREPG2 + 12;
+constexpr uint32_t S_LEN = S_ISREP0LONG + 12;       // choice1, choice2, low[8], mid[8], high[256]
+constexpr uint32_t S_REPLEN = S_LEN + LEN_SLOTS;
+constexpr uint32_t S_POSSLOT = S_REPLEN + LEN_SLOTS;  // [4][64]
+constexpr uint32_t S_ALIGN = S_POSSLOT + 256;       // [16]
+constexpr uint32_t S_POSCODER = S_ALIGN + 16;       // [115]
+constexpr uint32_t S_TOTAL = S_POSCODER + 115;
 constexpr uint32_t S_DUMMY = S_TOTAL;               // spare slot: lanes with no event of their own adapt this one
+constexpr uint32_t S_COUNT = ((S_TOTAL + 1 + 7) / 8) * 8;  // probabilities stored per record (16-byte multiple)
+// is_match[0] is touched by every literal of a run: keep it off the banks of the shallow tree levels
+static_assert(((S_ISMATCH / 2) % 32) >= 16, "is_match[0] must only share a bank with the deepest literal tree level");
 
-// Working set of one warp == checkpoint record in HBM.  3600 bytes = 225 x 16.
+// Slot of literal-tree node `node` = variant << 8 | (1 << depth | prefix), the reference's index
+// into its 0x300 literal probabilities (src/lzma_packet_encoder.c:106-136).
+__host__ __device__ inline uint32_t lit_slot(uint32_t node)
+{
+	const uint32_t v = node >> 8, i = node & 0xff;
+	if (i < 2) return S_LIT01 + v;
+	if (i < 4) return S_LIT01 + 4 + 2 * v + (i & 1);
+	uint32_t d = 2;
+	while ((i >> (d + 1)) != 0) d++;
+	const uint32_t top2 = (i >> (d - 2)) & 3, sub = (1u << (d - 2)) | (i & ((1u << (d - 2)) - 1));
+	return S_LIT + v * 256 + top2 * 64 + sub;
+}
+
+// Working set of one warp == checkpoint record in HBM.
 struct alignas(16) Record {
-	uint16_t probs[S_TOTAL + 1];  // 3552 B
+	uint16_t probs[S_COUNT];
 	uint32_t rep[4];
 	uint32_t pos;   // byte position of the next packet
 	uint32_t pidx;  // index of that packet in the live chain
@@ -48,7 +74,7 @@ struct alignas(16) Record {
 	uint64_t cost;  // cost of everything before pos, 1/2048 bit
 	uint64_t pad1;
 };
-static_assert(sizeof(Record) == 3600, "record must stay a multiple of 16 bytes for cp.async.bulk");
+static_assert(sizeof(Record) % 16 == 0 && sizeof(Record) == S_COUNT * 2 + 48, "record must stay a multiple of 16 bytes for cp.async.bulk");
 
 // Packed slab slot: dist[31:0] | len[47:32] | type[55:48]
 __host__ __device__ __forceinline__ uint64_t pk_pack(uint32_t type, uint32_t dist, uint32_t len)
@@ -258,11 +284,16 @@ __device__ __forceinline__ DistParts dist_parts(uint32_t dist)
 __device__ __forceinline__ void lit_event(uint32_t depth, uint32_t byte, bool matched_mode, uint32_t mbyte,
                                           uint32_t& slot, uint32_t& bit)
 {
-	uint32_t top = byte >> (8 - depth);
-	uint32_t node = (1u << depth) | top;
+	const uint32_t top = byte >> (8 - depth);
 	bit = (byte >> (7 - depth)) & 1;
-	if (matched_mode && (mbyte >> (8 - depth)) == top) node += (1u + ((mbyte >> (7 - depth)) & 1)) << 8;
-	slot = S_LIT + node;
+	uint32_t v = 0;
+	if (matched_mode && (mbyte >> (8 - depth)) == top) v = 1u + ((mbyte >> (7 - depth)) & 1);
+	if (depth == 0)
+		slot = S_LIT01 + v;
+	else if (depth == 1)
+		slot = S_LIT01 + 4 + 2 * v + top;
+	else
+		slot = S_LIT + v * 256 + (byte >> 6) * 64 + ((1u << (depth - 2)) | (top & ((1u << (depth - 2)) - 1)));
 }
 
 // The length coder's three trees (src/lzma_packet_encoder.c:42-63) as one: nb bits of value w
@@ -478,7 +509,7 @@ __device__ __forceinline__ uint32_t apply_packet(int lane, SmemU16 probs, SmemU3
 
 __device__ __forceinline__ void model_init(int lane, SmemU16 probs, Model& m)
 {
-	for (uint32_t i = (uint32_t)lane; i <= S_TOTAL; i += 32) probs.set(i, 1024);
+	for (uint32_t i = (uint32_t)lane; i < S_COUNT; i += 32) probs.set(i, 1024);
 	m.pos = m.pidx = m.ctx = 0;
 	m.rep0 = m.rep1 = m.rep2 = m.rep3 = 0;
 	__syncwarp();

@@ -172,11 +172,16 @@ struct WalkEnv {
 	uint32_t trans_addr;  // shared address of trans[]
 	uint32_t wb_addr;     // shared address of the window byte mirror
 	uint32_t lane_tab_addr;  // shared address of this lane's match_lane_const() entry
+	// literal fast path (see the slot map in mg_device.cuh): the lane's slot for data byte b is
+	//   lit_addr + 2 * (((b >> lit_sh) & lowmask) | (b & topmask))  (+ 2 * ctx on lane 0)
 	uint32_t lit_addr;    // shared address of this lane's first slot
-	uint32_t lit_sh;      // byte >> lit_sh = tree prefix at this lane's depth
+	uint32_t lit_sh;      // b >> lit_sh = tree prefix at this lane's depth
+	uint32_t bit_shl;     // b << bit_shl puts the lane's data bit at bit 11 (the table's bit position)
+	uint32_t lowmask;     // prefix bits that index inside the row
+	uint32_t topmask;     // 0xC0 on depths 2..7: the top two bits of b select the row
 	uint32_t bitmask;     // 0x800 on tree lanes
 	uint32_t ctxmask;     // ~0 on lane 0
-	uint32_t treemask;    // ~0 on tree lanes
+	bool lit_active;      // lanes 0..8
 };
 
 __device__ __forceinline__ WalkEnv make_env(int lane, WarpShared* ws, const CtaShared* sh, const uint64_t* slab,
@@ -202,12 +207,25 @@ __device__ __forceinline__ WalkEnv make_env(int lane, WarpShared* ws, const CtaS
 	e.wb_addr = warp_base + (uint32_t)offsetof(WarpShared, wbytes);
 	e.lane_tab_addr = cta_base + (uint32_t)offsetof(CtaShared, lane_tab) + 16u * (uint32_t)lane;
 	const bool tree = lane >= 1 && lane <= 8;
-	const uint32_t first = lane == 0 ? S_ISMATCH : tree ? S_LIT + (1u << (lane - 1)) : S_DUMMY;
+	const uint32_t depth = tree ? (uint32_t)lane - 1 : 0;
+	uint32_t first = S_DUMMY;
+	if (lane == 0) first = S_ISMATCH;
+	else if (lane == 1) first = S_LIT01;
+	else if (lane == 2) first = S_LIT01 + 4;
+	else if (tree) first = S_LIT + (1u << (depth - 2));
 	e.lit_addr = e.probs.a + 2 * first;
-	e.lit_sh = tree ? 9u - (uint32_t)lane : 8u;
+	e.lit_sh = tree ? 8u - depth : 8u;
+	e.lowmask = !tree || depth == 0 ? 0u : depth == 1 ? 1u : (1u << (depth - 2)) - 1u;
+	e.topmask = tree && depth >= 2 ? 0xC0u : 0u;
 	e.bitmask = tree ? 0x800u : 0u;
 	e.ctxmask = lane == 0 ? 0xffffffffu : 0u;
-	e.treemask = tree ? 0xffffffffu : 0u;
+	e.bit_shl = 12u - e.lit_sh;
+	e.lit_active = lane <= 8;
+	// Opaque to the compiler on purpose: it otherwise re-derives these seven constants from
+	// threadIdx inside the literal loop (14 instructions per four literals) instead of keeping
+	// them in registers.
+	asm volatile("" : "+r"(e.lit_addr), "+r"(e.lit_sh), "+r"(e.bit_shl), "+r"(e.lowmask), "+r"(e.topmask), "+r"(e.bitmask),
+	             "+r"(e.ctxmask));
 	return e;
 }
 
@@ -339,7 +357,7 @@ __device__ __forceinline__ bool walker_rejoined(const WalkEnv& e, const Walker& 
 		return false;
 	const uint32_t* mine = reinterpret_cast<const uint32_t*>(e.probs_ptr);
 	const uint32_t* theirs = reinterpret_cast<const uint32_t*>(old->probs);
-	constexpr uint32_t WORDS = (S_TOTAL + 1) / 2;
+	constexpr uint32_t WORDS = S_COUNT / 2;
 	for (uint32_t base = 0; base < WORDS; base += 32) {  // uniform trip count: the vote needs every lane
 		const uint32_t i = base + (uint32_t)e.lane;
 		const bool differs = i < WORDS && mine[i] != theirs[i];
@@ -447,45 +465,83 @@ __device__ __forceinline__ uint32_t walk(const uint32_t MODE, const WalkEnv& e, 
 					uint32_t baddr = e.wb_addr + idx;
 					const uint32_t bend = baddr + run;
 					uint32_t cj = ctx;
-					uint32_t next_byte = lds_u8(baddr);  // one packet ahead, off the dependent chain
-					// the automaton reaches state 0 after at most three literals (lzma_state.c:34-40)
-					while (cj != 0 && baddr != bend) {
-						const uint32_t byte = next_byte;
-						next_byte = lds_u8(++baddr);
-						const uint32_t addr = e.lit_addr + 2 * ((byte >> e.lit_sh) + (cj & e.ctxmask));
-						const uint32_t bit11 = (byte << (12 - e.lit_sh)) & e.bitmask;
-						const uint32_t tr = lds_u32(e.trans_addr + ((lds_u16(addr) | bit11) << 2));
-						sts_u16(addr, tr);
-						k.t.acc += tr >> 16;
-						cj = (cj > 3 ? cj : 3) - 3;
+					// One literal on this lane.  b may carry other bytes above bit 7 (every use masks them
+					// off).  The probability of the NEXT literal is loaded before this one's is stored, so
+					// only the table lookup sits on the dependent chain; when both literals adapt the same
+					// slot the stored value is forwarded instead of the (stale) load.
+#define MG_LIT_ADDR(b, extra) (e.lit_addr + 2 * (((((b) >> e.lit_sh) & e.lowmask) | ((b) & e.topmask)) + (extra)))
+#define MG_LITERAL_STEP(bcur, bnext, extra_next)                                                         \
+	do {                                                                                                   \
+		const uint32_t addr_n_ = MG_LIT_ADDR(bnext, extra_next);                                           \
+		const uint32_t pl_ = lds_u16(addr_n_);                                                             \
+		const uint32_t tr_ = lds_u32(e.trans_addr + ((p | (((bcur) << e.bit_shl) & e.bitmask)) << 2));     \
+		sts_u16(addr, tr_);                                                                                \
+		k.t.acc += tr_ >> 16;                                                                              \
+		p = addr_n_ == addr ? (tr_ & 0xffffu) : pl_;                                                       \
+		addr = addr_n_;                                                                                    \
+	} while (0)
+					// Lanes 9..31 have no slot class of their own: they sit the whole run out (one
+					// divergence per run, no shared-memory traffic from them).
+					if (e.lit_active) {
+						uint32_t b = lds_u8(baddr);
+						uint32_t addr = MG_LIT_ADDR(b, cj & e.ctxmask);
+						uint32_t p = lds_u16(addr);
+						// head: the automaton reaches state 0 after at most three literals
+						// (lzma_state.c:34-40); carry on one by one up to a 4-byte boundary.  The byte
+						// past the end of the run is only used to form a (valid, unused) prefetch address.
+						while (baddr != bend && (cj != 0 || (baddr & 3u) != 0)) {
+							const uint32_t bn = lds_u8(baddr + 1);
+							cj = (cj > 3 ? cj : 3) - 3;
+							MG_LITERAL_STEP(b, bn, cj & e.ctxmask);
+							b = bn;
+							baddr++;
+						}
+						// body: four data bytes per shared-memory load
+						uint32_t groups = (bend - baddr) >> 2;
+						if (groups) {
+							uint32_t w = lds_u32(baddr);
+							do {
+								const uint32_t wn = lds_u32(baddr + 4);
+								MG_LITERAL_STEP(w, w >> 8, 0u);
+								MG_LITERAL_STEP(w >> 8, w >> 16, 0u);
+								MG_LITERAL_STEP(w >> 16, w >> 24, 0u);
+								MG_LITERAL_STEP(w >> 24, wn, 0u);
+								w = wn;
+								baddr += 4;
+							} while (--groups);
+							b = w;
+						}
+						while (baddr != bend) {
+							const uint32_t bn = lds_u8(baddr + 1);
+							MG_LITERAL_STEP(b, bn, 0u);
+							b = bn;
+							baddr++;
+						}
 					}
-					while (baddr != bend) {
-						const uint32_t byte = next_byte;
-						next_byte = lds_u8(++baddr);
-						const uint32_t addr = e.lit_addr + 2 * (byte >> e.lit_sh);
-						const uint32_t bit11 = (byte << (12 - e.lit_sh)) & e.bitmask;
-						const uint32_t tr = lds_u32(e.trans_addr + ((lds_u16(addr) | bit11) << 2));
-						sts_u16(addr, tr);
-						k.t.acc += tr >> 16;
-					}
+#undef MG_LIT_ADDR
+#undef MG_LITERAL_STEP
+					__syncwarp();
+					cj = ctx;
+					for (uint32_t i = 0; i < run && cj != 0; i++) cj = (cj > 3 ? cj : 3) - 3;
 					k.ctx = cj;
 					k.pos += run;
 					continue;
 				}
 				// ---- one matched literal (lzma_packet_encoder.c:123-130): the tree follows the match
 				// byte for as long as the prefixes agree ------------------------------------------------
-				const uint32_t byte = meta >> 16;
-				const uint32_t top = byte >> e.lit_sh;
-				const uint32_t bit11 = (byte << (12 - e.lit_sh)) & e.bitmask;
-				uint32_t off = top + (ctx & e.ctxmask);
+				const uint32_t byte = (meta >> 16) & 0xff;
 				const uint32_t mb = walker_mb(e, k);
-				const uint32_t extra = (0x100u + ((mb << (9 - e.lit_sh)) & 0x100u)) & e.treemask;
-				if ((mb >> e.lit_sh) == top) off += extra;
+				// variant stride of this lane's slot class: depth 0 -> 1, depth 1 -> 2, deeper -> 256
+				const uint32_t vstride = e.lane == 1 ? 1u : e.lane == 2 ? 2u : e.topmask ? 256u : 0u;
+				uint32_t off = (((byte >> e.lit_sh) & e.lowmask) | (byte & e.topmask)) + (ctx & e.ctxmask);
+				if ((mb >> e.lit_sh) == (byte >> e.lit_sh)) off += (1u + ((mb >> (e.lit_sh - 1)) & 1u)) * vstride;
 				k.ctx = ctx < 10 ? ctx - 3 : ctx - 6;
 				const uint32_t addr = e.lit_addr + 2 * off;
-				const uint32_t tr = lds_u32(e.trans_addr + ((lds_u16(addr) | bit11) << 2));
-				sts_u16(addr, tr);
-				k.t.acc += tr >> 16;
+				if (e.lit_active) {
+					const uint32_t tr = lds_u32(e.trans_addr + ((lds_u16(addr) | ((byte << e.bit_shl) & e.bitmask)) << 2));
+					sts_u16(addr, tr);
+					k.t.acc += tr >> 16;
+				}
 				k.pos++;
 				continue;
 			}
