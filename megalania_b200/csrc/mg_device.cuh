@@ -32,8 +32,10 @@ constexpr uint32_t T_INVALID = 0, T_LITERAL = 1, T_MATCH = 2, T_SHORT_REP = 3, T
 // The natural layout measured 1.84 wavefronts per probability access on the 1 MiB corpus.
 constexpr uint32_t LEN_LOW = 2, LEN_MID = 10, LEN_HIGH = 18, LEN_SLOTS = 274;
 constexpr uint32_t S_LIT = 0;                       // [3 trees][4 rows][64]: slot 0 of each row unused
-constexpr uint32_t S_LIT01 = 768 + 32;              // depth 0: [3], depth 1 (+4): [3][2]; over banks 16..21
-constexpr uint32_t S_ISMATCH = S_LIT01 + 12;        // [12]; is_match[0] is touched by every literal of a run
+constexpr uint32_t S_LIT01 = 768 + 40;              // depth 0: [3], depth 1 (+4): [3][2]; banks 20..25 of the deepest level
+constexpr uint32_t S_ISMATCH = S_LIT01 + 22;        // [12]; is_match[0] is touched by every literal of a run: bank 31.
+                                                    // (these two offsets minimise the clashes simulated over the 1 MiB corpus:
+                                                    // 1.05 wavefronts per access instead of 1.30)
 constexpr uint32_t S_ISREP = S_ISMATCH + 12;
 constexpr uint32_t S_ISREPG0 = S_ISREP + 12;
 constexpr uint32_t S_ISREPG1 = S_ISREPG0 + 12;
@@ -173,6 +175,12 @@ __device__ __forceinline__ void sts_u16(uint32_t addr, uint32_t v)
 __device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v)
 {
 	asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint4 lds_v4(uint32_t addr)
+{
+	uint4 v;
+	asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+	return v;
 }
 
 // Arrays in shared memory addressed by their 32-bit shared address.  Going through generic
@@ -525,53 +533,44 @@ __device__ __forceinline__ uint32_t meta_len(uint32_t meta) { return (meta >> 3)
 __device__ __forceinline__ uint32_t meta_byte(uint32_t meta) { return meta >> 16; }
 
 struct Window {
-	uint32_t meta, dist, meta_next, dist_next, meta_next2, dist_next2;  // current + two prefetched windows
+	uint32_t meta, dist;            // current window, decoded
+	uint32_t nlo, nhi, nbyte;       // next window exactly as loaded: nothing reads these registers until the
+	                                // window becomes current, so the loads stay in flight for a whole window
 	uint32_t base;     // multiple of 32; WINDOW_NONE = nothing loaded
 	uint32_t litmask;  // bit i: slot base+i is a canonical LITERAL
+	uint32_t ev_base;  // window whose literal events sit in the warp's event mirror (WINDOW_NONE = none)
 };
 constexpr uint32_t WINDOW_NONE = 0x7fffffe0u;  // never within 32 of a real position (inputs < 2 GiB... see mg_ctx_create)
 
-__device__ __forceinline__ void window_load(int lane, const uint64_t* __restrict__ slab,
-                                            const uint8_t* __restrict__ data, uint32_t n, uint32_t base,
-                                            uint32_t& meta, uint32_t& dist)
+__device__ __forceinline__ void window_fetch(int lane, const uint64_t* __restrict__ slab,
+                                             const uint8_t* __restrict__ data, uint32_t n, uint32_t base,
+                                             uint32_t& lo, uint32_t& hi, uint32_t& byte)
 {
 	const uint32_t i = base + (uint32_t)lane;
 	const bool in = i < n;
 	const uint64_t pk = in ? slab[i] : 0;
-	const uint32_t byte = in ? data[i] : 0;
-	const uint32_t len = pk_len(pk);
-	meta = pk_type(pk) | ((len < 0x1fff ? len : 0x1fff) << 3) | (byte << 16);
-	dist = pk_dist(pk);
+	byte = in ? data[i] : 0;
+	lo = (uint32_t)pk;
+	hi = (uint32_t)(pk >> 32);
 }
 
-// wbytes: shared address of the warp's 32-byte staging buffer; the window's data bytes are
-// mirrored there so that the literal-run loop can read them without a shuffle.
+__device__ __forceinline__ void window_decode(uint32_t lo, uint32_t hi, uint32_t byte, uint32_t& meta, uint32_t& dist)
+{
+	const uint32_t len = hi & 0xffffu, type = (hi >> 16) & 0xffu;
+	meta = type | ((len < 0x1fff ? len : 0x1fff) << 3) | (byte << 16);
+	dist = lo;
+}
+
 __device__ __forceinline__ void window_seek(int lane, Window& w, const uint64_t* __restrict__ slab,
-                                            const uint8_t* __restrict__ data, uint32_t n, uint32_t pos, uint32_t wbytes)
+                                            const uint8_t* __restrict__ data, uint32_t n, uint32_t pos)
 {
 	const uint32_t want = pos & ~31u;
 	if (want == w.base) return;
-	if (want == w.base + 32) {
-		// the common case: slide by one window, fetch the one two ahead (HBM latency exceeds the
-		// time a warp spends on 32 packets)
-		w.meta = w.meta_next;
-		w.dist = w.dist_next;
-		w.meta_next = w.meta_next2;
-		w.dist_next = w.dist_next2;
-	} else if (want == w.base + 64) {
-		w.meta = w.meta_next2;
-		w.dist = w.dist_next2;
-		window_load(lane, slab, data, n, want + 32, w.meta_next, w.dist_next);
-	} else {
-		window_load(lane, slab, data, n, want, w.meta, w.dist);
-		window_load(lane, slab, data, n, want + 32, w.meta_next, w.dist_next);
-	}
+	if (want != w.base + 32) window_fetch(lane, slab, data, n, want, w.nlo, w.nhi, w.nbyte);  // a jump: nothing prefetched
+	window_decode(w.nlo, w.nhi, w.nbyte, w.meta, w.dist);
 	w.base = want;
-	window_load(lane, slab, data, n, want + 64, w.meta_next2, w.dist_next2);
+	window_fetch(lane, slab, data, n, want + 32, w.nlo, w.nhi, w.nbyte);
 	w.litmask = __ballot_sync(FULL, (w.meta & 0xffffu) == META_LITERAL);
-	__syncwarp();  // readers of the previous window's bytes are done
-	asm volatile("st.shared.u8 [%0], %1;" ::"r"(wbytes + (uint32_t)lane), "r"(w.meta >> 16) : "memory");
-	__syncwarp();
 }
 
 __device__ __forceinline__ uint32_t window_meta(const Window& w, uint32_t pos)

@@ -20,7 +20,9 @@ constexpr uint32_t MAX_MATCH = 273;  // src/packet_enumerator.c:6-7
 struct FindScratch {
 	uint64_t ent_pk[MAX_K];
 	uint32_t ent_price[MAX_K];
-	uint32_t len_price[2][MAX_MATCH - 1];  // [0] match lengths, [1] rep lengths; index len-2
+	// [0] match lengths, [1] rep lengths; index len-2.  Only live during a find: between finds the
+	// walk keeps its literal-event mirror here (EVENT_* below, mg_kernels.cuh window_events()).
+	uint32_t len_price[2][MAX_MATCH - 1];
 	uint32_t hkey[MAX_K];                  // heap order -> price << 5 | entry index
 	uint8_t pop_order[MAX_K];              // entry indices, worst first
 	uint32_t count;
@@ -28,6 +30,12 @@ struct FindScratch {
 	uint32_t candidates;  // candidates enumerated by the last find
 	uint32_t chunks;      // 32-occurrence steps the last find took (its cost in the step budget)
 };
+
+// Literal-event mirror: for each of the nine literal lanes a row of 32 events (one per slot of the
+// current slab window) + 4 words of padding, so that a lane fetches four consecutive events with one
+// 16-byte load and the nine rows start on different banks.
+constexpr uint32_t EVENT_ROW_WORDS = 36, EVENT_LANES = 9;
+static_assert(EVENT_LANES * EVENT_ROW_WORDS * 4 <= sizeof(uint32_t) * 2 * (MAX_MATCH - 1), "event mirror must fit in len_price");
 
 // floor(c / len) for c*len < 2^32 via one multiply: recip[len] = floor((2^32-1)/len) + 1
 __device__ __forceinline__ uint32_t per_byte(uint32_t cost, uint32_t len, SmemU32 recip)

@@ -62,8 +62,6 @@ struct WarpShared {
 	Record rec;
 	FindScratch fs;
 	uint64_t bar;
-	uint32_t wbytes[8];  // data bytes of the current slab window (see window_seek)
-	uint64_t pad;
 	ChainStats stats;    // counters of the running launch (kept out of the register file; lane 0 only)
 };
 struct CtaShared {
@@ -170,8 +168,9 @@ struct WalkEnv {
 	const uint8_t* __restrict__ data;
 	uint32_t n;
 	uint32_t trans_addr;  // shared address of trans[]
-	uint32_t wb_addr;     // shared address of the window byte mirror
 	uint32_t lane_tab_addr;  // shared address of this lane's match_lane_const() entry
+	uint32_t ev_addr;        // shared address of the warp's literal-event mirror
+	uint32_t ev_row_addr;    // ... of this lane's row in it (lanes 0..8)
 	// literal fast path (see the slot map in mg_device.cuh): the lane's slot for data byte b is
 	//   lit_addr + 2 * (((b >> lit_sh) & lowmask) | (b & topmask))  (+ 2 * ctx on lane 0)
 	uint32_t lit_addr;    // shared address of this lane's first slot
@@ -204,8 +203,9 @@ __device__ __forceinline__ WalkEnv make_env(int lane, WarpShared* ws, const CtaS
 	e.data = data;
 	e.n = n;
 	e.trans_addr = e.trans.a;
-	e.wb_addr = warp_base + (uint32_t)offsetof(WarpShared, wbytes);
 	e.lane_tab_addr = cta_base + (uint32_t)offsetof(CtaShared, lane_tab) + 16u * (uint32_t)lane;
+	e.ev_addr = warp_base + (uint32_t)offsetof(WarpShared, fs) + (uint32_t)offsetof(FindScratch, len_price);
+	e.ev_row_addr = e.ev_addr + 4u * EVENT_ROW_WORDS * (uint32_t)(lane < (int)EVENT_LANES ? lane : 0);
 	const bool tree = lane >= 1 && lane <= 8;
 	const uint32_t depth = tree ? (uint32_t)lane - 1 : 0;
 	uint32_t first = S_DUMMY;
@@ -225,8 +225,34 @@ __device__ __forceinline__ WalkEnv make_env(int lane, WarpShared* ws, const CtaS
 	// threadIdx inside the literal loop (14 instructions per four literals) instead of keeping
 	// them in registers.
 	asm volatile("" : "+r"(e.lit_addr), "+r"(e.lit_sh), "+r"(e.bit_shl), "+r"(e.lowmask), "+r"(e.topmask), "+r"(e.bitmask),
-	             "+r"(e.ctxmask));
+	             "+r"(e.ctxmask), "+r"(e.ev_row_addr));
 	return e;
+}
+
+// Literal events of the current window.  Lane i prices nothing here: it turns ITS data byte into the
+// nine (slot address, bit) pairs the nine literal lanes will need at window position i and stores
+// them transposed, so the literal loop costs each lane one 16-byte load per four literals instead
+// of five ALU instructions per literal (the ALU pipe issues one warp instruction every two cycles
+// and was the limiter).  Event = shared address of the probability | bit << 31: `ev >> 18` is then
+// the byte offset of the table half for that bit (bit << 13), `ev & 0x3ffff` the address.
+// Plain literals only (automaton state 0; src/lzma_packet_encoder.c:106-121): the first three
+// literals after a match add the state to the is_match slot themselves.
+__device__ __forceinline__ void window_events(const WalkEnv& e, Window& w)
+{
+	__syncwarp();
+	const uint32_t b = (w.meta >> 16) & 0xffu;
+	const uint32_t out = e.ev_addr + 4u * (uint32_t)e.lane;
+	const uint32_t row = S_LIT + (b >> 6) * 64;
+	sts_u32(out + 0 * 4 * EVENT_ROW_WORDS, e.probs.a + 2 * S_ISMATCH);
+	sts_u32(out + 1 * 4 * EVENT_ROW_WORDS, (e.probs.a + 2 * S_LIT01) | ((b >> 7) << 31));
+	sts_u32(out + 2 * 4 * EVENT_ROW_WORDS, (e.probs.a + 2 * (S_LIT01 + 4 + (b >> 7))) | (((b >> 6) & 1u) << 31));
+#pragma unroll
+	for (uint32_t d = 2; d < 8; d++) {
+		const uint32_t slot = row + ((1u << (d - 2)) | ((b >> (8 - d)) & ((1u << (d - 2)) - 1u)));
+		sts_u32(out + (d + 1) * 4 * EVENT_ROW_WORDS, (e.probs.a + 2 * slot) | (((b >> (7 - d)) & 1u) << 31));
+	}
+	w.ev_base = w.base;
+	__syncwarp();
 }
 
 // Per-checkpoint bookkeeping kept beside the records, in DELTA form: cost and packets between the
@@ -304,6 +330,7 @@ __device__ __forceinline__ void walker_init(const WalkEnv& e, Walker& k)
 	k.pos = k.delta = k.ctx = k.mb = 0;
 	k.t = {0, 0, 0};
 	k.w.base = WINDOW_NONE;
+	k.w.ev_base = WINDOW_NONE;
 }
 
 __device__ __forceinline__ void walker_load(const WalkEnv& e, Walker& k, const Record* src, uint64_t* bar, uint32_t& parity)
@@ -316,6 +343,7 @@ __device__ __forceinline__ void walker_load(const WalkEnv& e, Walker& k, const R
 	k.ctx = m.ctx;
 	k.t = {cost, 0, 0};
 	k.w.base = WINDOW_NONE;
+	k.w.ev_base = WINDOW_NONE;
 	k.mb = MB_UNKNOWN;
 }
 
@@ -442,7 +470,7 @@ __device__ __forceinline__ uint32_t walk(const uint32_t MODE, const WalkEnv& e, 
 		}
 		if (k.pos - k.w.base >= 32u) {
 			tally_flush(k.t);
-			window_seek(e.lane, k.w, e.slab, e.data, e.n, k.pos, e.wb_addr);
+			window_seek(e.lane, k.w, e.slab, e.data, e.n, k.pos);
 		}
 		uint32_t limit = k.w.base + 32 < stop_pos ? k.w.base + 32 : stop_pos;
 		limit = ck.next < limit ? ck.next : limit;
@@ -462,64 +490,43 @@ __device__ __forceinline__ uint32_t walk(const uint32_t MODE, const WalkEnv& e, 
 					const uint32_t idx = k.pos - k.w.base;
 					uint32_t run = (uint32_t)__ffs((int)~(k.w.litmask >> idx)) - 1u;
 					run = run < limit - k.pos ? run : limit - k.pos;
-					uint32_t baddr = e.wb_addr + idx;
-					const uint32_t bend = baddr + run;
+					if (k.w.ev_base != k.w.base) window_events(e, k.w);
 					uint32_t cj = ctx;
-					// One literal on this lane.  b may carry other bytes above bit 7 (every use masks them
-					// off).  The probability of the NEXT literal is loaded before this one's is stored, so
-					// only the table lookup sits on the dependent chain; when both literals adapt the same
-					// slot the stored value is forwarded instead of the (stale) load.
-#define MG_LIT_ADDR(b, extra) (e.lit_addr + 2 * (((((b) >> e.lit_sh) & e.lowmask) | ((b) & e.topmask)) + (extra)))
-#define MG_LITERAL_STEP(bcur, bnext, extra_next)                                                         \
-	do {                                                                                                   \
-		const uint32_t addr_n_ = MG_LIT_ADDR(bnext, extra_next);                                           \
-		const uint32_t pl_ = lds_u16(addr_n_);                                                             \
-		const uint32_t tr_ = lds_u32(e.trans_addr + ((p | (((bcur) << e.bit_shl) & e.bitmask)) << 2));     \
-		sts_u16(addr, tr_);                                                                                \
-		k.t.acc += tr_ >> 16;                                                                              \
-		p = addr_n_ == addr ? (tr_ & 0xffffu) : pl_;                                                       \
-		addr = addr_n_;                                                                                    \
-	} while (0)
 					// Lanes 9..31 have no slot class of their own: they sit the whole run out (one
 					// divergence per run, no shared-memory traffic from them).
 					if (e.lit_active) {
-						uint32_t b = lds_u8(baddr);
-						uint32_t addr = MG_LIT_ADDR(b, cj & e.ctxmask);
-						uint32_t p = lds_u16(addr);
+						uint32_t ea = e.ev_row_addr + 4u * idx;
+						const uint32_t eend = ea + 4u * run;
+#define MG_LITERAL_STEP(ev, extra)                                                          \
+	do {                                                                                      \
+		const uint32_t ev_ = (ev);                                                            \
+		const uint32_t pa_ = (ev_ & 0x3ffffu) + (extra);                                      \
+		const uint32_t tr_ = lds_u32(e.trans_addr + (lds_u16(pa_) << 2) + (ev_ >> 18));       \
+		sts_u16(pa_, tr_);                                                                    \
+		k.t.acc += tr_ >> 16;                                                                 \
+	} while (0)
 						// head: the automaton reaches state 0 after at most three literals
-						// (lzma_state.c:34-40); carry on one by one up to a 4-byte boundary.  The byte
-						// past the end of the run is only used to form a (valid, unused) prefetch address.
-						while (baddr != bend && (cj != 0 || (baddr & 3u) != 0)) {
-							const uint32_t bn = lds_u8(baddr + 1);
+						// (lzma_state.c:34-40); carry on one by one up to a 16-byte boundary of the row
+						while (ea != eend && (cj != 0 || (ea & 15u) != 0)) {
+							MG_LITERAL_STEP(lds_u32(ea), 2u * (cj & e.ctxmask));
+							ea += 4;
 							cj = (cj > 3 ? cj : 3) - 3;
-							MG_LITERAL_STEP(b, bn, cj & e.ctxmask);
-							b = bn;
-							baddr++;
 						}
-						// body: four data bytes per shared-memory load
-						uint32_t groups = (bend - baddr) >> 2;
-						if (groups) {
-							uint32_t w = lds_u32(baddr);
-							do {
-								const uint32_t wn = lds_u32(baddr + 4);
-								MG_LITERAL_STEP(w, w >> 8, 0u);
-								MG_LITERAL_STEP(w >> 8, w >> 16, 0u);
-								MG_LITERAL_STEP(w >> 16, w >> 24, 0u);
-								MG_LITERAL_STEP(w >> 24, wn, 0u);
-								w = wn;
-								baddr += 4;
-							} while (--groups);
-							b = w;
+						// body: the events of four literals per shared-memory load
+						for (uint32_t groups = (eend - ea) >> 4; groups != 0; groups--) {
+							const uint4 v = lds_v4(ea);
+							MG_LITERAL_STEP(v.x, 0u);
+							MG_LITERAL_STEP(v.y, 0u);
+							MG_LITERAL_STEP(v.z, 0u);
+							MG_LITERAL_STEP(v.w, 0u);
+							ea += 16;
 						}
-						while (baddr != bend) {
-							const uint32_t bn = lds_u8(baddr + 1);
-							MG_LITERAL_STEP(b, bn, 0u);
-							b = bn;
-							baddr++;
+						while (ea != eend) {
+							MG_LITERAL_STEP(lds_u32(ea), 0u);
+							ea += 4;
 						}
-					}
-#undef MG_LIT_ADDR
 #undef MG_LITERAL_STEP
+					}
 					__syncwarp();
 					cj = ctx;
 					for (uint32_t i = 0; i < run && cj != 0; i++) cj = (cj > 3 ? cj : 3) - 3;
@@ -978,7 +985,7 @@ __global__ void __launch_bounds__(CTA_THREADS, MG_ANNEAL_MIN_CTAS) anneal_kernel
 				pos = k.pos;
 				if (pos - k.w.base >= 32u) {
 					tally_flush(k.t);
-					window_seek(lane, k.w, slab, a.data, n, pos, e.wb_addr);
+					window_seek(lane, k.w, slab, a.data, n, pos);
 				}
 				const uint32_t meta0 = window_meta(k.w, pos);
 				const uint32_t dist0 = window_dist(k.w, pos);
@@ -1026,6 +1033,7 @@ __global__ void __launch_bounds__(CTA_THREADS, MG_ANNEAL_MIN_CTAS) anneal_kernel
 				const long long t_find = clock64();
 				const uint32_t count = warp_find(lane, e.probs, e.trans, e.recip, &ws->fs, a.data, n, a.occ_start, a.occ,
 				                                 walker_model(e, k), excluded, a.k);
+				k.w.ev_base = WINDOW_NONE;  // the finder's length tables share the event mirror's memory
 				if (lane == 0) {
 					cs.candidates += ws->fs.candidates;
 					cs.chunks += ws->fs.chunks;
@@ -1315,7 +1323,6 @@ __global__ void __launch_bounds__(32) encode_kernel(EncodeArgs a)
 {
 	__shared__ __align__(16) Record rec;
 	__shared__ uint32_t ev[32];
-	__shared__ uint32_t wbytes[8];
 	const int lane = threadIdx.x;
 	Model m;
 	model_init(lane, SmemU16{smem_u32(rec.probs)}, m);
@@ -1324,7 +1331,7 @@ __global__ void __launch_bounds__(32) encode_kernel(EncodeArgs a)
 	w.base = WINDOW_NONE;
 	uint32_t err = 0;
 	while (m.pos < a.n) {
-		window_seek(lane, w, a.slab, a.data, a.n, m.pos, smem_u32(wbytes));
+		window_seek(lane, w, a.slab, a.data, a.n, m.pos);
 		const uint32_t meta = window_meta(w, m.pos);
 		const uint32_t type = meta_type(meta), len = meta_len(meta), dist = window_dist(w, m.pos);
 		const uint32_t byte = meta_byte(meta) & 0xff;
