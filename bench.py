@@ -5,8 +5,10 @@
     python bench.py --impl reference [--gpus N] --steps K --warmup W  # the reference's CPU path
 
 A "step" = every chain runs successful neighbour proposals (mutate, repair, full cost, accept/undo)
-until it has priced `--packet-budget` packets, on the 1 MiB synthetic mixed text/binary input of
-BASELINE.json configs[1], all chains starting from the all-literal slab like the reference does.  `value` counts successful
+for `--step-ms` of SM clocks (a proposal cut by the deadline is suspended at a checkpoint and carried
+on by the next step, so every warp works to the end of the step), on the 1 MiB synthetic mixed
+text/binary input of BASELINE.json configs[1], all chains starting from the all-literal slab like
+the reference does (`--packet-budget` gives a reproducible budget instead).  `value` counts successful
 evaluations of ALL chains on ALL GPUs per second of device time (CUDA events on the library's
 launch stream, max over ranks).  `e2e` is the same metric through the one-shot host call with
 host buffers in and out (input upload, index build, chain allocation, best slab read-back).
@@ -241,9 +243,12 @@ def run_cuda(args) -> None:
 
     step_no = [0]
 
+    sm_khz = int(getattr(props, "clock_rate", 0) or peaks()[0].get("sm_max_mhz", 1965.0) * 1000)
+    cycle_budget = 0 if args.packet_budget else int(args.step_ms * sm_khz)
+
     def step(first_eval):
         st = an.run(args.evals, schedule=mg.SCHEDULE_REFERENCE, step=0, first_eval=mg.CONTINUE_EVALS,
-                    packet_budget=args.packet_budget)
+                    packet_budget=args.packet_budget, cycle_budget=cycle_budget, suspend=True)
         step_no[0] += 1
         if step_no[0] % args.exchange_every == 0:
             exchange()
@@ -315,7 +320,7 @@ def run_cuda(args) -> None:
         for s in range(args.e2e_steps):
             c2 = mg.Context(data, device=local)                   # H2D of the input + index build
             best, cost, st2 = mg.anneal_oneshot(c2, chains=e2e_chains, evals=args.evals, seed=args.seed + s,
-                                                packet_budget=args.packet_budget)
+                                                packet_budget=args.packet_budget, cycle_budget=cycle_budget, suspend=True)
             e2e_evals += st2["evals"]                              # best slab + cost came back to the host
             c2.close()
         barrier()
@@ -340,8 +345,10 @@ def run_cuda(args) -> None:
                 "scaling": "weak", "vs_baseline": None, "dtype": "u16 probabilities / u64 cost (integer)",
                 "data": "synthetic",
                 "config": {"workload": WORKLOAD, "input_bytes": n, "chains_per_gpu": chains,
-                           "step": f"each chain runs whole evaluations until it has priced {args.packet_budget} packets "
-                                   f"(cap {args.evals} evaluations)", "top_k": 20, "l2": "inputs_exceed_l2",
+                           "step": (f"each chain prices exactly {args.packet_budget} packets" if args.packet_budget else
+                                    f"each chain anneals for {args.step_ms} ms of SM clocks ({cycle_budget} cycles)") +
+                                   "; a proposal cut by the budget is suspended at a checkpoint and finished by the next step",
+                           "top_k": 20, "l2": "inputs_exceed_l2",
                            "per_gpu_slab_bytes": chains * n * 8,
                            "multi_gpu": f"independent chains per rank; all-gather of best costs + NCCL broadcast of the best slab every {args.exchange_every} steps"},
                 "device_ms_per_step": 1e3 * device_s / args.steps,
@@ -351,7 +358,10 @@ def run_cuda(args) -> None:
                 "roofline": roofline, "roofline_issue": roofline_issue, "cpu_baseline": cpu,
                 "stats": {"evals": total_evals, "modelled_bits": total_bits, "packets": total_packets,
                           "attempts": agg["attempts"], "accepted": agg["accepted"],
-                          "finder_candidates": agg["finder_candidates"], "log_overflows": agg["log_overflows"]}}
+                          "finder_candidates": agg["finder_candidates"], "log_overflows": agg["log_overflows"],
+                          "finder_share_of_warp_time": agg["finder_cycles"] / max(1, agg["chain_cycles"]),
+                          "warp_busy_fraction": agg["chain_cycles"] / max(1, chains * agg["max_chain_cycles"]) * 1.0 if args.steps == 1 else None,
+                          "suspended_resumed": "proposals cut by the step deadline are finished by the next step"}}
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()
@@ -367,10 +377,10 @@ def main() -> None:
     ap.add_argument("--size", type=int, default=1 << 20)
     ap.add_argument("--chains", type=int, default=0, help="chains per GPU (default: SMs x --warps-per-sm)")
     ap.add_argument("--warps-per-sm", type=int, default=32)
-    ap.add_argument("--evals", type=int, default=1000, help="cap on successful evaluations per chain per step")
-    ap.add_argument("--packet-budget", type=int, default=8_000_000,
-                    help="a chain ends its step after the evaluation that brings its priced packets to this many "
-                         "(time-boxed steps keep all warps busy; about 16 evaluations per chain per step at 1 MiB)")
+    ap.add_argument("--evals", type=int, default=1_000_000, help="cap on successful evaluations per chain per step")
+    ap.add_argument("--step-ms", type=float, default=1000.0, help="length of a step in milliseconds of SM clocks")
+    ap.add_argument("--packet-budget", type=int, default=0,
+                    help="instead of --step-ms: a chain ends its step when it has priced this many packets (reproducible)")
     ap.add_argument("--seed", type=int, default=1673551)
     ap.add_argument("--exchange-every", type=int, default=4, help="multi-GPU: best-slab broadcast every this many steps")
     ap.add_argument("--e2e-steps", type=int, default=2)

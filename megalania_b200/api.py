@@ -336,11 +336,11 @@ class Annealer:
 
 def anneal_oneshot(ctx: Context, *, chains: int, evals: int, init: np.ndarray | None = None, seed: int = 1673551,
                    top_k: int = 20, schedule: int = SCHEDULE_REFERENCE, step: int = 0, num_iters: int = 0,
-                   packet_budget: int = 0):
+                   packet_budget: int = 0, cycle_budget: int = 0, suspend: bool = False):
     """Host buffers in, host buffers out: the call the end-to-end benchmark times."""
     lib = ctx._lib
     p = AnnealParams(chains, top_k, 0, 0, 1, 0, seed)
-    rp = AnnealRunParams(evals, 0, schedule, step, num_iters, 0, None, packet_budget, 0, 0, 0)
+    rp = AnnealRunParams(evals, 0, schedule, step, num_iters, 0, None, packet_budget, 0, int(suspend), cycle_budget)
     st = AnnealStats()
     best = np.zeros(ctx.n, dtype=PACKET_DTYPE)
     cost = C.c_uint64(0)
