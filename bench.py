@@ -194,6 +194,11 @@ def run_reference(args) -> None:
 # the CUDA arm
 # ------------------------------------------------------------------------------------------------
 def run_cuda(args) -> None:
+    # stdout carries exactly one JSON line: anything libraries print on the way (NCCL's version
+    # banner under NCCL_DEBUG) goes to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import megalania_b200 as mg
 
@@ -362,7 +367,8 @@ def run_cuda(args) -> None:
                           "finder_share_of_warp_time": agg["finder_cycles"] / max(1, agg["chain_cycles"]),
                           "warp_busy_fraction": agg["chain_cycles"] / max(1, chains * agg["max_chain_cycles"]) * 1.0 if args.steps == 1 else None,
                           "suspended_resumed": "proposals cut by the step deadline are finished by the next step"}}
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()

@@ -111,6 +111,9 @@ class ReplicaExchange:
         if self.rank == src:
             export_fn(buffer)
         self.dist.broadcast(buffer, src=src)
+        # the library works on its own stream: the broadcast must have landed before it reads the buffer
+        if getattr(buffer, "is_cuda", False):
+            torch.cuda.synchronize(buffer.device)
         if self.rank != src:
             import_fn(buffer)
         return src, int(costs[src])
