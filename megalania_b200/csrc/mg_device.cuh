@@ -176,6 +176,10 @@ __device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v)
 {
 	asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
+__device__ __forceinline__ void sts_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d)
+{
+	asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
 __device__ __forceinline__ uint4 lds_v4(uint32_t addr)
 {
 	uint4 v;
@@ -538,7 +542,7 @@ struct Window {
 	                                // window becomes current, so the loads stay in flight for a whole window
 	uint32_t base;     // multiple of 32; WINDOW_NONE = nothing loaded
 	uint32_t litmask;  // bit i: slot base+i is a canonical LITERAL
-	uint32_t ev_base;  // window whose literal events sit in the warp's event mirror (WINDOW_NONE = none)
+	uint32_t ev_base;  // window base | 1 literal events mirrored | 2 MATCH descriptors mirrored (see window_events / window_matches)
 };
 constexpr uint32_t WINDOW_NONE = 0x7fffffe0u;  // never within 32 of a real position (inputs < 2 GiB... see mg_ctx_create)
 

@@ -35,7 +35,9 @@ struct FindScratch {
 // current slab window) + 4 words of padding, so that a lane fetches four consecutive events with one
 // 16-byte load and the nine rows start on different banks.
 constexpr uint32_t EVENT_ROW_WORDS = 36, EVENT_LANES = 9;
-static_assert(EVENT_LANES * EVENT_ROW_WORDS * 4 <= sizeof(uint32_t) * 2 * (MAX_MATCH - 1), "event mirror must fit in len_price");
+// ... followed by one 16-byte MATCH descriptor per slot of the window (window_matches()).
+constexpr uint32_t MATCH_DESC_OFFSET = EVENT_LANES * EVENT_ROW_WORDS * 4;
+static_assert(MATCH_DESC_OFFSET + 32 * 16 <= sizeof(uint32_t) * 2 * (MAX_MATCH - 1), "window mirrors must fit in len_price");
 
 // floor(c / len) for c*len < 2^32 via one multiply: recip[len] = floor((2^32-1)/len) + 1
 __device__ __forceinline__ uint32_t per_byte(uint32_t cost, uint32_t len, SmemU32 recip)

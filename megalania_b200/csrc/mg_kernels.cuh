@@ -251,7 +251,25 @@ __device__ __forceinline__ void window_events(const WalkEnv& e, Window& w)
 		const uint32_t slot = row + ((1u << (d - 2)) | ((b >> (8 - d)) & ((1u << (d - 2)) - 1u)));
 		sts_u32(out + (d + 1) * 4 * EVENT_ROW_WORDS, (e.probs.a + 2 * slot) | (((b >> (7 - d)) & 1u) << 31));
 	}
-	w.ev_base = w.base;
+	w.ev_base = (w.ev_base & ~31u) == w.base ? (w.ev_base | 1u) : (w.base | 1u);
+	__syncwarp();
+}
+
+// MATCH descriptors of the current window: lane i turns ITS slot, if it holds a MATCH that is valid
+// at position base+i, into the packed words the MATCH fast path needs (match_desc() with state 0)
+// and stores {F, G, amask | direct << 26, dist}; F == 0 marks every other slot.  ~70 instructions
+// once per window for all its matches instead of once per match.
+__device__ __forceinline__ void window_matches(const WalkEnv& e, Window& w)
+{
+	__syncwarp();
+	const uint32_t len = meta_len(w.meta), dist = w.dist, pos = w.base + (uint32_t)e.lane;
+	const bool ok = meta_type(w.meta) == T_MATCH && len - 2 <= MAX_MATCH - 2 && pos < e.n && len <= e.n - pos && dist < pos;
+	if (__any_sync(FULL, ok)) {
+		MatchDesc d = {0, 0, 0, 0};
+		if (ok) d = match_desc(0, len, dist);
+		sts_v4(e.ev_addr + MATCH_DESC_OFFSET + 16u * (uint32_t)e.lane, d.F, d.G, d.amask | (d.direct << 26), dist);
+	}
+	w.ev_base = (w.ev_base & ~31u) == w.base ? (w.ev_base | 2u) : (w.base | 2u);
 	__syncwarp();
 }
 
@@ -490,7 +508,7 @@ __device__ __forceinline__ uint32_t walk(const uint32_t MODE, const WalkEnv& e, 
 					const uint32_t idx = k.pos - k.w.base;
 					uint32_t run = (uint32_t)__ffs((int)~(k.w.litmask >> idx)) - 1u;
 					run = run < limit - k.pos ? run : limit - k.pos;
-					if (k.w.ev_base != k.w.base) window_events(e, k.w);
+					if ((k.w.ev_base | 2u) != (k.w.base | 3u)) window_events(e, k.w);
 					uint32_t cj = ctx;
 					// Lanes 9..31 have no slot class of their own: they sit the whole run out (one
 					// divergence per run, no shared-memory traffic from them).
@@ -556,19 +574,19 @@ __device__ __forceinline__ uint32_t walk(const uint32_t MODE, const WalkEnv& e, 
 			// is priced straight from the slab.  One warp step: F/G/amask are the same on every lane,
 			// the lane's four constants turn them into its slot and bit ----------------------------
 			if (MODE != WALK_REPAIR_HEAD && meta_type(meta) == T_MATCH) {
-				const uint32_t len = meta_len(meta);
-				const uint32_t dist = window_dist(k.w, k.pos);
-				if (len - 2 <= MAX_MATCH - 2 && len <= e.n - k.pos && dist < k.pos) {
-					const MatchDesc d = match_desc(k.ctx, len, dist);
+				if ((k.w.ev_base | 1u) != (k.w.base | 3u)) window_matches(e, k.w);
+				const uint4 d = lds_v4(e.ev_addr + MATCH_DESC_OFFSET + 16u * (k.pos - k.w.base));
+				if (d.x != 0) {
+					const uint32_t len = meta_len(meta), dist = d.w, amask = d.z & 0x3ffffffu;
 					uint32_t shb, mask2, base, sel;
 					asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
 					             : "=r"(shb), "=r"(mask2), "=r"(base), "=r"(sel)
 					             : "r"(e.lane_tab_addr));
-					const uint32_t nwb = (d.F >> shb) & mask2;
-					const uint32_t slot = base + __byte_perm(d.G, 0, sel) + (nwb >> 1);
-					if ((d.amask >> e.lane) & 1u) code_bit(e.probs, e.trans, slot, (nwb & 1u) << 11, k.t.acc);
-					if (e.lane == 0) k.t.acc += d.direct << 11;  // src/perplexity_encoder.c:12-17
-					k.t.bits += (uint32_t)__popc(d.amask) - 9u;
+					const uint32_t nwb = (d.x >> shb) & mask2;
+					const uint32_t slot = base + __byte_perm(d.y | k.ctx, 0, sel) + (nwb >> 1);
+					if ((amask >> e.lane) & 1u) code_bit(e.probs, e.trans, slot, (nwb & 1u) << 11, k.t.acc);
+					if (e.lane == 0) k.t.acc += (d.z >> 26) << 11;  // src/perplexity_encoder.c:12-17
+					k.t.bits += (uint32_t)__popc(amask) - 9u;
 					// src/lzma_state.c:59-65, 29-57
 					const uint32_t r0 = e.reps.get(0), r1 = e.reps.get(1), r2 = e.reps.get(2);
 					e.reps.set(0, dist);
@@ -1033,7 +1051,7 @@ __global__ void __launch_bounds__(CTA_THREADS, MG_ANNEAL_MIN_CTAS) anneal_kernel
 				const long long t_find = clock64();
 				const uint32_t count = warp_find(lane, e.probs, e.trans, e.recip, &ws->fs, a.data, n, a.occ_start, a.occ,
 				                                 walker_model(e, k), excluded, a.k);
-				k.w.ev_base = WINDOW_NONE;  // the finder's length tables share the event mirror's memory
+				k.w.ev_base = WINDOW_NONE;  // the finder's length tables share the window mirrors' memory
 				if (lane == 0) {
 					cs.candidates += ws->fs.candidates;
 					cs.chunks += ws->fs.chunks;
