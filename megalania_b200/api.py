@@ -175,11 +175,19 @@ class Context:
         self._data = np.ascontiguousarray(np.frombuffer(bytes(data), dtype=np.uint8))
         self.n = int(self._data.size)
         self._h = C.c_void_p()
+        self._children = []  # weak references to the Annealers living on this context
         _check(self._lib.mg_ctx_create(self._data.ctypes.data_as(C.c_void_p), self.n, LZMAProperties(0, 0, 0),
                                        device, C.byref(self._h)))
 
     def close(self) -> None:
+        """Destroys the context; chain populations created on it are destroyed first (mg_ctx_destroy
+        does the same on the C side), whatever order Python finalises the objects in."""
         if getattr(self, "_h", None):
+            for ref in self._children:
+                child = ref()
+                if child is not None:
+                    child.close()
+            self._children = []
             self._lib.mg_ctx_destroy(self._h)
             self._h = None
 
@@ -260,6 +268,8 @@ class Annealer:
                                    trace_capacity, seed)
         self._h = C.c_void_p()
         _check(self._lib.mg_anneal_create(ctx._h, C.byref(self.params), C.byref(self._h)))
+        import weakref
+        ctx._children.append(weakref.ref(self))
 
     def close(self) -> None:
         if getattr(self, "_h", None):

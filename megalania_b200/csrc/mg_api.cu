@@ -47,6 +47,7 @@ struct mg_ctx {
 	Tables tables{};
 	int sm_count = 0;
 	double index_ms = 0;
+	std::vector<mg_anneal*> annealers;  // live chain populations on this context (destroyed with it)
 };
 
 struct DevBuf {
@@ -190,6 +191,8 @@ extern "C" MG_API void mg_ctx_destroy(mg_ctx* ctx)
 {
 	if (!ctx) return;
 	cudaSetDevice(ctx->device);
+	// chain populations hold pointers into the context: they go first (their handles die with it)
+	while (!ctx->annealers.empty()) mg_anneal_destroy(ctx->annealers.back());
 	if (ctx->stream) cudaStreamSynchronize(ctx->stream);
 	cudaFree(ctx->d_data);
 	cudaFree(ctx->d_occ_start);
@@ -587,6 +590,14 @@ extern "C" MG_API size_t mg_anneal_chain_bytes(const mg_ctx* ctx, const mg_annea
 extern "C" MG_API void mg_anneal_destroy(mg_anneal* an)
 {
 	if (!an) return;
+	{
+		std::vector<mg_anneal*>& live = an->ctx->annealers;
+		for (size_t i = 0; i < live.size(); i++)
+			if (live[i] == an) {
+				live.erase(live.begin() + (long)i);
+				break;
+			}
+	}
 	cudaSetDevice(an->ctx->device);
 	cudaStreamSynchronize(an->ctx->stream);
 	cudaFree(an->d_slabs);
@@ -676,6 +687,7 @@ extern "C" MG_API int mg_anneal_create(mg_ctx* ctx, const mg_anneal_params* para
 		return rc;
 	}
 	an->have_slab.assign(C, 0);
+	ctx->annealers.push_back(an);
 	*out = an;
 	return MG_OK;
 }

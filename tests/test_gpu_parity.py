@@ -148,3 +148,33 @@ def test_suspended_proposals_do_not_change_trajectories(mg, port, corpora, kind,
             assert (g["flags"][attempts:] == 0).all()
             assert int(best[c]) == bc
         an.close()
+
+
+def test_clock_boxed_steps_keep_trajectories(mg, port, corpora):
+    """SM-clock budgets (mg_anneal_run_params.cycle_budget): how many evaluations fit in a step is
+    not reproducible, the trajectory of every chain is - suspended proposals included."""
+    n, chains, seed = 16384, 6, 77
+    data = corpora("mixed", n)
+    with mg.Context(data) as ctx:
+        an = mg.Annealer(ctx, chains, trace_capacity=8192, seed=seed, checkpoint_stride=512)
+        an.set_slab(None, adopt_cost=False)
+        got = [[] for _ in range(chains)]
+        for _ in range(12):
+            st = an.run(100000, cycle_budget=3_000_000, suspend=True, first_eval=mg.CONTINUE_EVALS)
+            assert st["max_chain_cycles"] < 100_000_000  # a chain stops at its next checkpoint or evaluation boundary
+            for c in range(chains):
+                got[c].append(an.trace(c))
+        cur, best = an.costs()
+        lit = mg.literal_slab(n)
+        for c in range(chains):
+            g = np.concatenate(got[c])
+            evals = int((g["flags"] & 1).sum())
+            assert evals >= 5
+            slab, bslab = lit.copy(), lit.copy()
+            attempts, bc, cc, _, trace = port.anneal_epoch(data, slab, bslab, 0, 0, rng_mode=1,
+                                                           rng_state=port.chain_seed(seed, c), evals=evals)
+            assert len(g) >= attempts
+            assert (g["flags"][:attempts] == trace["flags"]).all()
+            assert (g["cost"][:attempts] == trace["cost"]).all()
+            assert int(best[c]) == bc
+        an.close()
