@@ -162,6 +162,12 @@ typedef struct {
 	uint64_t cycle_budget;  /* 0 = none; else SM clocks after which the chains stop: at the end of the evaluation
 	                           in flight, or (with suspend) at the next checkpoint it writes.  A wall-clock box:
 	                           how many evaluations fit is not reproducible, each chain's trajectory still is */
+	const uint32_t* regions; /* NULL, or host array [chains][2]: chain c only mutates packets that START in the byte range
+	                           [regions[2c], regions[2c+1]) (it still re-prices everything after them).  Instead of
+	                           src/packet_slab_neighbour.c:163's uniform packet index the chain draws a byte of
+	                           its range and mutates the first packet at or after it.  With all chains started
+	                           from one slab this turns the population into a cooperative search: see
+	                           mg_anneal_merge_regions */
 } mg_anneal_run_params;
 #define MG_CONTINUE_EVALS 0xffffffffu
 
@@ -207,6 +213,18 @@ MG_API size_t mg_anneal_chain_bytes(const mg_ctx* ctx, const mg_anneal_params* p
  * src/main.c:74,87).  Best slabs/costs are reset only when reset_best != 0. */
 MG_API int mg_anneal_set_slab(mg_anneal* an, uint32_t first, uint32_t count, const LZMAPacket* slab,
                        int adopt_cost, int reset_best);
+
+/* Cooperative regions.  After region-confined chains (mg_anneal_run_params.regions) have run from a
+ * common slab, builds the slab that takes region r = [bounds[r], bounds[r+1]) from chain owners[r]
+ * (bounds[0] = 0, bounds[nregions] = n), stores it as the current slab of chain `dst_chain`, repairs the
+ * packets the seams broke with the reference's own repair rule (src/packet_slab_neighbour.c:82-117: SHORT_REP
+ * and LONG_REP packets whose rep distances changed), prices it exactly and rewrites the chain's checkpoints.
+ * *cost_out receives the merged slab's cost: the caller keeps it only if it beats the best single chain. */
+MG_API int mg_anneal_merge_regions(mg_anneal* an, uint32_t nregions, const uint32_t* bounds, const uint32_t* owners,
+                                   uint32_t dst_chain, uint64_t* cost_out);
+/* Makes every chain's current slab (with its checkpoints and cost) a copy of chain `src_chain`'s: the restart
+ * from the best slab of src/main.c:75-77, without a round trip through the host.  Best slabs are kept. */
+MG_API int mg_anneal_broadcast_chain(mg_anneal* an, uint32_t src_chain);
 
 /* Runs `evals` successful proposals on every chain: packet_slab_neighbour_generate
  * (src/packet_slab_neighbour.c:154-173) + the accept/undo/best logic of src/main.c:78-102.

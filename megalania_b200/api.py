@@ -53,7 +53,7 @@ class AnnealRunParams(C.Structure):
     _fields_ = [("evals", C.c_uint32), ("max_attempts", C.c_uint32), ("schedule", C.c_uint32),
                 ("step", C.c_uint32), ("num_iters", C.c_uint32), ("first_eval", C.c_uint32),
                 ("temperatures", C.POINTER(C.c_float)), ("packet_budget", C.c_uint64), ("no_early_exit", C.c_uint32),
-                ("suspend", C.c_uint32), ("cycle_budget", C.c_uint64)]
+                ("suspend", C.c_uint32), ("cycle_budget", C.c_uint64), ("regions", C.POINTER(C.c_uint32))]
 
 
 class AnnealStats(C.Structure):
@@ -81,7 +81,7 @@ EXPORTS = [
     "mg_anneal_destroy", "mg_anneal_chain_bytes", "mg_anneal_set_slab", "mg_anneal_run", "mg_anneal_costs",
     "mg_anneal_get_slab", "mg_anneal_get_trace", "mg_anneal_swap_chains", "mg_anneal_device_slab",
     "mg_anneal_refresh_chain", "mg_anneal_oneshot", "mg_debug_model_after_prefix", "mg_anneal_export_slab",
-    "mg_anneal_import_slab",
+    "mg_anneal_import_slab", "mg_anneal_merge_regions", "mg_anneal_broadcast_chain",
 ]
 
 _lib = None
@@ -129,6 +129,8 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
     L.mg_anneal_swap_chains.argtypes = [vp, u32, u32]
     L.mg_anneal_device_slab.argtypes = [vp, u32, i32, C.POINTER(vp), C.POINTER(sz)]
     L.mg_anneal_refresh_chain.argtypes = [vp, u32, i32]
+    L.mg_anneal_merge_regions.argtypes = [vp, u32, vp, vp, u32, C.POINTER(u64)]
+    L.mg_anneal_broadcast_chain.argtypes = [vp, u32]
     L.mg_anneal_export_slab.argtypes = [vp, u32, i32, vp]
     L.mg_anneal_import_slab.argtypes = [vp, u32, vp, i32]
     L.mg_anneal_oneshot.argtypes = [vp, C.POINTER(AnnealParams), C.POINTER(AnnealRunParams), vp, vp,
@@ -293,7 +295,7 @@ class Annealer:
 
     def run(self, evals: int, *, schedule: int = SCHEDULE_REFERENCE, step: int = 0, num_iters: int = 0,
             first_eval: int = 0, max_attempts: int = 0, temperatures=None, packet_budget: int = 0,
-            early_exit: bool = True, suspend: bool = False, cycle_budget: int = 0) -> dict:
+            early_exit: bool = True, suspend: bool = False, cycle_budget: int = 0, regions=None) -> dict:
         temps = None
         tptr = None
         if temperatures is not None:
@@ -301,8 +303,14 @@ class Annealer:
             if temps.size != self.chains:
                 raise ValueError("one temperature per chain")
             tptr = temps.ctypes.data_as(C.POINTER(C.c_float))
+        rptr = None
+        if regions is not None:
+            regs = np.ascontiguousarray(regions, dtype=np.uint32)
+            if regs.shape != (self.chains, 2):
+                raise ValueError("regions must be a [chains][2] array of byte ranges")
+            rptr = regs.ctypes.data_as(C.POINTER(C.c_uint32))
         rp = AnnealRunParams(evals, max_attempts, schedule, step, num_iters, first_eval, tptr, packet_budget,
-                             0 if early_exit else 1, int(suspend), cycle_budget)
+                             0 if early_exit else 1, int(suspend), cycle_budget, rptr)
         st = AnnealStats()
         _check(self._lib.mg_anneal_run(self._h, C.byref(rp), C.byref(st)))
         return st.as_dict()
@@ -340,6 +348,20 @@ class Annealer:
     def import_slab(self, chain: int, device_ptr: int, adopt_cost: bool = True) -> None:
         _check(self._lib.mg_anneal_import_slab(self._h, chain, C.c_void_p(device_ptr), int(adopt_cost)))
 
+    def merge_regions(self, bounds, owners, dst_chain: int = 0) -> int:
+        """Region r = [bounds[r], bounds[r+1]) from chain owners[r] -> chain dst_chain, repaired and priced."""
+        b = np.ascontiguousarray(bounds, dtype=np.uint32)
+        o = np.ascontiguousarray(owners, dtype=np.uint32)
+        if b.size != o.size + 1:
+            raise ValueError("bounds must hold one more entry than owners")
+        cost = C.c_uint64(0)
+        _check(self._lib.mg_anneal_merge_regions(self._h, o.size, b.ctypes.data_as(C.c_void_p), o.ctypes.data_as(C.c_void_p),
+                                                 dst_chain, C.byref(cost)))
+        return int(cost.value)
+
+    def broadcast_chain(self, src_chain: int) -> None:
+        _check(self._lib.mg_anneal_broadcast_chain(self._h, src_chain))
+
     def refresh_chain(self, chain: int, adopt_cost: bool = True) -> None:
         _check(self._lib.mg_anneal_refresh_chain(self._h, chain, int(adopt_cost)))
 
@@ -350,7 +372,7 @@ def anneal_oneshot(ctx: Context, *, chains: int, evals: int, init: np.ndarray | 
     """Host buffers in, host buffers out: the call the end-to-end benchmark times."""
     lib = ctx._lib
     p = AnnealParams(chains, top_k, 0, 0, 1, 0, seed)
-    rp = AnnealRunParams(evals, 0, schedule, step, num_iters, 0, None, packet_budget, 0, int(suspend), cycle_budget)
+    rp = AnnealRunParams(evals, 0, schedule, step, num_iters, 0, None, packet_budget, 0, int(suspend), cycle_budget, None)
     st = AnnealStats()
     best = np.zeros(ctx.n, dtype=PACKET_DTYPE)
     cost = C.c_uint64(0)

@@ -1,0 +1,98 @@
+"""Cooperative annealing over byte regions: how thousands of chains work on ONE slab.
+
+The reference anneals a single slab sequentially (src/main.c:64-105).  Thousands of independent
+chains explore thousands of trajectories, but only the best of them survives a restart, so the
+population advances at the pace of one chain.  Edits far apart in the file barely interact (they
+meet only through the adaptive model), which makes the search separable by position:
+
+  round:  every chain starts from the same slab and only mutates packets that start inside its own
+          byte region (mg_anneal_run_params.regions); `group` chains share a region;
+  merge:  for every region the chain of its group with the lowest total cost is taken, the regions
+          are stitched into one slab, the seams are repaired with the reference's own repair rule
+          and the result is priced exactly (mg_anneal_merge_regions);
+  keep:   the merged slab if it is the cheapest slab seen, else the best single chain;
+  shift:  region boundaries move every round, so no position stays a seam.
+
+Every cost is exact (the merged slab is re-priced, never estimated) and every slab handed back
+decodes to the input.  Host logic only: the hot path is the same annealing kernel.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import api
+
+
+def region_plan(n: int, chains: int, group: int, shift: int, min_region: int = 64):
+    """bounds [R+1] and the region index of every chain.  R = chains // group regions of equal size
+    (at least min_region bytes), the boundaries rotated by `shift` bytes."""
+    group = max(1, min(group, chains))
+    nreg = max(1, min(chains // group, n // max(1, min_region)))
+    size = n / nreg
+    off = shift % max(1, int(size))
+    cuts = [0] + [min(n - 1, max(1, int(round(off + r * size)))) for r in range(1, nreg)] + [n]
+    bounds = np.array(sorted(set(cuts)), dtype=np.uint32)
+    nreg = bounds.size - 1
+    region_of_chain = np.arange(chains, dtype=np.int64) % nreg
+    return bounds, region_of_chain
+
+
+class CooperativeAnnealer:
+    def __init__(self, annealer: api.Annealer, *, group: int = 8, min_region: int = 64, seed: int = 0):
+        self.an = annealer
+        self.n = annealer.ctx.n
+        self.group = group
+        self.min_region = min_region
+        self.round_no = 0
+        self.rng = np.random.default_rng(seed)
+        self.best_cost = None
+        self.history = []
+
+    def start(self, slab=None) -> int:
+        """All chains from `slab` (None = all literals, like packet_slab_new)."""
+        self.an.set_slab(slab, adopt_cost=True, reset_best=True)
+        cur, _ = self.an.costs()
+        self.best_cost = int(cur[0])
+        return self.best_cost
+
+    def round(self, *, cycle_budget: int = 0, packet_budget: int = 0, evals: int = 1_000_000, temperature: float = 0.0) -> dict:
+        """One round: confined annealing, merge, keep the better of {merged, best chain, previous}.
+        temperature (1/2048 bit units) > 0 lets chains climb: exp(-delta/T) acceptance."""
+        an, n = self.an, self.n
+        shift = int(self.rng.integers(0, n))
+        bounds, region_of_chain = region_plan(n, an.chains, self.group, shift, self.min_region)
+        regions = np.stack([bounds[region_of_chain], bounds[region_of_chain + 1]], axis=1).astype(np.uint32)
+        temps = np.full(an.chains, temperature, dtype=np.float32)
+        st = an.run(evals, schedule=api.SCHEDULE_TEMPERATURE, temperatures=temps, first_eval=api.CONTINUE_EVALS,
+                    cycle_budget=cycle_budget, packet_budget=packet_budget, suspend=False, regions=regions)
+        cur, _ = an.costs()
+        cur = cur.astype(np.int64)
+        nreg = bounds.size - 1
+        owners = np.zeros(nreg, dtype=np.uint32)
+        for r in range(nreg):
+            members = np.nonzero(region_of_chain == r)[0]
+            owners[r] = members[np.argmin(cur[members])]
+        best_chain = int(np.argmin(cur))
+        best_single = int(cur[best_chain])
+        # the merged slab goes to the most expensive chain's slot, so the best single chain survives the merge
+        dst = int(np.argmax(cur))
+        if dst == best_chain:
+            dst = (best_chain + 1) % an.chains
+        merged = an.merge_regions(bounds, owners, dst_chain=dst)
+        if merged <= best_single:
+            winner, cost, kind = dst, merged, "merged"
+        else:
+            winner, cost, kind = best_chain, best_single, "single"
+        if self.best_cost is not None and cost > self.best_cost and temperature == 0.0:
+            kind += "(no gain)"
+        an.broadcast_chain(winner)
+        self.best_cost = cost if self.best_cost is None else min(self.best_cost, cost)
+        self.round_no += 1
+        rec = {"round": self.round_no, "cost": cost, "merged": merged, "best_single": best_single, "kept": kind,
+               "regions": int(nreg), "evals": st["evals"], "kernel_ms": st["kernel_ms"]}
+        self.history.append(rec)
+        return rec
+
+    def slab(self) -> np.ndarray:
+        """The current common slab (all chains hold it after a round)."""
+        return self.an.get_slab(0)

@@ -536,6 +536,8 @@ extern "C" MG_API int mg_encode_slab_buffer(mg_ctx* ctx, const LZMAPacket* slab,
 
 // ---- annealing ----------------------------------------------------------------------------------------
 struct mg_anneal {
+	uint32_t* d_regions = nullptr;  // [chains][2] byte ranges of the last region-mode run
+
 	mg_ctx* ctx = nullptr;
 	mg_anneal_params p{};
 	uint32_t stride = 0, nslots = 0, nck = 0;
@@ -600,6 +602,7 @@ extern "C" MG_API void mg_anneal_destroy(mg_anneal* an)
 	}
 	cudaSetDevice(an->ctx->device);
 	cudaStreamSynchronize(an->ctx->stream);
+	cudaFree(an->d_regions);
 	cudaFree(an->d_slabs);
 	cudaFree(an->d_bests);
 	cudaFree(an->d_ck);
@@ -811,8 +814,7 @@ extern "C" MG_API int mg_anneal_set_slab(mg_anneal* an, uint32_t first, uint32_t
 			st[i].live_count = st[0].live_count;
 			st[i].err = 0;
 			st[i].eval_index = 0;
-			st[i].susp_slot = 0;
-		st[i].susp_slot = 0;  // a suspended proposal belongs to the slab that was replaced
+			st[i].susp_slot = 0;  // a suspended proposal belongs to the slab that was replaced
 			st[i].journal_count = 0;
 			st[i].journal_overflow = reset_best ? 0 : 1;
 			if (reset_best) st[i].best_cost = 0;
@@ -832,19 +834,11 @@ extern "C" MG_API int mg_anneal_refresh_chain(mg_anneal* an, uint32_t chain, int
 	return MG_OK;
 }
 
-extern "C" MG_API int mg_anneal_run(mg_anneal* an, const mg_anneal_run_params* run, mg_anneal_stats* stats)
+// The launch arguments that do not depend on the call.
+static void anneal_common_args(mg_anneal* an, AnnealArgs& a)
 {
-	if (!an || !run) return fail(MG_EINVAL, "mg_anneal_run: null argument");
 	mg_ctx* ctx = an->ctx;
-	for (uint8_t h : an->have_slab)
-		if (!h) return fail(MG_ESTATE, "mg_anneal_run: every chain needs mg_anneal_set_slab first");
-	if (run->schedule > 1) return fail(MG_EINVAL, "mg_anneal_run: unknown schedule");
-	if (run->schedule == MG_SCHEDULE_TEMPERATURE && !run->temperatures)
-		return fail(MG_EINVAL, "mg_anneal_run: temperatures required");
-	CU(cudaSetDevice(ctx->device));
 	const uint32_t C = an->p.chains;
-	if (run->temperatures) CU(cudaMemcpyAsync(an->d_temps, run->temperatures, (size_t)C * 4, cudaMemcpyHostToDevice, ctx->stream));
-	AnnealArgs a;
 	a.data = ctx->d_data;
 	a.n = ctx->n;
 	a.occ_start = ctx->d_occ_start;
@@ -868,6 +862,37 @@ extern "C" MG_API int mg_anneal_run(mg_anneal* an, const mg_anneal_run_params* r
 	a.trace = an->d_trace;
 	a.trace_cap = an->p.trace_capacity;
 	a.attempts_out = an->d_attempts;
+	a.regions = nullptr;
+	a.chain_first = 0;
+	a.repair_only = 0;
+	a.suspend = 0;
+	a.cycle_budget = 0;
+	a.packet_budget = 0;
+	a.early_exit = 0;
+	a.temps = nullptr;
+	a.schedule = 0;
+	a.step = 0;
+	a.num_iters = ctx->n;
+	a.first_eval = 0xffffffffu;
+	a.evals = 0;
+	a.max_attempts = 0;
+	if (an->nslots <= 1) a.nslots = 1;  // a single slot has no checkpoints: the kernel's nck is 0
+}
+
+extern "C" MG_API int mg_anneal_run(mg_anneal* an, const mg_anneal_run_params* run, mg_anneal_stats* stats)
+{
+	if (!an || !run) return fail(MG_EINVAL, "mg_anneal_run: null argument");
+	mg_ctx* ctx = an->ctx;
+	for (uint8_t h : an->have_slab)
+		if (!h) return fail(MG_ESTATE, "mg_anneal_run: every chain needs mg_anneal_set_slab first");
+	if (run->schedule > 1) return fail(MG_EINVAL, "mg_anneal_run: unknown schedule");
+	if (run->schedule == MG_SCHEDULE_TEMPERATURE && !run->temperatures)
+		return fail(MG_EINVAL, "mg_anneal_run: temperatures required");
+	CU(cudaSetDevice(ctx->device));
+	const uint32_t C = an->p.chains;
+	if (run->temperatures) CU(cudaMemcpyAsync(an->d_temps, run->temperatures, (size_t)C * 4, cudaMemcpyHostToDevice, ctx->stream));
+	AnnealArgs a;
+	anneal_common_args(an, a);
 	a.evals = run->evals;
 	a.max_attempts = run->max_attempts ? run->max_attempts : run->evals * 64u + 1024u;
 	a.schedule = run->schedule;
@@ -879,9 +904,13 @@ extern "C" MG_API int mg_anneal_run(mg_anneal* an, const mg_anneal_run_params* r
 	a.suspend = run->suspend ? 1u : 0u;
 	a.cycle_budget = run->cycle_budget;
 	a.temps = run->temperatures ? an->d_temps : nullptr;
-	if (an->nslots <= 1) {
-		// a single slot has no checkpoints: the kernel's nck is 0
-		a.nslots = 1;
+	if (run->regions) {
+		for (uint32_t c = 0; c < C; c++)
+			if (run->regions[2 * c] >= run->regions[2 * c + 1] || run->regions[2 * c + 1] > ctx->n)
+				return fail(MG_EINVAL, "mg_anneal_run: chain %u has an empty or out-of-range region", c);
+		if (!an->d_regions) CU(cudaMalloc(&an->d_regions, (size_t)C * 8));
+		CU(cudaMemcpyAsync(an->d_regions, run->regions, (size_t)C * 8, cudaMemcpyHostToDevice, ctx->stream));
+		a.regions = an->d_regions;
 	}
 	const int blocks = (int)((C + WARPS_PER_CTA - 1) / WARPS_PER_CTA);
 	CU(cudaEventRecord(an->e0, ctx->stream));
@@ -1036,6 +1065,96 @@ extern "C" MG_API int mg_anneal_swap_chains(mg_anneal* an, uint32_t x, uint32_t 
 	nx.journal_overflow = ny.journal_overflow = 1;  // the best slabs stayed, the current ones moved
 	CU(cudaMemcpy(an->d_state + x, &nx, sizeof(ChainState), cudaMemcpyHostToDevice));
 	CU(cudaMemcpy(an->d_state + y, &ny, sizeof(ChainState), cudaMemcpyHostToDevice));
+	return MG_OK;
+}
+
+extern "C" MG_API int mg_anneal_merge_regions(mg_anneal* an, uint32_t nregions, const uint32_t* bounds, const uint32_t* owners,
+                                       uint32_t dst_chain, uint64_t* cost_out)
+{
+	if (!an || !bounds || !owners || nregions == 0 || dst_chain >= an->p.chains)
+		return fail(MG_EINVAL, "mg_anneal_merge_regions: bad argument");
+	mg_ctx* ctx = an->ctx;
+	const size_t n = ctx->n;
+	if (bounds[0] != 0 || bounds[nregions] != n) return fail(MG_EINVAL, "mg_anneal_merge_regions: regions must cover the input");
+	for (uint32_t r = 0; r < nregions; r++) {
+		if (bounds[r] >= bounds[r + 1]) return fail(MG_EINVAL, "mg_anneal_merge_regions: region %u is empty", r);
+		if (owners[r] >= an->p.chains) return fail(MG_EINVAL, "mg_anneal_merge_regions: region %u has no such owner", r);
+	}
+	CU(cudaSetDevice(ctx->device));
+	DevBuf d_bounds, d_owners, tmp;
+	if (int rc = dev_alloc(d_bounds, (size_t)(nregions + 1) * 4)) return rc;
+	if (int rc = dev_alloc(d_owners, (size_t)nregions * 4)) return rc;
+	if (int rc = dev_alloc(tmp, n * 8)) return rc;
+	CU(cudaMemcpyAsync(d_bounds.p, bounds, (size_t)(nregions + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+	CU(cudaMemcpyAsync(d_owners.p, owners, (size_t)nregions * 4, cudaMemcpyHostToDevice, ctx->stream));
+	merge_regions_kernel<<<grid_for(nregions, 1, ctx->sm_count * 8), 256, 0, ctx->stream>>>(
+	    an->d_slabs, (uint32_t)n, d_bounds.as<uint32_t>(), d_owners.as<uint32_t>(), nregions, tmp.as<uint64_t>());
+	CU(cudaGetLastError());
+	CU(cudaMemcpyAsync(an->d_slabs + (size_t)dst_chain * n, tmp.p, n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+	// the destination's bookkeeping no longer describes its slab: the forced pass below rebuilds it
+	ChainState st;
+	CU(cudaStreamSynchronize(ctx->stream));
+	CU(cudaMemcpy(&st, an->d_state + dst_chain, sizeof(ChainState), cudaMemcpyDeviceToHost));
+	st.susp_slot = 0;
+	st.journal_count = 0;
+	st.journal_overflow = 1;
+	st.err = 0;
+	CU(cudaMemcpy(an->d_state + dst_chain, &st, sizeof(ChainState), cudaMemcpyHostToDevice));
+	// one forced pass over the merged slab: repair what the seams broke (SHORT_REP / LONG_REP packets
+	// whose rep distances changed; src/packet_slab_neighbour.c:82-117), price it, rewrite the checkpoints
+	AnnealArgs a;
+	anneal_common_args(an, a);
+	a.chains = 1;
+	a.chain_first = dst_chain;
+	a.repair_only = 1;
+	a.evals = 1;
+	a.max_attempts = 1;
+	anneal_kernel<<<1, CTA_THREADS, sizeof(CtaShared), ctx->stream>>>(a);
+	CU(cudaGetLastError());
+	CU(cudaStreamSynchronize(ctx->stream));
+	CU(cudaMemcpy(&st, an->d_state + dst_chain, sizeof(ChainState), cudaMemcpyDeviceToHost));
+	if (st.err) return fail(MG_ESLAB, "mg_anneal_merge_regions: merged slab: %s", walk_error(st.err));
+	if (cost_out) *cost_out = st.slab_cost;
+	return MG_OK;
+}
+
+extern "C" MG_API int mg_anneal_broadcast_chain(mg_anneal* an, uint32_t src_chain)
+{
+	if (!an || src_chain >= an->p.chains) return fail(MG_EINVAL, "mg_anneal_broadcast_chain: bad argument");
+	mg_ctx* ctx = an->ctx;
+	CU(cudaSetDevice(ctx->device));
+	const size_t n = ctx->n, nck = an->nck;
+	const uint32_t C = an->p.chains;
+	if (C == 1) return MG_OK;
+	if (src_chain != 0) {
+		CU(cudaMemcpyAsync(an->d_slabs, an->d_slabs + (size_t)src_chain * n, n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+		if (nck) {
+			CU(cudaMemcpyAsync(an->d_ck, an->d_ck + (size_t)src_chain * 2 * nck, 2 * nck * sizeof(Record), cudaMemcpyDeviceToDevice, ctx->stream));
+			CU(cudaMemcpyAsync(an->d_ck_meta, an->d_ck_meta + (size_t)src_chain * 2 * nck, 2 * nck * sizeof(CkMeta), cudaMemcpyDeviceToDevice, ctx->stream));
+			CU(cudaMemcpyAsync(an->d_ck_live, an->d_ck_live + (size_t)src_chain * nck, nck, cudaMemcpyDeviceToDevice, ctx->stream));
+		}
+	}
+	if (int rc = replicate(ctx, an->d_slabs, an->d_slabs + n, n * 8, n * 8, C - 1)) return rc;
+	if (nck) {
+		if (int rc = replicate(ctx, an->d_ck, an->d_ck + 2 * nck, 2 * nck * sizeof(Record), 2 * nck * sizeof(Record), C - 1)) return rc;
+		if (int rc = replicate(ctx, an->d_ck_meta, an->d_ck_meta + 2 * nck, 2 * nck * sizeof(CkMeta), 2 * nck * sizeof(CkMeta), C - 1)) return rc;
+		if (int rc = replicate(ctx, an->d_ck_live, an->d_ck_live + nck, nck, nck, C - 1)) return rc;
+	}
+	std::vector<ChainState> st(C);
+	CU(cudaStreamSynchronize(ctx->stream));
+	CU(cudaMemcpy(st.data(), an->d_state, (size_t)C * sizeof(ChainState), cudaMemcpyDeviceToHost));
+	const ChainState src = st[src_chain];
+	for (uint32_t c = 0; c < C; c++) {
+		st[c].cur_cost = src.slab_cost;
+		st[c].slab_cost = src.slab_cost;
+		st[c].live_count = src.live_count;
+		st[c].susp_slot = 0;
+		st[c].err = 0;
+		st[c].journal_count = 0;
+		st[c].journal_overflow = 1;  // the best slabs stay where they are, the current ones moved
+		an->have_slab[c] = 1;
+	}
+	CU(cudaMemcpy(an->d_state, st.data(), (size_t)C * sizeof(ChainState), cudaMemcpyHostToDevice));
 	return MG_OK;
 }
 

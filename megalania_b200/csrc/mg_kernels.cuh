@@ -828,6 +828,9 @@ struct AnnealArgs {
 	unsigned long long packet_budget;
 	unsigned long long cycle_budget;  // SM clocks: chains stop (suspending their proposal) once the launch has run this long
 	uint32_t early_exit;  // stop a proposal where its model re-joins the current slab's checkpoints
+	const uint32_t* regions;  // [chains][2] or null: a chain only mutates packets that start in its byte range
+	uint32_t chain_first;     // the launch covers chains [chain_first, chain_first + chains)
+	uint32_t repair_only;     // one forced pass per chain: repair + price the whole slab, commit (after a merge)
 	uint32_t suspend;     // packet_budget is exact: a proposal that crosses it is suspended at its next
 	                      // checkpoint and carried on by the next launch, so all warps end together
 	const float* temps;
@@ -842,10 +845,11 @@ __global__ void __launch_bounds__(CTA_THREADS, MG_ANNEAL_MIN_CTAS) anneal_kernel
 	CtaShared* sh = reinterpret_cast<CtaShared*>(smem_raw);
 	cta_tables_load(sh, a.tables);
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	const uint32_t c = blockIdx.x * WARPS_PER_CTA + warp;
-	if (c >= a.chains) return;
+	if (blockIdx.x * WARPS_PER_CTA + warp >= a.chains) return;
+	const uint32_t c = a.chain_first + blockIdx.x * WARPS_PER_CTA + warp;
 	WarpShared* ws = &sh->warp[warp];
 	const uint32_t n = a.n, nck = a.nslots - 1;
+	const uint32_t reg_lo = a.regions ? a.regions[2 * c] : 0u, reg_hi = a.regions ? a.regions[2 * c + 1] : 0u;
 	uint64_t* slab = a.slabs + (size_t)c * n;
 	const WalkEnv e = make_env(lane, ws, sh, slab, a.data, n);
 	Record* ck_base = a.ck + (size_t)c * 2 * nck;
@@ -909,11 +913,18 @@ __global__ void __launch_bounds__(CTA_THREADS, MG_ANNEAL_MIN_CTAS) anneal_kernel
 			lg.overflow = false;
 
 			// ---- pick the packet to mutate and the checkpoint to start from ------------------
-			target = rng31(rng) % st.live_count;  // neighbour.c:163
-			// last checkpoint whose packet index is <= target: running sums of the delta records
+			// neighbour.c:163 draws a packet index; a chain confined to a byte range (cooperative
+			// regions, see mg_anneal_merge_regions) draws a byte of its range instead and mutates
+			// the first packet that starts at or after it
+			const bool by_pos = a.regions != nullptr;
+			if (by_pos)
+				target = reg_lo + rng31(rng) % (reg_hi - reg_lo);
+			else if (!a.repair_only)
+				target = rng31(rng) % st.live_count;
+			// last checkpoint at or before the target: running sums of the delta records
 			uint32_t pidx0 = 0;
 			uint64_t cost0 = 0;
-			{
+			if (!a.repair_only) {
 				uint32_t carry_p = 0;
 				uint64_t carry_c = 0;
 				for (uint32_t base = 0; base < nck; base += 32) {
@@ -932,7 +943,7 @@ __global__ void __launch_bounds__(CTA_THREADS, MG_ANNEAL_MIN_CTAS) anneal_kernel
 					}
 					p += carry_p;
 					cc += carry_c;
-					const uint32_t cnt = __popc(__ballot_sync(FULL, i < nck && p <= target));
+					const uint32_t cnt = __popc(__ballot_sync(FULL, i < nck && (by_pos ? mt.pos : p) <= target));
 					if (cnt) {
 						j0 = base + cnt;
 						pidx0 = __shfl_sync(FULL, p, (int)cnt - 1);
@@ -956,6 +967,12 @@ __global__ void __launch_bounds__(CTA_THREADS, MG_ANNEAL_MIN_CTAS) anneal_kernel
 			ck.last_pidx = pidx0;
 			ck.last_cost = cost0;
 			ck.test = 0;
+			if (a.repair_only) {
+				// no mutation: the whole slab goes through the repair rules, every checkpoint is rewritten
+				ck.next = a.stride;
+				phase = 2;
+				mode = WALK_REPAIR;
+			}
 		}
 		const uint32_t start_pos = k.pos, start_pidx = walker_pidx(k);
 		ck.suspend_pidx = 0xffffffffu;
@@ -973,14 +990,16 @@ __global__ void __launch_bounds__(CTA_THREADS, MG_ANNEAL_MIN_CTAS) anneal_kernel
 		//            checkpoint instead of from byte 0), then mutate it (neighbour.c:119-152)
 		//   phase 1  repair + price the next three packets (neighbour.c:82-98, count < 4)
 		//   phase 2  repair + price the rest, writing fresh checkpoints
-		uint32_t stop_pidx = resumed ? 0xffffffffu : target;
+		const bool by_pos = a.regions != nullptr;
+		uint32_t stop_pidx = (resumed || by_pos || a.repair_only) ? 0xffffffffu : target;
+		uint32_t stop_pos = (by_pos && phase == 0) ? target : n;
 		uint32_t pos = 0, byte0 = 0;       // the mutated packet's position and data byte
 		uint64_t first = 0, newpk = 0, override_pk = 0, excluded = 0;
 		uint32_t override_pos = 0xffffffffu;
 		uint32_t want_find = 0;            // 1 mutation pick, 2 repair pick
 		bool pick_best = false, failed = false, suspended = false;
 		for (;;) {
-			const uint32_t res = walk(mode, e, k, n, stop_pidx, ck, &lg, override_pos, override_pk, pending, pending_old, err);
+			const uint32_t res = walk(mode, e, k, stop_pos, stop_pidx, ck, &lg, override_pos, override_pk, pending, pending_old, err);
 			if (res == WALK_ERROR) {
 				st.err = err;
 				break;
@@ -995,10 +1014,15 @@ __global__ void __launch_bounds__(CTA_THREADS, MG_ANNEAL_MIN_CTAS) anneal_kernel
 				excluded = pending;
 				want_find = 2;
 			} else if (phase == 0) {
+				if (by_pos && (k.pos >= n || k.pos >= reg_hi)) {
+					failed = true;  // no packet starts in the rest of the chain's range: not an evaluation
+					break;
+				}
 				if (k.pos >= n) {
 					st.err = ERR_NOT_BOUNDARY;
 					break;
 				}
+				stop_pos = n;
 				// ---- mutate ----------------------------------------------------------------------
 				pos = k.pos;
 				if (pos - k.w.base >= 32u) {
@@ -1169,7 +1193,7 @@ __global__ void __launch_bounds__(CTA_THREADS, MG_ANNEAL_MIN_CTAS) anneal_kernel
 			uphill = (float)(cost - st.cur_cost) <= temp * ex;
 		}
 		uint32_t flags = 1;
-		if (st.cur_cost == 0 || cost < st.cur_cost || uphill) {
+		if (st.cur_cost == 0 || cost < st.cur_cost || uphill || a.repair_only) {
 			flags |= 2;
 			st.cur_cost = cost;
 			st.slab_cost = cost;
@@ -1434,6 +1458,16 @@ __global__ void replicate_kernel(const uint4* __restrict__ src, uint4* __restric
 	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < words; i += (size_t)gridDim.x * blockDim.x) {
 		const uint4 v = src[i];
 		for (uint32_t c = 0; c < copies; c++) dst[(size_t)c * stride + i] = v;
+	}
+}
+
+// Cooperative regions: dst[i] = slab of chain owners[r] at i, for i in region r = [bounds[r], bounds[r+1]).
+__global__ void merge_regions_kernel(const uint64_t* __restrict__ slabs, uint32_t n, const uint32_t* __restrict__ bounds,
+                                     const uint32_t* __restrict__ owners, uint32_t nregions, uint64_t* __restrict__ dst)
+{
+	for (uint32_t r = blockIdx.x; r < nregions; r += gridDim.x) {
+		const uint64_t* src = slabs + (size_t)owners[r] * n;
+		for (uint32_t i = bounds[r] + threadIdx.x; i < bounds[r + 1]; i += blockDim.x) dst[i] = src[i];
 	}
 }
 

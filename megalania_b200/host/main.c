@@ -7,6 +7,10 @@
  * then one range-coder pass over the winning slab through the OutputInterface plug-in.  What
  * changes is the engine: every epoch runs on thousands of chains at once (mg_anneal_run), and
  * the iteration budget is explicit because the stock 3 x 200 x n schedule is O(n^2).
+ *
+ * --rounds N switches to the cooperative search (mg_anneal_merge_regions): all chains work on ONE
+ * slab, each confined to a byte region for --round-ms of SM time, the regions' winners are stitched,
+ * repaired, priced exactly and kept if cheaper; region boundaries move every round.
  */
 #include <stdio.h>
 #include <stdlib.h>
@@ -19,7 +23,8 @@
 static void usage(const char* argv0)
 {
 	fprintf(stderr,
-	        "usage: %s [--chains N] [--iters N] [--epochs N] [--steps N] [--seed N] [--device N] [--top-k N] filename\n",
+	        "usage: %s [--chains N] [--iters N] [--epochs N] [--steps N] [--seed N] [--device N] [--top-k N]\n"
+	        "          [--rounds N [--round-ms N] [--group N]] filename\n",
 	        argv0);
 }
 
@@ -32,6 +37,7 @@ static int die(const char* what)
 int main(int argc, char** argv)
 {
 	unsigned chains = 1184, iters = 0, epochs = 2, steps = 3, device = 0, top_k = 20;
+	unsigned rounds = 0, round_ms = 250, group = 8;
 	unsigned long long seed = 1673551; /* src/main.c:68 */
 	const char* filename = NULL;
 	for (int i = 1; i < argc; i++) {
@@ -43,6 +49,9 @@ int main(int argc, char** argv)
 		else if (!strcmp(a, "--steps")) target = &steps;
 		else if (!strcmp(a, "--device")) target = &device;
 		else if (!strcmp(a, "--top-k")) target = &top_k;
+		else if (!strcmp(a, "--rounds")) target = &rounds;
+		else if (!strcmp(a, "--round-ms")) target = &round_ms;
+		else if (!strcmp(a, "--group")) target = &group;
 		if (target) {
 			if (++i >= argc) { usage(argv[0]); return -1; }
 			*target = (unsigned)strtoul(argv[i], NULL, 10);
@@ -59,7 +68,7 @@ int main(int argc, char** argv)
 			return -1;
 		}
 	}
-	if (filename == NULL || chains == 0 || steps == 0 || epochs == 0) {
+	if (filename == NULL || chains == 0 || (rounds == 0 && (steps == 0 || epochs == 0))) {
 		usage(argv[0]);
 		return -1;
 	}
@@ -93,6 +102,83 @@ int main(int argc, char** argv)
 	int have_best = 0;
 	unsigned long long evals = 0;
 	double device_ms = 0;
+
+	if (rounds > 0) {
+		/* ---- cooperative regions (megalania_b200/cooperative.py is the same logic) ---------------- */
+		if (group == 0 || group > chains) group = chains;
+		unsigned nreg = chains / group;
+		if (nreg > file_size / 64) nreg = (unsigned)(file_size / 64);
+		if (nreg == 0) nreg = 1;
+		uint32_t* bounds = malloc(sizeof(uint32_t) * (nreg + 1));
+		uint32_t* owners = malloc(sizeof(uint32_t) * nreg);
+		uint32_t* regions = malloc(sizeof(uint32_t) * 2 * chains);
+		float* temps = calloc(chains, sizeof(float));
+		uint64_t* cur = malloc(sizeof(uint64_t) * chains);
+		if (!bounds || !owners || !regions || !temps || !cur) {
+			fprintf(stderr, "out of memory\n");
+			return -1;
+		}
+		if (mg_anneal_set_slab(an, 0, chains, NULL, 1, 1)) return die("mg_anneal_set_slab");
+		unsigned long long lcg = seed;
+		for (unsigned r = 0; r < rounds; r++) {
+			/* equal regions, boundaries rotated by a pseudo-random shift */
+			lcg = lcg * 6364136223846793005ull + 1442695040888963407ull;
+			const double size = (double)file_size / nreg;
+			const double off = (double)((lcg >> 33) % (unsigned long long)(size < 1 ? 1 : size));
+			unsigned nb = 0;
+			bounds[nb++] = 0;
+			for (unsigned k = 1; k < nreg; k++) {
+				uint32_t cut = (uint32_t)(off + k * size);
+				if (cut >= file_size) cut = (uint32_t)file_size - 1;
+				if (cut > bounds[nb - 1]) bounds[nb++] = cut;
+			}
+			bounds[nb] = (uint32_t)file_size;
+			const unsigned regs = nb;
+			for (unsigned c = 0; c < chains; c++) {
+				regions[2 * c] = bounds[c % regs];
+				regions[2 * c + 1] = bounds[c % regs + 1];
+			}
+			mg_anneal_run_params run;
+			memset(&run, 0, sizeof(run));
+			run.evals = 1000000;
+			run.schedule = MG_SCHEDULE_TEMPERATURE;
+			run.temperatures = temps; /* 0: only moves that do not raise the cost */
+			run.first_eval = MG_CONTINUE_EVALS;
+			run.cycle_budget = (uint64_t)round_ms * 1965000ull;
+			run.regions = regions;
+			mg_anneal_stats stats;
+			if (mg_anneal_run(an, &run, &stats)) return die("mg_anneal_run");
+			evals += stats.evals;
+			device_ms += stats.kernel_ms;
+			if (mg_anneal_costs(an, cur, NULL)) return die("mg_anneal_costs");
+			unsigned best_chain = 0, worst_chain = 0;
+			for (unsigned k = 0; k < regs; k++) owners[k] = k;
+			for (unsigned c = 0; c < chains; c++) {
+				if (cur[c] < cur[owners[c % regs]]) owners[c % regs] = c;
+				if (cur[c] < cur[best_chain]) best_chain = c;
+				if (cur[c] > cur[worst_chain]) worst_chain = c;
+			}
+			if (worst_chain == best_chain) worst_chain = (best_chain + 1) % chains;
+			uint64_t merged = 0;
+			unsigned winner = best_chain;
+			if (chains > 1) {
+				if (mg_anneal_merge_regions(an, regs, bounds, owners, worst_chain, &merged)) return die("mg_anneal_merge_regions");
+				if (merged <= cur[best_chain]) winner = worst_chain;
+			}
+			best_perplexity = winner == best_chain ? cur[best_chain] : merged;
+			if (mg_anneal_broadcast_chain(an, winner)) return die("mg_anneal_broadcast_chain");
+			fprintf(stderr, "current file size: %f\tround: %u/%u - %s, %llu evals, %.0f evals/s\n", 18 + best_perplexity / 16384.f,
+			        r + 1, rounds, winner == best_chain ? "best chain" : "merged", evals, evals / (device_ms / 1e3));
+		}
+		if (mg_anneal_get_slab(an, 0, 0, packets_best)) return die("mg_anneal_get_slab");
+		have_best = 1;
+		free(bounds);
+		free(owners);
+		free(regions);
+		free(temps);
+		free(cur);
+		steps = 0;
+	}
 
 	for (unsigned step = 0; step < steps; step++) {
 		for (unsigned epoch = 0; epoch < epochs; epoch++) {
