@@ -18,6 +18,8 @@ decodes to the input.  Host logic only: the hot path is the same annealing kerne
 """
 from __future__ import annotations
 
+import time
+
 import numpy as np
 
 from . import api
@@ -63,15 +65,17 @@ class CooperativeAnnealer:
         bounds, region_of_chain = region_plan(n, an.chains, self.group, shift, self.min_region)
         regions = np.stack([bounds[region_of_chain], bounds[region_of_chain + 1]], axis=1).astype(np.uint32)
         temps = np.full(an.chains, temperature, dtype=np.float32)
+        t0 = time.perf_counter()
         st = an.run(evals, schedule=api.SCHEDULE_TEMPERATURE, temperatures=temps, first_eval=api.CONTINUE_EVALS,
                     cycle_budget=cycle_budget, packet_budget=packet_budget, suspend=False, regions=regions)
+        t1 = time.perf_counter()
         cur, _ = an.costs()
         cur = cur.astype(np.int64)
         nreg = bounds.size - 1
-        owners = np.zeros(nreg, dtype=np.uint32)
-        for r in range(nreg):
-            members = np.nonzero(region_of_chain == r)[0]
-            owners[r] = members[np.argmin(cur[members])]
+        # per region the cheapest chain of its group (chains c, c + nreg, c + 2 nreg, ... share region c % nreg)
+        order = np.lexsort((cur, region_of_chain))
+        first = np.searchsorted(region_of_chain[order], np.arange(nreg))
+        owners = order[first].astype(np.uint32)
         best_chain = int(np.argmin(cur))
         best_single = int(cur[best_chain])
         # the merged slab goes to the most expensive chain's slot, so the best single chain survives the merge
@@ -79,6 +83,7 @@ class CooperativeAnnealer:
         if dst == best_chain:
             dst = (best_chain + 1) % an.chains
         merged = an.merge_regions(bounds, owners, dst_chain=dst)
+        t2 = time.perf_counter()
         if merged <= best_single:
             winner, cost, kind = dst, merged, "merged"
         else:
@@ -86,10 +91,12 @@ class CooperativeAnnealer:
         if self.best_cost is not None and cost > self.best_cost and temperature == 0.0:
             kind += "(no gain)"
         an.broadcast_chain(winner)
+        t3 = time.perf_counter()
         self.best_cost = cost if self.best_cost is None else min(self.best_cost, cost)
         self.round_no += 1
         rec = {"round": self.round_no, "cost": cost, "merged": merged, "best_single": best_single, "kept": kind,
-               "regions": int(nreg), "evals": st["evals"], "kernel_ms": st["kernel_ms"]}
+               "regions": int(nreg), "evals": st["evals"], "kernel_ms": st["kernel_ms"],
+               "run_s": t1 - t0, "merge_s": t2 - t1, "broadcast_s": t3 - t2}
         self.history.append(rec)
         return rec
 

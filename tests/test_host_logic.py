@@ -45,3 +45,19 @@ def test_python_mirror_checks_arguments():
     repacked = np.concatenate([slab, slab])
     fixed = api.as_slab(repacked)
     assert fixed.dtype == api.PACKET_DTYPE and fixed.size == 16 and (fixed["len"] == 1).all()
+
+
+def test_region_plan_covers_the_input_and_balances_groups():
+    from megalania_b200.cooperative import region_plan
+    for n, chains, group, shift in ((65536, 4736, 8, 12345), (4096, 4736, 8, 7), (1 << 20, 4736, 1, 999999), (300, 64, 4, 5)):
+        bounds, region_of_chain = region_plan(n, chains, group, shift)
+        assert bounds[0] == 0 and bounds[-1] == n
+        assert (np.diff(bounds.astype(np.int64)) > 0).all()
+        nreg = bounds.size - 1
+        assert region_of_chain.min() == 0 and region_of_chain.max() == nreg - 1
+        counts = np.bincount(region_of_chain, minlength=nreg)
+        assert counts.min() >= 1 and counts.max() - counts.min() <= 1
+    # boundaries move with the shift
+    a, _ = region_plan(65536, 4736, 8, 0)
+    b, _ = region_plan(65536, 4736, 8, 50)
+    assert not np.array_equal(a, b)

@@ -30,7 +30,8 @@ t0 = time.time()
 for r in range(rounds):
     rec = coop.round(cycle_budget=int(ms * 1.965e6))
     print(rec["round"], "t=%.1fs" % (time.time() - t0), "bytes %.1f" % (rec["cost"] / 16384 + 18), "merged %.1f single %.1f" % (rec["merged"] / 16384 + 18, rec["best_single"] / 16384 + 18),
-          rec["kept"], "regions", rec["regions"], "evals", rec["evals"])
+          rec["kept"], "regions", rec["regions"], "evals", rec["evals"],
+          "run %.2fs merge %.2fs bcast %.2fs" % (rec["run_s"], rec["merge_s"], rec["broadcast_s"]))
 stream = ctx.encode_slab(coop.slab())
 assert lzma.decompress(stream, format=lzma.FORMAT_ALONE) == data
 print("final .lzma", len(stream), "bytes; xz -9e", xz, "; round-trips")
