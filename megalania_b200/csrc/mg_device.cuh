@@ -537,26 +537,13 @@ __device__ __forceinline__ uint32_t meta_len(uint32_t meta) { return (meta >> 3)
 __device__ __forceinline__ uint32_t meta_byte(uint32_t meta) { return meta >> 16; }
 
 struct Window {
-	uint32_t meta, dist;            // current window, decoded
-	uint32_t nlo, nhi, nbyte;       // next window exactly as loaded: nothing reads these registers until the
-	                                // window becomes current, so the loads stay in flight for a whole window
-	uint32_t base;     // multiple of 32; WINDOW_NONE = nothing loaded
-	uint32_t litmask;  // bit i: slot base+i is a canonical LITERAL
-	uint32_t ev_base;  // window base | 1 literal events mirrored | 2 MATCH descriptors mirrored (see window_events / window_matches)
+	uint32_t meta, dist;  // current window, decoded
+	uint32_t base;        // multiple of 32; WINDOW_NONE = nothing loaded
+	uint32_t pf_base;     // window being copied into the warp's staging area by cp.async (WINDOW_NONE = none)
+	uint32_t litmask;     // bit i: slot base+i is a canonical LITERAL
+	uint32_t ev_base;     // window base | 1 literal events mirrored | 2 MATCH descriptors mirrored (see window_events / window_matches)
 };
 constexpr uint32_t WINDOW_NONE = 0x7fffffe0u;  // never within 32 of a real position (inputs < 2 GiB... see mg_ctx_create)
-
-__device__ __forceinline__ void window_fetch(int lane, const uint64_t* __restrict__ slab,
-                                             const uint8_t* __restrict__ data, uint32_t n, uint32_t base,
-                                             uint32_t& lo, uint32_t& hi, uint32_t& byte)
-{
-	const uint32_t i = base + (uint32_t)lane;
-	const bool in = i < n;
-	const uint64_t pk = in ? slab[i] : 0;
-	byte = in ? data[i] : 0;
-	lo = (uint32_t)pk;
-	hi = (uint32_t)(pk >> 32);
-}
 
 __device__ __forceinline__ void window_decode(uint32_t lo, uint32_t hi, uint32_t byte, uint32_t& meta, uint32_t& dist)
 {
@@ -565,15 +552,52 @@ __device__ __forceinline__ void window_decode(uint32_t lo, uint32_t hi, uint32_t
 	dist = lo;
 }
 
+// The next window travels global -> shared memory by cp.async (LDGSTS): no register holds it and
+// nothing waits for it until the walk gets there, a whole window of work later.  (Held in registers,
+// the raw loads were spilled by the compiler - i.e. consumed at once - and every window stalled on
+// HBM latency: 11 % of all warp samples.)  `stage` = shared address of 32 x 8 B slots + 32 data bytes.
+__device__ __forceinline__ void window_prefetch(int lane, const uint64_t* __restrict__ slab,
+                                                const uint8_t* __restrict__ data, uint32_t n, uint32_t base, uint32_t stage)
+{
+	const uint32_t i = base + (uint32_t)lane;
+	const uint32_t in = i < n ? 8u : 0u;  // src-size 0 zero-fills
+	asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(stage + 8u * (uint32_t)lane), "l"(slab + (i < n ? i : 0)), "r"(in) : "memory");
+	if (lane < 8) {
+		// the input buffer is padded by 32 bytes (mg_ctx_create), base is a multiple of 32
+		const uint32_t b = base + 4u * (uint32_t)lane;
+		const uint32_t inb = b < n ? 4u : 0u;
+		asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(stage + 256u + 4u * (uint32_t)lane), "l"(data + (b < n ? b : 0)), "r"(inb) : "memory");
+	}
+	asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
 __device__ __forceinline__ void window_seek(int lane, Window& w, const uint64_t* __restrict__ slab,
-                                            const uint8_t* __restrict__ data, uint32_t n, uint32_t pos)
+                                            const uint8_t* __restrict__ data, uint32_t n, uint32_t pos, uint32_t stage)
 {
 	const uint32_t want = pos & ~31u;
 	if (want == w.base) return;
-	if (want != w.base + 32) window_fetch(lane, slab, data, n, want, w.nlo, w.nhi, w.nbyte);  // a jump: nothing prefetched
-	window_decode(w.nlo, w.nhi, w.nbyte, w.meta, w.dist);
+	uint32_t lo, hi, byte;
+	// also on a jump: a copy still in flight must not land on top of the one issued below
+	asm volatile("cp.async.wait_group 0;" ::: "memory");
+	if (want == w.pf_base) {
+		__syncwarp();
+		asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(lo), "=r"(hi) : "r"(stage + 8u * (uint32_t)lane) : "memory");
+		byte = lds_u8(stage + 256u + (uint32_t)lane);
+		if (want + (uint32_t)lane >= n) byte = 0;  // the padding behind the input is not part of it
+	} else {
+		// a jump: nothing staged for this window
+		const uint32_t i = want + (uint32_t)lane;
+		const bool in = i < n;
+		const uint64_t pk = in ? slab[i] : 0;
+		byte = in ? data[i] : 0;
+		lo = (uint32_t)pk;
+		hi = (uint32_t)(pk >> 32);
+	}
+	window_decode(lo, hi, byte, w.meta, w.dist);
 	w.base = want;
-	window_fetch(lane, slab, data, n, want + 32, w.nlo, w.nhi, w.nbyte);
+	__syncwarp();  // every lane has read the staging area
+	window_prefetch(lane, slab, data, n, want + 32, stage);
+	w.pf_base = want + 32;
 	w.litmask = __ballot_sync(FULL, (w.meta & 0xffffu) == META_LITERAL);
 }
 

@@ -37,7 +37,10 @@ struct FindScratch {
 constexpr uint32_t EVENT_ROW_WORDS = 36, EVENT_LANES = 9;
 // ... followed by one 16-byte MATCH descriptor per slot of the window (window_matches()).
 constexpr uint32_t MATCH_DESC_OFFSET = EVENT_LANES * EVENT_ROW_WORDS * 4;
-static_assert(MATCH_DESC_OFFSET + 32 * 16 <= sizeof(uint32_t) * 2 * (MAX_MATCH - 1), "window mirrors must fit in len_price");
+// ... followed by the staging area of the NEXT window: 32 slab slots (8 B) + 32 data bytes, filled by cp.async.
+constexpr uint32_t STAGE_OFFSET = MATCH_DESC_OFFSET + 32 * 16;
+constexpr uint32_t STAGE_BYTES = 32 * 8 + 32;
+static_assert(STAGE_OFFSET % 16 == 0 && STAGE_OFFSET + STAGE_BYTES <= sizeof(uint32_t) * 2 * (MAX_MATCH - 1), "window mirrors must fit in len_price");
 
 // floor(c / len) for c*len < 2^32 via one multiply: recip[len] = floor((2^32-1)/len) + 1
 __device__ __forceinline__ uint32_t per_byte(uint32_t cost, uint32_t len, SmemU32 recip)
@@ -176,6 +179,9 @@ __device__ __noinline__ uint32_t warp_find(int lane, SmemU16 probs, SmemU32 pric
                                            uint32_t k)
 {
 	uint32_t candidates = 0, chunks = 0;
+	// the length-price tables below share their memory with the walk's window mirrors: a window copy
+	// (cp.async) still in flight must have landed before they are written
+	asm volatile("cp.async.wait_group 0;" ::: "memory");
 	__syncwarp();
 	const uint32_t pos = m.pos, ctx = m.ctx;
 	if (lane == 0) {

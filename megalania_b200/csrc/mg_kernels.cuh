@@ -171,6 +171,7 @@ struct WalkEnv {
 	uint32_t lane_tab_addr;  // shared address of this lane's match_lane_const() entry
 	uint32_t ev_addr;        // shared address of the warp's literal-event mirror
 	uint32_t ev_row_addr;    // ... of this lane's row in it (lanes 0..8)
+	uint32_t stage_addr;     // shared address of the next window's staging area
 	// literal fast path (see the slot map in mg_device.cuh): the lane's slot for data byte b is
 	//   lit_addr + 2 * (((b >> lit_sh) & lowmask) | (b & topmask))  (+ 2 * ctx on lane 0)
 	uint32_t lit_addr;    // shared address of this lane's first slot
@@ -206,6 +207,7 @@ __device__ __forceinline__ WalkEnv make_env(int lane, WarpShared* ws, const CtaS
 	e.lane_tab_addr = cta_base + (uint32_t)offsetof(CtaShared, lane_tab) + 16u * (uint32_t)lane;
 	e.ev_addr = warp_base + (uint32_t)offsetof(WarpShared, fs) + (uint32_t)offsetof(FindScratch, len_price);
 	e.ev_row_addr = e.ev_addr + 4u * EVENT_ROW_WORDS * (uint32_t)(lane < (int)EVENT_LANES ? lane : 0);
+	e.stage_addr = e.ev_addr + STAGE_OFFSET;
 	const bool tree = lane >= 1 && lane <= 8;
 	const uint32_t depth = tree ? (uint32_t)lane - 1 : 0;
 	uint32_t first = S_DUMMY;
@@ -348,6 +350,7 @@ __device__ __forceinline__ void walker_init(const WalkEnv& e, Walker& k)
 	k.pos = k.delta = k.ctx = k.mb = 0;
 	k.t = {0, 0, 0};
 	k.w.base = WINDOW_NONE;
+	k.w.pf_base = WINDOW_NONE;
 	k.w.ev_base = WINDOW_NONE;
 }
 
@@ -361,6 +364,7 @@ __device__ __forceinline__ void walker_load(const WalkEnv& e, Walker& k, const R
 	k.ctx = m.ctx;
 	k.t = {cost, 0, 0};
 	k.w.base = WINDOW_NONE;
+	k.w.pf_base = WINDOW_NONE;
 	k.w.ev_base = WINDOW_NONE;
 	k.mb = MB_UNKNOWN;
 }
@@ -488,7 +492,7 @@ __device__ __forceinline__ uint32_t walk(const uint32_t MODE, const WalkEnv& e, 
 		}
 		if (k.pos - k.w.base >= 32u) {
 			tally_flush(k.t);
-			window_seek(e.lane, k.w, e.slab, e.data, e.n, k.pos);
+			window_seek(e.lane, k.w, e.slab, e.data, e.n, k.pos, e.stage_addr);
 		}
 		uint32_t limit = k.w.base + 32 < stop_pos ? k.w.base + 32 : stop_pos;
 		limit = ck.next < limit ? ck.next : limit;
@@ -1027,7 +1031,7 @@ __global__ void __launch_bounds__(CTA_THREADS, MG_ANNEAL_MIN_CTAS) anneal_kernel
 				pos = k.pos;
 				if (pos - k.w.base >= 32u) {
 					tally_flush(k.t);
-					window_seek(lane, k.w, slab, a.data, n, pos);
+					window_seek(lane, k.w, slab, a.data, n, pos, e.stage_addr);
 				}
 				const uint32_t meta0 = window_meta(k.w, pos);
 				const uint32_t dist0 = window_dist(k.w, pos);
@@ -1076,6 +1080,7 @@ __global__ void __launch_bounds__(CTA_THREADS, MG_ANNEAL_MIN_CTAS) anneal_kernel
 				const uint32_t count = warp_find(lane, e.probs, e.trans, e.recip, &ws->fs, a.data, n, a.occ_start, a.occ,
 				                                 walker_model(e, k), excluded, a.k);
 				k.w.ev_base = WINDOW_NONE;  // the finder's length tables share the window mirrors' memory
+				k.w.pf_base = WINDOW_NONE;  // ... and the staging area of the next window
 				if (lane == 0) {
 					cs.candidates += ws->fs.candidates;
 					cs.chunks += ws->fs.chunks;
@@ -1276,6 +1281,7 @@ __global__ void __launch_bounds__(CTA_THREADS, MG_ANNEAL_MIN_CTAS) anneal_kernel
 		__syncwarp();
 	}
 
+	asm volatile("cp.async.wait_group 0;" ::: "memory");
 	if (lane == 0) {
 		cs.evals = done;
 		cs.attempts = attempts;
@@ -1369,11 +1375,13 @@ __global__ void __launch_bounds__(32) encode_kernel(EncodeArgs a)
 	Model m;
 	model_init(lane, SmemU16{smem_u32(rec.probs)}, m);
 	RangeCoder rc = {0, 0xFFFFFFFFu, 0, 1, a.out, a.cap, 0};
+	__shared__ __align__(16) unsigned char stage[STAGE_BYTES];
 	Window w;
 	w.base = WINDOW_NONE;
+	w.pf_base = WINDOW_NONE;
 	uint32_t err = 0;
 	while (m.pos < a.n) {
-		window_seek(lane, w, a.slab, a.data, a.n, m.pos);
+		window_seek(lane, w, a.slab, a.data, a.n, m.pos, smem_u32(stage));
 		const uint32_t meta = window_meta(w, m.pos);
 		const uint32_t type = meta_type(meta), len = meta_len(meta), dist = window_dist(w, m.pos);
 		const uint32_t byte = meta_byte(meta) & 0xff;
