@@ -303,15 +303,28 @@ def run_cuda(args) -> None:
     pk, pk_src = peaks()
     alg_bytes = agg["slab_bytes_read"] + agg["checkpoint_bytes"] + 16 * agg["edits"]
     achieved = alg_bytes / (agg["kernel_ms"] / 1e3) / 1e9
+    # DRAM traffic: ncu (dram__bytes_read + write of one captured launch of this kernel on this workload,
+    # profiles/r01_final_traffic.json) as a ratio to the algorithmic bytes of that launch, applied to this run's
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "r01_final_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            tj = json.load(f)
+        traffic = tj["dram_over_algorithmic"] * alg_bytes / max(1, agg["launches"])
+        traffic_src = f"ncu dram bytes / algorithmic bytes = {tj['dram_over_algorithmic']} on a {tj['launch_ms']} ms launch of the same workload, scaled to this launch"
     roofline = {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                "frac": achieved / pk["hbm_gbs"], "traffic": None, "peak_source": pk_src, "kernel": "mg::anneal_kernel",
+                "frac": achieved / pk["hbm_gbs"], "traffic": traffic, "traffic_source": traffic_src,
+                "peak_source": pk_src, "kernel": "mg::anneal_kernel",
                 "algorithmic_bytes_per_launch": alg_bytes / max(1, agg["launches"]),
                 "avg_launch_ms": float(np.mean(per_launch_ms)),
                 "note": "the scorer is issue/shared-memory bound, not HBM bound: see roofline_issue"}
     bits_per_s = agg["bits_scored"] / (agg["kernel_ms"] / 1e3)
     roofline_issue = {"bound": "shared-memory banks / issue slots", "achieved": bits_per_s,
                       "peak": ISSUE_CEILING_BITS_PER_S, "unit": "modelled bits/s", "frac": bits_per_s / ISSUE_CEILING_BITS_PER_S,
-                      "bits_per_eval": agg["bits_scored"] / max(1, agg["attempts"])}
+                      "bits_per_eval": agg["bits_scored"] / max(1, agg["attempts"]),
+                      "note": "peak = 148 SMs x f_SM x 32 banks / 3 accesses per modelled bit (SURVEY 8d: every lane of every "
+                              "shared-memory instruction useful); the slot-class design issues ~4.9 shared-memory wavefronts per "
+                              "9-bit literal, i.e. its own ceiling is one wavefront per cycle per SM = ~5.3e11 bits/s (DESIGN.md 5)"}
 
     # ---- end to end through the one-shot host call (host buffers in and out) -------------------
     e2e = None
