@@ -863,6 +863,7 @@ static void anneal_common_args(mg_anneal* an, AnnealArgs& a)
 	a.trace_cap = an->p.trace_capacity;
 	a.attempts_out = an->d_attempts;
 	a.regions = nullptr;
+	a.abs_dist = nullptr;
 	a.chain_first = 0;
 	a.repair_only = 0;
 	a.suspend = 0;
@@ -1081,12 +1082,19 @@ extern "C" MG_API int mg_anneal_merge_regions(mg_anneal* an, uint32_t nregions, 
 		if (owners[r] >= an->p.chains) return fail(MG_EINVAL, "mg_anneal_merge_regions: region %u has no such owner", r);
 	}
 	CU(cudaSetDevice(ctx->device));
-	DevBuf d_bounds, d_owners, tmp;
+	DevBuf d_bounds, d_owners, tmp, d_abs;
 	if (int rc = dev_alloc(d_bounds, (size_t)(nregions + 1) * 4)) return rc;
 	if (int rc = dev_alloc(d_owners, (size_t)nregions * 4)) return rc;
 	if (int rc = dev_alloc(tmp, n * 8)) return rc;
+	if (int rc = dev_alloc(d_abs, n * 4)) return rc;
 	CU(cudaMemcpyAsync(d_bounds.p, bounds, (size_t)(nregions + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
 	CU(cudaMemcpyAsync(d_owners.p, owners, (size_t)nregions * 4, cudaMemcpyHostToDevice, ctx->stream));
+	// pass A (before the destination chain is overwritten: it may own a region itself)
+	CU(cudaMemsetAsync(d_abs.p, 0xff, n * 4, ctx->stream));
+	region_abs_reps_kernel<<<grid_for(nregions, 128, 1 << 20), 128, 0, ctx->stream>>>(
+	    an->d_slabs, (uint32_t)n, d_bounds.as<uint32_t>(), d_owners.as<uint32_t>(), nregions, an->d_ck, an->d_ck_meta, an->d_ck_live,
+	    (uint32_t)an->nck, an->nslots > 1 ? 1u : 0u, an->stride, d_abs.as<uint32_t>());
+	CU(cudaGetLastError());
 	merge_regions_kernel<<<grid_for(nregions, 1, ctx->sm_count * 8), 256, 0, ctx->stream>>>(
 	    an->d_slabs, (uint32_t)n, d_bounds.as<uint32_t>(), d_owners.as<uint32_t>(), nregions, tmp.as<uint64_t>());
 	CU(cudaGetLastError());
@@ -1107,6 +1115,7 @@ extern "C" MG_API int mg_anneal_merge_regions(mg_anneal* an, uint32_t nregions, 
 	a.chains = 1;
 	a.chain_first = dst_chain;
 	a.repair_only = 1;
+	a.abs_dist = d_abs.as<uint32_t>();
 	a.evals = 1;
 	a.max_attempts = 1;
 	anneal_kernel<<<1, CTA_THREADS, sizeof(CtaShared), ctx->stream>>>(a);

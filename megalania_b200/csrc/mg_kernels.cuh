@@ -166,6 +166,7 @@ struct WalkEnv {
 	Record* rec;
 	const uint64_t* __restrict__ slab;
 	const uint8_t* __restrict__ data;
+	const uint32_t* __restrict__ abs_dist;  // region merges: the distance a LONG_REP slot stood for in its owner chain, or null
 	uint32_t n;
 	uint32_t trans_addr;  // shared address of trans[]
 	uint32_t lane_tab_addr;  // shared address of this lane's match_lane_const() entry
@@ -202,6 +203,7 @@ __device__ __forceinline__ WalkEnv make_env(int lane, WarpShared* ws, const CtaS
 	e.rec = &ws->rec;
 	e.slab = slab;
 	e.data = data;
+	e.abs_dist = nullptr;
 	e.n = n;
 	e.trans_addr = e.trans.a;
 	e.lane_tab_addr = cta_base + (uint32_t)offsetof(CtaShared, lane_tab) + 16u * (uint32_t)lane;
@@ -636,6 +638,16 @@ __device__ __forceinline__ uint32_t walk(const uint32_t MODE, const WalkEnv& e, 
 						dist = idx;
 						good = model_rep(m, dist) < m.pos && rep_matches(e.lane, e.data, m.pos, model_rep(m, dist), len);
 					}
+					if (!good && e.abs_dist) {
+						// a merged slab: the rep distances in front of this region changed, but the distance
+						// the packet stood for in its owner chain is known - keep the match, as a MATCH
+						const uint32_t d = e.abs_dist[m.pos];
+						if (d < m.pos && rep_matches(e.lane, e.data, m.pos, d, len)) {
+							type = T_MATCH;
+							dist = d;
+							good = true;
+						}
+					}
 					if (!good) {
 						pending = pk_pack(T_LONG_REP, dist, len);
 						pending_old = old;
@@ -832,6 +844,7 @@ struct AnnealArgs {
 	unsigned long long packet_budget;
 	unsigned long long cycle_budget;  // SM clocks: chains stop (suspending their proposal) once the launch has run this long
 	uint32_t early_exit;  // stop a proposal where its model re-joins the current slab's checkpoints
+	const uint32_t* abs_dist; // repair_only after a region merge: see WalkEnv::abs_dist
 	const uint32_t* regions;  // [chains][2] or null: a chain only mutates packets that start in its byte range
 	uint32_t chain_first;     // the launch covers chains [chain_first, chain_first + chains)
 	uint32_t repair_only;     // one forced pass per chain: repair + price the whole slab, commit (after a merge)
@@ -855,7 +868,9 @@ __global__ void __launch_bounds__(CTA_THREADS, MG_ANNEAL_MIN_CTAS) anneal_kernel
 	const uint32_t n = a.n, nck = a.nslots - 1;
 	const uint32_t reg_lo = a.regions ? a.regions[2 * c] : 0u, reg_hi = a.regions ? a.regions[2 * c + 1] : 0u;
 	uint64_t* slab = a.slabs + (size_t)c * n;
-	const WalkEnv e = make_env(lane, ws, sh, slab, a.data, n);
+	WalkEnv e_init = make_env(lane, ws, sh, slab, a.data, n);
+	e_init.abs_dist = a.abs_dist;
+	const WalkEnv e = e_init;
 	Record* ck_base = a.ck + (size_t)c * 2 * nck;
 	CkMeta* ck_meta = a.ck_meta + (size_t)c * 2 * nck;
 	uint8_t* ck_live = a.ck_live + (size_t)c * nck;
@@ -1466,6 +1481,51 @@ __global__ void replicate_kernel(const uint4* __restrict__ src, uint4* __restric
 	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < words; i += (size_t)gridDim.x * blockDim.x) {
 		const uint4 v = src[i];
 		for (uint32_t c = 0; c < copies; c++) dst[(size_t)c * stride + i] = v;
+	}
+}
+
+// Cooperative regions, pass A: for every LONG_REP slot on the live path of region r's owner chain, the
+// absolute distance it stands for there (rep distances only: no probabilities, one thread per region,
+// started from the owner's last checkpoint at or before the region).
+__global__ void region_abs_reps_kernel(const uint64_t* __restrict__ slabs, uint32_t n, const uint32_t* __restrict__ bounds,
+                                       const uint32_t* __restrict__ owners, uint32_t nregions, const Record* __restrict__ ck,
+                                       const CkMeta* __restrict__ ck_meta, const uint8_t* __restrict__ ck_live, uint32_t nck,
+                                       uint32_t has_ck, uint32_t stride, uint32_t* __restrict__ abs_dist)
+{
+	const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+	if (r >= nregions) return;
+	const uint32_t c = owners[r], lo = bounds[r], hi = bounds[r + 1];
+	const uint64_t* slab = slabs + (size_t)c * n;
+	uint32_t pos = 0, rep[4] = {0, 0, 0, 0};
+	if (has_ck) {
+		uint32_t j = lo / stride;
+		if (j > nck) j = nck;
+		while (j > 0) {
+			const uint32_t live = ck_live[(size_t)c * nck + (j - 1)];
+			if (ck_meta[((size_t)c * 2 + live) * nck + (j - 1)].pos <= lo) {
+				const Record* rec = ck + ((size_t)c * 2 + live) * nck + (j - 1);
+				pos = rec->pos;
+				for (int i = 0; i < 4; i++) rep[i] = rec->rep[i];
+				break;
+			}
+			j--;
+		}
+	}
+	while (pos < hi) {
+		const uint64_t pk = slab[pos];
+		const uint32_t type = pk_type(pk), len = pk_len(pk), dist = pk_dist(pk);
+		if (type == T_MATCH) {
+			rep[3] = rep[2];
+			rep[2] = rep[1];
+			rep[1] = rep[0];
+			rep[0] = dist;
+		} else if (type == T_LONG_REP) {
+			const uint32_t idx = dist & 3, d = rep[idx];
+			if (pos >= lo) abs_dist[pos] = d;
+			for (uint32_t i = idx; i > 0; i--) rep[i] = rep[i - 1];  // src/lzma_state.c:67-81
+			rep[0] = d;
+		}
+		pos += len ? len : 1;
 	}
 }
 
