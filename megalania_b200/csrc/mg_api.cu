@@ -501,7 +501,10 @@ static int encode_to_host(mg_ctx* ctx, const LZMAPacket* slab, std::vector<uint8
 static void make_header(const mg_ctx* ctx, uint8_t hdr[13])
 {
 	hdr[0] = 0;
-	const uint32_t dict = 0x400000;
+	// the reference always writes 4 MiB (its todo: "peg dict size to data size"), which makes any match
+	// farther than 4 MiB undecodable; same bytes up to 4 MiB, the next power of two above it
+	uint32_t dict = 0x400000;
+	while (dict < ctx->n && dict < 0x80000000u) dict <<= 1;
 	for (int i = 0; i < 4; i++) hdr[1 + i] = (uint8_t)(dict >> (8 * i));
 	const uint64_t size = ctx->n;
 	for (int i = 0; i < 8; i++) hdr[5 + i] = (uint8_t)(size >> (8 * i));
