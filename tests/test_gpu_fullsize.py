@@ -200,3 +200,30 @@ def test_c_host_cli(tmp_path, corpora):
     # usage / IO errors keep the reference's exit status (255)
     assert subprocess.run([cli]).returncode == 255
     assert subprocess.run([cli, str(tmp_path / "missing")], stderr=subprocess.DEVNULL).returncode == 255
+
+
+def test_header_dictionary_covers_inputs_above_4mib(mg, corpora):
+    """src/lzma_header_encoder.c:16 always writes 4 MiB; above 4 MiB of input that makes far matches
+    undecodable, so the dictionary size grows to the next power of two (identical bytes up to 4 MiB)."""
+    import lzma
+    n = (4 << 20) + 4096
+    data = corpora("corpus16", n)
+    with mg.Context(data) as ctx:
+        slab = mg.literal_slab(n)
+        # one match that reaches farther than 4 MiB: the last 64 bytes copy an earlier block
+        src = 100
+        tail = n - 64
+        patched = bytearray(data)
+        patched[tail:] = patched[src:src + 64]
+    data2 = bytes(patched)
+    with mg.Context(data2) as ctx:
+        slab = mg.literal_slab(n)
+        slab[tail] = (mg.MATCH, tail - src - 1, 64)
+        stream = ctx.encode_slab_buffer(slab)
+        assert int.from_bytes(stream[1:5], "little") == 8 << 20
+        assert int.from_bytes(stream[5:13], "little") == n
+        assert lzma.decompress(stream, format=lzma.FORMAT_ALONE) == data2
+    small = corpora("text", 4096)
+    with mg.Context(small) as ctx:
+        stream = ctx.encode_slab_buffer(mg.literal_slab(4096))
+        assert int.from_bytes(stream[1:5], "little") == 0x400000
