@@ -725,6 +725,7 @@ __global__ void __launch_bounds__(CTA_THREADS) score_kernel(ScoreArgs a)
 	if (!a.ck) ck.next = 0xffffffffu;
 	walk(WALK_PLAIN, e, k, a.stop_pos, 0xffffffffu, ck, nullptr, 0xffffffffu, 0, pending, pending_old, err);
 	tally_flush(k.t);
+	asm volatile("cp.async.wait_group 0;" ::: "memory");  // the window staged ahead of the walk
 	if (!err && k.pos != a.stop_pos) err = ERR_NOT_BOUNDARY;
 	if (a.final_model) walker_store(e, k, a.final_model + s);
 	if (lane == 0) {
@@ -808,6 +809,7 @@ __global__ void __launch_bounds__(CTA_THREADS) topk_kernel(TopkArgs a)
 		}
 		__syncwarp();
 	}
+	asm volatile("cp.async.wait_group 0;" ::: "memory");
 	if (lane == 0 && cand) atomicAdd(a.candidates, cand);
 }
 
@@ -1440,6 +1442,7 @@ __global__ void __launch_bounds__(32) encode_kernel(EncodeArgs a)
 		__syncwarp();
 		model_advance(m, type, len, dist);
 	}
+	asm volatile("cp.async.wait_group 0;" ::: "memory");
 	if (lane == 0) {
 		for (int i = 0; i < 5; i++) rc_shift_low(rc);  // src/range_encoder.c:40-45
 		*a.out_len = rc.len;
