@@ -1384,63 +1384,70 @@ __device__ __forceinline__ void rc_direct(RangeCoder& rc, uint32_t bits, uint32_
 	}
 }
 
+// Two phases per batch of packets: (A) the warp prices packets exactly as the scorer does and appends
+// their (bit, probability) events - in the reference's coding order, direct bits included - to a queue
+// in shared memory; (B) lane 0 runs the range coder's carry / shift-low recurrence over the queue in
+// one tight loop.  (Interleaving A and B per packet cost 3000 cycles per packet.)
+constexpr uint32_t ENCODE_QUEUE = 2048;
 __global__ void __launch_bounds__(32) encode_kernel(EncodeArgs a)
 {
 	__shared__ __align__(16) Record rec;
-	__shared__ uint32_t ev[32];
+	__shared__ uint32_t queue[ENCODE_QUEUE];  // bit << 15 | prob, or 1 << 31 | nbits << 26 | direct bits
+	__shared__ __align__(16) unsigned char stage[STAGE_BYTES];
 	const int lane = threadIdx.x;
 	Model m;
 	model_init(lane, SmemU16{smem_u32(rec.probs)}, m);
 	RangeCoder rc = {0, 0xFFFFFFFFu, 0, 1, a.out, a.cap, 0};
-	__shared__ __align__(16) unsigned char stage[STAGE_BYTES];
 	Window w;
 	w.base = WINDOW_NONE;
 	w.pf_base = WINDOW_NONE;
 	uint32_t err = 0;
-	while (m.pos < a.n) {
-		window_seek(lane, w, a.slab, a.data, a.n, m.pos, smem_u32(stage));
-		const uint32_t meta = window_meta(w, m.pos);
-		const uint32_t type = meta_type(meta), len = meta_len(meta), dist = window_dist(w, m.pos);
-		const uint32_t byte = meta_byte(meta) & 0xff;
-		if (!packet_ok(m, a.n, type, len, dist)) {
-			err = ERR_BAD_PACKET;
-			break;
+	while (m.pos < a.n && !err) {
+		uint32_t qn = 0;
+		while (m.pos < a.n && qn + 28 <= ENCODE_QUEUE) {
+			window_seek(lane, w, a.slab, a.data, a.n, m.pos, smem_u32(stage));
+			const uint32_t meta = window_meta(w, m.pos);
+			const uint32_t type = meta_type(meta), len = meta_len(meta), dist = window_dist(w, m.pos);
+			const uint32_t byte = meta_byte(meta) & 0xff;
+			if (!packet_ok(m, a.n, type, len, dist)) {
+				err = ERR_BAD_PACKET;
+				break;
+			}
+			uint32_t mbyte = 0;
+			if (type == T_LITERAL && m.ctx >= 7) mbyte = a.data[m.pos - m.rep0 - 1];
+			DistParts dp;
+			dp.pslot = dp.nlow = dp.low = dp.rbase = dp.rbits = dp.direct = 0;
+			if (type == T_MATCH) dp = dist_parts(dist);
+			uint32_t slot = 0, bit = 0;
+			const bool active = packet_event(lane, lane_role(lane), type, len, dist, m.ctx, byte, mbyte, dp, slot, bit);
+			const uint32_t mask = __ballot_sync(FULL, active);
+			// lanes are in coding order; the direct bits of a far match sit before the reverse-tree lanes
+			const uint32_t has_direct = dp.direct ? 1u : 0u;
+			const uint32_t before_direct = __popc(mask & ((1u << FIRST_REVTREE_LANE) - 1u));
+			if (active) {
+				uint32_t p = rec.probs[slot];
+				const uint32_t rank = __popc(mask & ((1u << lane) - 1u));
+				queue[qn + rank + (lane >= FIRST_REVTREE_LANE ? has_direct : 0u)] = (bit << 15) | p;
+				p = bit ? p - (p >> 5) : p + ((2048u - p) >> 5);
+				rec.probs[slot] = (uint16_t)p;
+			}
+			if (lane == 0 && has_direct)
+				queue[qn + before_direct] = 0x80000000u | (dp.direct << 26) | ((dist & ((1u << dp.nlow) - 1u)) >> 4);
+			qn += __popc(mask) + has_direct;
+			__syncwarp();
+			model_advance(m, type, len, dist);
 		}
-		uint32_t mbyte = 0;
-		if (type == T_LITERAL && m.ctx >= 7) mbyte = a.data[m.pos - m.rep0 - 1];
-		DistParts dp;
-		dp.pslot = dp.nlow = dp.low = dp.rbase = dp.rbits = dp.direct = 0;
-		if (type == T_MATCH) dp = dist_parts(dist);
-		uint32_t slot = 0, bit = 0;
-		const bool active = packet_event(lane, lane_role(lane), type, len, dist, m.ctx, byte, mbyte, dp, slot, bit);
-		uint32_t word = 0;
-		if (active) {
-			uint32_t p = rec.probs[slot];
-			word = (bit << 15) | p;
-			p = bit ? p - (p >> 5) : p + ((2048u - p) >> 5);
-			rec.probs[slot] = (uint16_t)p;
-		}
-		ev[lane] = word;
-		uint32_t mask = __ballot_sync(FULL, active);
 		__syncwarp();
 		if (lane == 0) {
-			// lanes are in coding order; the direct bits of a far match sit before the reverse-tree lanes
-			const uint32_t direct_val = dp.direct ? (dist & ((1u << dp.nlow) - 1)) >> 4 : 0;
-			bool direct_done = dp.direct == 0;
-			while (mask) {
-				const int l = __ffs(mask) - 1;
-				mask &= mask - 1;
-				if (!direct_done && l >= FIRST_REVTREE_LANE) {
-					rc_direct(rc, direct_val, dp.direct);
-					direct_done = true;
-				}
-				const uint32_t e = ev[l];
-				rc_bit(rc, e >> 15, e & 0x7fff);
+			for (uint32_t i = 0; i < qn; i++) {
+				const uint32_t e = queue[i];
+				if (e >> 31)
+					rc_direct(rc, e & 0x3ffffffu, (e >> 26) & 31u);
+				else
+					rc_bit(rc, e >> 15, e & 0x7fffu);
 			}
-			if (!direct_done) rc_direct(rc, direct_val, dp.direct);
 		}
 		__syncwarp();
-		model_advance(m, type, len, dist);
 	}
 	asm volatile("cp.async.wait_group 0;" ::: "memory");
 	if (lane == 0) {
