@@ -24,7 +24,7 @@ static void usage(const char* argv0)
 {
 	fprintf(stderr,
 	        "usage: %s [--chains N] [--iters N] [--epochs N] [--steps N] [--seed N] [--device N] [--top-k N]\n"
-	        "          [--rounds N [--round-ms N] [--group N]] filename\n",
+	        "          [--rounds N [--round-ms N] [--group N] [--temp T]] filename\n",
 	        argv0);
 }
 
@@ -37,7 +37,7 @@ static int die(const char* what)
 int main(int argc, char** argv)
 {
 	unsigned chains = 1184, iters = 0, epochs = 2, steps = 3, device = 0, top_k = 20;
-	unsigned rounds = 0, round_ms = 250, group = 8;
+	unsigned rounds = 0, round_ms = 250, group = 8, temp0 = 4096; /* --temp: 1/2048 bit, cooled linearly to 0 */
 	unsigned long long seed = 1673551; /* src/main.c:68 */
 	const char* filename = NULL;
 	for (int i = 1; i < argc; i++) {
@@ -52,6 +52,7 @@ int main(int argc, char** argv)
 		else if (!strcmp(a, "--rounds")) target = &rounds;
 		else if (!strcmp(a, "--round-ms")) target = &round_ms;
 		else if (!strcmp(a, "--group")) target = &group;
+		else if (!strcmp(a, "--temp")) target = &temp0;
 		if (target) {
 			if (++i >= argc) { usage(argv[0]); return -1; }
 			*target = (unsigned)strtoul(argv[i], NULL, 10);
@@ -142,7 +143,8 @@ int main(int argc, char** argv)
 			memset(&run, 0, sizeof(run));
 			run.evals = 1000000;
 			run.schedule = MG_SCHEDULE_TEMPERATURE;
-			run.temperatures = temps; /* 0: only moves that do not raise the cost */
+			for (unsigned c = 0; c < chains; c++) temps[c] = (float)temp0 * (1.f - (float)(r + 1) / (float)rounds);
+			run.temperatures = temps; /* uphill moves with probability exp(-delta / T); the last round is T = 0 */
 			run.first_eval = MG_CONTINUE_EVALS;
 			run.cycle_budget = (uint64_t)round_ms * 1965000ull;
 			run.regions = regions;
