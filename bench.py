@@ -353,6 +353,26 @@ def run_cuda(args) -> None:
         e2e = {"value": e2e_evals / e2e_s, "unit": UNIT, "h2d_bytes_per_step": n, "d2h_bytes_per_step": 12 * n + 8,
                "steps": args.e2e_steps, "call": "mg_ctx_create + mg_anneal_oneshot (host data in, best slab + cost out)"}
 
+    # ---- the match finder on its own: top-k at every position of the first 64 KiB plus
+    # 4096 sampled ones, state-free pricing; reported beside the headline, not part of it
+    finder = None
+    if rank == 0 and world == 1 and not args.no_finder:
+        fctx = mg.Context(data, device=local)
+        fpos = np.concatenate([np.arange(min(n, 65536), dtype=np.uint64),
+                               np.random.default_rng(7).integers(0, n, 4096).astype(np.uint64)])
+        lit = mg.literal_slab(n)
+        fctx.find_topk(lit, fpos[:256], state_mode=0)  # warm-up
+        fctx.find_topk(lit, fpos, state_mode=0)
+        fs = fctx.find_topk_stats()
+        fctx.close()
+        fsec = fs["kernel_ms"] / 1e3
+        finder = {"kernel": "mg::topk_kernel", "positions": int(fpos.size), "kernel_ms": fs["kernel_ms"],
+                  "positions_per_s": fpos.size / fsec, "candidates_per_s": fs["candidates"] / fsec,
+                  "candidates_per_position": fs["candidates"] / fpos.size,
+                  "hbm_algorithmic_GBps": 325.0 * fpos.size / fsec / 1e9,
+                  "note": "325 B per query is the compulsory HBM traffic (SURVEY 8d); the kernel is bound by the serial "
+                          "replay of the reference's heap and by L1/L2 reads of the window, not by HBM"}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu = cpu_baseline(n, args.cpu_evals)
@@ -373,7 +393,7 @@ def run_cuda(args) -> None:
                 "timing": "value = evaluations / wall clock between barrier+cudaDeviceSynchronize brackets, max over ranks; "
                           "device_ms_per_step = CUDA events around the kernel on the library's launch stream",
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
-                "roofline": roofline, "roofline_issue": roofline_issue, "cpu_baseline": cpu,
+                "roofline": roofline, "roofline_issue": roofline_issue, "finder": finder, "cpu_baseline": cpu,
                 "stats": {"evals": total_evals, "modelled_bits": total_bits, "packets": total_packets,
                           "attempts": agg["attempts"], "accepted": agg["accepted"],
                           "finder_candidates": agg["finder_candidates"], "log_overflows": agg["log_overflows"],
@@ -405,6 +425,7 @@ def main() -> None:
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-finder", action="store_true")
     ap.add_argument("--cpu-evals", type=int, default=0, help="evaluations of the CPU sample (default: sized to ~15 s)")
     ap.add_argument("--cpu-procs", type=int, default=1 << 30)
     args = ap.parse_args()

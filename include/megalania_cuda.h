@@ -108,6 +108,9 @@ MG_API int mg_score_slabs(mg_ctx* ctx, const LZMAPacket* slabs, size_t nslabs, u
 MG_API int mg_find_topk(mg_ctx* ctx, const LZMAPacket* slab, int state_mode, const uint64_t* positions,
                  size_t npos, int k, LZMAPacket* out_pops, uint32_t* out_prices, int32_t* out_counts);
 
+/* Device time (CUDA events around the kernel) and candidates enumerated by the last mg_find_topk on ctx. */
+MG_API int mg_find_topk_stats(const mg_ctx* ctx, double* kernel_ms, uint64_t* candidates);
+
 /* ---- parity function 3: bytes(data, slab) ---------------------------------------------- */
 
 /* Replaces the final pass of src/main.c:110-119: lzma_encode_header

@@ -81,7 +81,7 @@ EXPORTS = [
     "mg_anneal_destroy", "mg_anneal_chain_bytes", "mg_anneal_set_slab", "mg_anneal_run", "mg_anneal_costs",
     "mg_anneal_get_slab", "mg_anneal_get_trace", "mg_anneal_swap_chains", "mg_anneal_device_slab",
     "mg_anneal_refresh_chain", "mg_anneal_oneshot", "mg_debug_model_after_prefix", "mg_anneal_export_slab",
-    "mg_anneal_import_slab", "mg_anneal_merge_regions", "mg_anneal_broadcast_chain",
+    "mg_anneal_import_slab", "mg_anneal_merge_regions", "mg_anneal_broadcast_chain", "mg_find_topk_stats",
 ]
 
 _lib = None
@@ -114,6 +114,7 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
     L.mg_ctx_device.argtypes = [vp]
     L.mg_score_slabs.argtypes = [vp, vp, sz, vp]
     L.mg_find_topk.argtypes = [vp, vp, i32, vp, sz, i32, vp, vp, vp]
+    L.mg_find_topk_stats.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(u64)]
     L.mg_encode_slab.argtypes = [vp, vp, C.POINTER(OutputInterface)]
     L.mg_encode_slab_buffer.argtypes = [vp, vp, vp, sz, C.POINTER(sz)]
     L.mg_anneal_create.argtypes = [vp, C.POINTER(AnnealParams), C.POINTER(vp)]
@@ -226,6 +227,11 @@ class Context:
                                       pos.size, k, pops.ctypes.data_as(C.c_void_p),
                                       prices.ctypes.data_as(C.c_void_p), counts.ctypes.data_as(C.c_void_p)))
         return pops, prices, counts
+
+    def find_topk_stats(self) -> dict:
+        ms, cand = C.c_double(0), C.c_uint64(0)
+        _check(self._lib.mg_find_topk_stats(self._h, C.byref(ms), C.byref(cand)))
+        return {"kernel_ms": ms.value, "candidates": int(cand.value)}
 
     def encode_slab(self, slab: np.ndarray) -> bytes:
         """Through the OutputInterface plug-in, exactly as a C host would receive it."""

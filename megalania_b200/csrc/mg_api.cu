@@ -48,6 +48,8 @@ struct mg_ctx {
 	int sm_count = 0;
 	double index_ms = 0;
 	std::vector<mg_anneal*> annealers;  // live chain populations on this context (destroyed with it)
+	double last_topk_ms = 0;          // mg_find_topk: device time and candidates of the last call
+	unsigned long long last_topk_candidates = 0;
 };
 
 struct DevBuf {
@@ -204,6 +206,13 @@ extern "C" MG_API void mg_ctx_destroy(mg_ctx* ctx)
 }
 
 extern "C" MG_API size_t mg_ctx_size(const mg_ctx* ctx) { return ctx ? ctx->n : 0; }
+extern "C" MG_API int mg_find_topk_stats(const mg_ctx* ctx, double* kernel_ms, uint64_t* candidates)
+{
+	if (!ctx) return fail(MG_EINVAL, "mg_find_topk_stats: null context");
+	if (kernel_ms) *kernel_ms = ctx->last_topk_ms;
+	if (candidates) *candidates = ctx->last_topk_candidates;
+	return MG_OK;
+}
 extern "C" MG_API int mg_ctx_device(const mg_ctx* ctx) { return ctx ? ctx->device : -1; }
 
 // Upload `count` host packets (12 B each) and pack them into dst (device, u64 each).
@@ -434,7 +443,12 @@ extern "C" MG_API int mg_find_topk(mg_ctx* ctx, const LZMAPacket* slab, int stat
 	size_t blocks = (npos + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
 	const size_t cap = (size_t)ctx->sm_count * 4 * 8;
 	if (blocks > cap) blocks = cap;
+	cudaEvent_t t0, t1;
+	CU(cudaEventCreate(&t0));
+	CU(cudaEventCreate(&t1));
+	CU(cudaEventRecord(t0, ctx->stream));
 	topk_kernel<<<(int)blocks, CTA_THREADS, sizeof(CtaShared), ctx->stream>>>(a);
+	CU(cudaEventRecord(t1, ctx->stream));
 	CU(cudaGetLastError());
 	std::vector<uint64_t> hpk(npos * k);
 	std::vector<uint32_t> hprice(npos * k), herr(npos);
@@ -442,7 +456,15 @@ extern "C" MG_API int mg_find_topk(mg_ctx* ctx, const LZMAPacket* slab, int stat
 	CU(cudaMemcpyAsync(hprice.data(), oprice.p, npos * k * 4, cudaMemcpyDeviceToHost, ctx->stream));
 	CU(cudaMemcpyAsync(out_counts, ocount.p, npos * 4, cudaMemcpyDeviceToHost, ctx->stream));
 	CU(cudaMemcpyAsync(herr.data(), oerr.p, npos * 4, cudaMemcpyDeviceToHost, ctx->stream));
+	CU(cudaMemcpyAsync(&ctx->last_topk_candidates, cand.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
 	CU(cudaStreamSynchronize(ctx->stream));
+	{
+		float ms = 0;
+		cudaEventElapsedTime(&ms, t0, t1);
+		ctx->last_topk_ms = ms;
+		cudaEventDestroy(t0);
+		cudaEventDestroy(t1);
+	}
 	for (size_t q = 0; q < npos; q++) {
 		if (herr[q]) return fail(MG_ESLAB, "mg_find_topk: query %zu (position %u): %s", q, pos32[q], walk_error(herr[q]));
 		for (int i = 0; i < k; i++) {
