@@ -57,14 +57,20 @@ class CooperativeAnnealer:
         self.best_cost = int(cur[0])
         return self.best_cost
 
-    def round(self, *, cycle_budget: int = 0, packet_budget: int = 0, evals: int = 1_000_000, temperature: float = 0.0) -> dict:
+    def round(self, *, cycle_budget: int = 0, packet_budget: int = 0, evals: int = 1_000_000, temperature: float = 0.0,
+              ladder: bool = False) -> dict:
         """One round: confined annealing, merge, keep the better of {merged, best chain, previous}.
-        temperature (1/2048 bit units) > 0 lets chains climb: exp(-delta/T) acceptance."""
+        temperature (1/2048 bit units) > 0 lets chains climb: exp(-delta/T) acceptance.  With `ladder` the
+        chains of a region's group run at 0, T/(g-1), 2T/(g-1), ... T: cold ones exploit, hot ones explore."""
         an, n = self.an, self.n
         shift = int(self.rng.integers(0, n))
         bounds, region_of_chain = region_plan(n, an.chains, self.group, shift, self.min_region)
         regions = np.stack([bounds[region_of_chain], bounds[region_of_chain + 1]], axis=1).astype(np.uint32)
         temps = np.full(an.chains, temperature, dtype=np.float32)
+        if ladder:
+            nreg_ = bounds.size - 1
+            member = np.arange(an.chains) // nreg_
+            temps = (temperature * member / max(1, member.max())).astype(np.float32)
         t0 = time.perf_counter()
         st = an.run(evals, schedule=api.SCHEDULE_TEMPERATURE, temperatures=temps, first_eval=api.CONTINUE_EVALS,
                     cycle_budget=cycle_budget, packet_budget=packet_budget, suspend=False, regions=regions)

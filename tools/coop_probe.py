@@ -15,6 +15,7 @@ ms = float(sys.argv[4]) if len(sys.argv) > 4 else 500.0
 group = int(sys.argv[5]) if len(sys.argv) > 5 else 8
 start = sys.argv[6] if len(sys.argv) > 6 else "literal"
 temp0 = float(sys.argv[7]) if len(sys.argv) > 7 else 0.0  # initial temperature (1/2048 bit), cooled linearly to 0
+ladder = len(sys.argv) > 8 and sys.argv[8] == "ladder"
 data = corpus.make(kind, n)
 xz = len(subprocess.run(["xz", "-9e", "--format=lzma", "-c"], input=data, stdout=subprocess.PIPE).stdout)
 print("xz -9e --format=lzma:", xz, "bytes")
@@ -29,7 +30,7 @@ c0 = coop.start(init)
 print("start", start, c0 / 16384 + 18)
 t0 = time.time()
 for r in range(rounds):
-    rec = coop.round(cycle_budget=int(ms * 1.965e6), temperature=temp0 * (1.0 - (r + 1) / rounds))
+    rec = coop.round(cycle_budget=int(ms * 1.965e6), temperature=temp0 * (1.0 - (r + 1) / rounds), ladder=ladder)
     print(rec["round"], "t=%.1fs" % (time.time() - t0), "bytes %.1f" % (rec["cost"] / 16384 + 18), "merged %.1f single %.1f" % (rec["merged"] / 16384 + 18, rec["best_single"] / 16384 + 18),
           rec["kept"], "regions", rec["regions"], "evals", rec["evals"],
           "run %.2fs merge %.2fs bcast %.2fs" % (rec["run_s"], rec["merge_s"], rec["broadcast_s"]))
