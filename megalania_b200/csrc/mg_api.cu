@@ -168,7 +168,7 @@ extern "C" MG_API int mg_ctx_create(const uint8_t* data, size_t n, LZMAPropertie
 			trans[p] = (p + ((2048u - p) >> 5)) | (price[p] << 16);                        // bit 0
 			trans[2048 + p] = (p - (p >> 5)) | (price[(2048u - p) & 2047u] << 16);        // bit 1
 		}
-		trans[0] = 0;  // probability 0 never occurs in a model: (0, bit 0) is the zero-price fixed point idle lanes sit on
+		trans[0] = 0;  // probability 0 never occurs in a model: (0, bit 0) is a zero-price fixed point (the spare slot's value)
 		std::vector<uint32_t> recip(RECIP_ENTRIES, 0);
 		for (uint32_t i = 1; i < RECIP_ENTRIES; i++) recip[i] = 0xffffffffu / i + 1u;
 		CUB(cudaMalloc(&ctx->d_trans, 4096 * sizeof(uint32_t)));

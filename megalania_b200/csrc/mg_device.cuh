@@ -47,7 +47,7 @@ constexpr uint32_t S_POSSLOT = S_REPLEN + LEN_SLOTS;  // [4][64]
 constexpr uint32_t S_ALIGN = S_POSSLOT + 256;       // [16]
 constexpr uint32_t S_POSCODER = S_ALIGN + 16;       // [115]
 constexpr uint32_t S_TOTAL = S_POSCODER + 115;
-constexpr uint32_t S_DUMMY = S_TOTAL;               // spare slot: lanes with no event of their own adapt this one
+constexpr uint32_t S_DUMMY = S_TOTAL;               // spare slot: the address lanes without a slot class point at (never coded)
 constexpr uint32_t S_COUNT = ((S_TOTAL + 1 + 7) / 8) * 8;  // probabilities stored per record (16-byte multiple)
 // is_match[0] is touched by every literal of a run: keep it off the banks of the shallow tree levels
 static_assert(((S_ISMATCH / 2) % 32) >= 16, "is_match[0] must only share a bank with the deepest literal tree level");
@@ -527,10 +527,10 @@ __device__ __forceinline__ void model_init(int lane, SmemU16 probs, Model& m)
 	__syncwarp();
 }
 
-// Window of 32 consecutive slab slots + data bytes held across the warp's registers, with the
-// next window prefetched, so the live-chain walk costs one shuffle per packet instead of a
-// dependent load.  meta = type[2:0] | len[11:3] | data byte[23:16]; dist separately (only
-// matches and long reps need it).
+// Window of 32 consecutive slab slots + data bytes held across the warp's registers (one slot per
+// lane), so the live-chain walk costs one shuffle per packet instead of a dependent load; the next
+// window is staged in shared memory by cp.async (window_prefetch).
+// meta = type[2:0] | len[15:3] | data byte[23:16]; dist separately (only matches and long reps need it).
 constexpr uint32_t META_LITERAL = T_LITERAL | (1u << 3);
 __device__ __forceinline__ uint32_t meta_type(uint32_t meta) { return meta & 7; }
 __device__ __forceinline__ uint32_t meta_len(uint32_t meta) { return (meta >> 3) & 0x1fff; }

@@ -153,9 +153,7 @@ __device__ __forceinline__ void log_put(int lane, EditLog& lg, uint32_t pos, uin
 
 // ---- the walk ----------------------------------------------------------------------------------------
 // Everything a walking warp needs besides its registers.  Lane roles in the literal fast path:
-// lane 0 owns is_match[ctx], lanes 1..8 own literal-tree depth 0..7, lanes 9..31 adapt the
-// dummy slot (value 0 is a zero-price fixed point of the transition table), so the fast path
-// is branch-free across the warp.
+// lane 0 owns is_match[ctx], lanes 1..8 own literal-tree depth 0..7, lanes 9..31 sit literal runs out.
 struct WalkEnv {
 	int lane;
 	SmemU16 probs;        // the model's probabilities
@@ -509,7 +507,7 @@ __device__ __forceinline__ uint32_t walk(const uint32_t MODE, const WalkEnv& e, 
 				const uint32_t ctx = k.ctx;
 				if (ctx < 7) {
 					// ---- run of plain literals: every lane follows its own slot class through the
-					// whole run (lane 0 is_match, lanes 1..8 one tree depth, the rest the idle slot);
+					// whole run (lane 0 is_match, lanes 1..8 one tree depth, the other lanes wait);
 					// classes never share a slot, so no cross-lane traffic is needed per packet ---------
 					const uint32_t idx = k.pos - k.w.base;
 					uint32_t run = (uint32_t)__ffs((int)~(k.w.litmask >> idx)) - 1u;
