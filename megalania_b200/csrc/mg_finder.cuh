@@ -15,6 +15,7 @@
 namespace mg {
 
 constexpr int MAX_K = 32;
+constexpr uint32_t FIND_GAVE_UP = 0xffffffffu;  // warp_find: the deadline passed inside a long bucket
 constexpr uint32_t MAX_MATCH = 273;  // src/packet_enumerator.c:6-7
 
 struct FindScratch {
@@ -176,7 +177,7 @@ __device__ __noinline__ uint32_t warp_find(int lane, SmemU16 probs, SmemU32 pric
                                            SmemU32 recip, FindScratch* fs, const uint8_t* __restrict__ data,
                                            uint32_t n, const uint32_t* __restrict__ occ_start,
                                            const uint32_t* __restrict__ occ, const Model m, uint64_t excluded,
-                                           uint32_t k)
+                                           uint32_t k, long long give_up_at = 0)
 {
 	uint32_t candidates = 0, chunks = 0;
 	// the length-price tables below share their memory with the walk's window mirrors: a window copy
@@ -237,6 +238,12 @@ __device__ __noinline__ uint32_t warp_find(int lane, SmemU16 probs, SmemU32 pric
 			const uint32_t valid_mask = __ballot_sync(FULL, valid);
 			if (valid_mask == 0) break;
 			chunks++;
+			// a clock-boxed step: a bucket of 100 k occurrences takes tens of milliseconds on its own -
+			// the caller takes the proposal back and draws it again in the next launch (FIND_GAVE_UP)
+			if (give_up_at != 0 && (chunks & 63u) == 0 && clock64() >= give_up_at) {
+				__syncwarp();
+				return FIND_GAVE_UP;
+			}
 			uint32_t L = 0;
 			if (valid) {
 				L = 2;

@@ -894,6 +894,7 @@ __global__ void __launch_bounds__(CTA_THREADS, MG_ANNEAL_MIN_CTAS) anneal_kernel
 	while (done < a.evals && attempts < a.max_attempts && st.err == 0 &&
 	       (a.packet_budget == 0 || packets_done < a.packet_budget) && (deadline == 0 || clock64() < deadline)) {
 		attempts++;
+		const uint64_t rng_at_start = rng;
 		Walker k;
 		CkSink ck;
 		ck.ck = ck_base;
@@ -1016,7 +1017,7 @@ __global__ void __launch_bounds__(CTA_THREADS, MG_ANNEAL_MIN_CTAS) anneal_kernel
 		uint64_t first = 0, newpk = 0, override_pk = 0, excluded = 0;
 		uint32_t override_pos = 0xffffffffu;
 		uint32_t want_find = 0;            // 1 mutation pick, 2 repair pick
-		bool pick_best = false, failed = false, suspended = false;
+		bool pick_best = false, failed = false, suspended = false, gave_up = false;
 		for (;;) {
 			const uint32_t res = walk(mode, e, k, stop_pos, stop_pidx, ck, &lg, override_pos, override_pk, pending, pending_old, err);
 			if (res == WALK_ERROR) {
@@ -1092,10 +1093,17 @@ __global__ void __launch_bounds__(CTA_THREADS, MG_ANNEAL_MIN_CTAS) anneal_kernel
 			if (want_find) {
 				if (lane == 0) cs.finds++;
 				const long long t_find = clock64();
+				// in a clock-boxed launch the finder may give a long bucket up - never on the launch's first
+				// proposal, so every launch makes progress
 				const uint32_t count = warp_find(lane, e.probs, e.trans, e.recip, &ws->fs, a.data, n, a.occ_start, a.occ,
-				                                 walker_model(e, k), excluded, a.k);
+				                                 walker_model(e, k), excluded, a.k,
+				                                 (a.suspend && attempts > 1) ? deadline : 0);
 				k.w.ev_base = WINDOW_NONE;  // the finder's length tables share the window mirrors' memory
 				k.w.pf_base = WINDOW_NONE;  // ... and the staging area of the next window
+				if (count == FIND_GAVE_UP) {
+					gave_up = true;
+					break;
+				}
 				if (lane == 0) {
 					cs.candidates += ws->fs.candidates;
 					cs.chunks += ws->fs.chunks;
@@ -1154,6 +1162,13 @@ __global__ void __launch_bounds__(CTA_THREADS, MG_ANNEAL_MIN_CTAS) anneal_kernel
 			cs.bits += walker_bits(k, start_pidx);
 			cs.slab_bytes += (uint64_t)(k.pos - start_pos) * 9;
 			cs.ck_bytes += (uint64_t)ck.written * sizeof(Record);
+		}
+		if (gave_up) {
+			// the deadline passed inside the match finder: the proposal is taken back whole (same generator
+			// state, nothing committed) and the next launch draws it again
+			rng = rng_at_start;
+			attempts--;
+			break;
 		}
 		if (suspended) {
 			// out of budget in the middle of the suffix: the checkpoint just written is the resume point
