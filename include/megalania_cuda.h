@@ -225,6 +225,17 @@ MG_API int mg_anneal_set_slab(mg_anneal* an, uint32_t first, uint32_t count, con
  * *cost_out receives the merged slab's cost: the caller keeps it only if it beats the best single chain. */
 MG_API int mg_anneal_merge_regions(mg_anneal* an, uint32_t nregions, const uint32_t* bounds, const uint32_t* owners,
                                    uint32_t dst_chain, uint64_t* cost_out);
+/* The same in two halves, for hosts whose regions live on several GPUs.  Export writes this process's part into
+ * two caller device buffers: dev_slab (n x 8 B packed slots) and dev_abs (n x 4 B, what each LONG_REP of the
+ * owners' regions stands for, + 1), zero wherever owners[r] == MG_NO_OWNER.  Parts of different processes
+ * cover disjoint slots, so an element-wise SUM over the processes (ncclAllReduce) is the merged whole; every
+ * process then imports it: stores it as dst_chain's slab, repairs the seams, prices it, rewrites the
+ * checkpoints - deterministic, so all processes end up with the same slab and the same cost. */
+#define MG_NO_OWNER 0xffffffffu
+MG_API int mg_anneal_merge_export(mg_anneal* an, uint32_t nregions, const uint32_t* bounds, const uint32_t* owners,
+                                  void* dev_slab, void* dev_abs);
+MG_API int mg_anneal_merge_import(mg_anneal* an, const void* dev_slab, const void* dev_abs, uint32_t dst_chain,
+                                  uint64_t* cost_out);
 /* Makes every chain's current slab (with its checkpoints and cost) a copy of chain `src_chain`'s: the restart
  * from the best slab of src/main.c:75-77, without a round trip through the host.  Best slabs are kept. */
 MG_API int mg_anneal_broadcast_chain(mg_anneal* an, uint32_t src_chain);

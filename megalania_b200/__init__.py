@@ -6,4 +6,4 @@ Only what the path needs lives here:
   api.py  ctypes mirror of the host interface for tests and benchmarks
 """
 from .api import (Annealer, Context, MegalaniaError, PACKET_DTYPE, literal_slab, load_library,  # noqa: F401
-                  anneal_oneshot, LITERAL, MATCH, SHORT_REP, LONG_REP, SCHEDULE_REFERENCE, SCHEDULE_TEMPERATURE, CONTINUE_EVALS)
+                  anneal_oneshot, LITERAL, MATCH, SHORT_REP, LONG_REP, SCHEDULE_REFERENCE, SCHEDULE_TEMPERATURE, CONTINUE_EVALS, NO_OWNER)

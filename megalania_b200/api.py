@@ -29,6 +29,7 @@ MODEL_DTYPE = np.dtype({"names": ["probs", "ctx_state", "dists", "position", "co
 INVALID, LITERAL, MATCH, SHORT_REP, LONG_REP = 0, 1, 2, 3, 4
 SCHEDULE_REFERENCE, SCHEDULE_TEMPERATURE = 0, 1
 CONTINUE_EVALS = 0xFFFFFFFF
+NO_OWNER = 0xFFFFFFFF  # merge_export: a region that lives on another process
 
 ERRORS = {-1: "MG_EINVAL", -2: "MG_ECUDA", -3: "MG_ENOMEM", -4: "MG_ESLAB", -5: "MG_EOUTPUT", -6: "MG_ESTATE"}
 
@@ -82,6 +83,7 @@ EXPORTS = [
     "mg_anneal_get_slab", "mg_anneal_get_trace", "mg_anneal_swap_chains", "mg_anneal_device_slab",
     "mg_anneal_refresh_chain", "mg_anneal_oneshot", "mg_debug_model_after_prefix", "mg_anneal_export_slab",
     "mg_anneal_import_slab", "mg_anneal_merge_regions", "mg_anneal_broadcast_chain", "mg_find_topk_stats",
+    "mg_anneal_merge_export", "mg_anneal_merge_import",
 ]
 
 _lib = None
@@ -132,6 +134,8 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
     L.mg_anneal_refresh_chain.argtypes = [vp, u32, i32]
     L.mg_anneal_merge_regions.argtypes = [vp, u32, vp, vp, u32, C.POINTER(u64)]
     L.mg_anneal_broadcast_chain.argtypes = [vp, u32]
+    L.mg_anneal_merge_export.argtypes = [vp, u32, vp, vp, vp, vp]
+    L.mg_anneal_merge_import.argtypes = [vp, vp, vp, u32, C.POINTER(u64)]
     L.mg_anneal_export_slab.argtypes = [vp, u32, i32, vp]
     L.mg_anneal_import_slab.argtypes = [vp, u32, vp, i32]
     L.mg_anneal_oneshot.argtypes = [vp, C.POINTER(AnnealParams), C.POINTER(AnnealRunParams), vp, vp,
@@ -363,6 +367,22 @@ class Annealer:
         cost = C.c_uint64(0)
         _check(self._lib.mg_anneal_merge_regions(self._h, o.size, b.ctypes.data_as(C.c_void_p), o.ctypes.data_as(C.c_void_p),
                                                  dst_chain, C.byref(cost)))
+        return int(cost.value)
+
+    def merge_export(self, bounds, owners, dev_slab_ptr: int, dev_abs_ptr: int) -> None:
+        """This process's part of a multi-GPU merge into two device buffers (n*8 and n*4 bytes); owners[r] = NO_OWNER
+        for regions that live elsewhere."""
+        b = np.ascontiguousarray(bounds, dtype=np.uint32)
+        o = np.ascontiguousarray(owners, dtype=np.uint32)
+        if b.size != o.size + 1:
+            raise ValueError("bounds must hold one more entry than owners")
+        _check(self._lib.mg_anneal_merge_export(self._h, o.size, b.ctypes.data_as(C.c_void_p), o.ctypes.data_as(C.c_void_p),
+                                                C.c_void_p(dev_slab_ptr), C.c_void_p(dev_abs_ptr)))
+
+    def merge_import(self, dev_slab_ptr: int, dev_abs_ptr: int, dst_chain: int = 0) -> int:
+        cost = C.c_uint64(0)
+        _check(self._lib.mg_anneal_merge_import(self._h, C.c_void_p(dev_slab_ptr), C.c_void_p(dev_abs_ptr), dst_chain,
+                                                C.byref(cost)))
         return int(cost.value)
 
     def broadcast_chain(self, src_chain: int) -> None:

@@ -1094,39 +1094,55 @@ extern "C" MG_API int mg_anneal_swap_chains(mg_anneal* an, uint32_t x, uint32_t 
 	return MG_OK;
 }
 
-extern "C" MG_API int mg_anneal_merge_regions(mg_anneal* an, uint32_t nregions, const uint32_t* bounds, const uint32_t* owners,
-                                       uint32_t dst_chain, uint64_t* cost_out)
+extern "C" MG_API int mg_anneal_merge_export(mg_anneal* an, uint32_t nregions, const uint32_t* bounds, const uint32_t* owners,
+                                      void* dev_slab, void* dev_abs)
 {
-	if (!an || !bounds || !owners || nregions == 0 || dst_chain >= an->p.chains)
-		return fail(MG_EINVAL, "mg_anneal_merge_regions: bad argument");
+	if (!an || !bounds || !owners || nregions == 0 || !dev_slab || !dev_abs)
+		return fail(MG_EINVAL, "mg_anneal_merge_export: bad argument");
 	mg_ctx* ctx = an->ctx;
 	const size_t n = ctx->n;
-	if (bounds[0] != 0 || bounds[nregions] != n) return fail(MG_EINVAL, "mg_anneal_merge_regions: regions must cover the input");
+	if (bounds[0] != 0 || bounds[nregions] != n) return fail(MG_EINVAL, "mg_anneal_merge_export: regions must cover the input");
 	for (uint32_t r = 0; r < nregions; r++) {
-		if (bounds[r] >= bounds[r + 1]) return fail(MG_EINVAL, "mg_anneal_merge_regions: region %u is empty", r);
-		if (owners[r] >= an->p.chains) return fail(MG_EINVAL, "mg_anneal_merge_regions: region %u has no such owner", r);
+		if (bounds[r] >= bounds[r + 1]) return fail(MG_EINVAL, "mg_anneal_merge_export: region %u is empty", r);
+		if (owners[r] != MG_NO_OWNER && owners[r] >= an->p.chains)
+			return fail(MG_EINVAL, "mg_anneal_merge_export: region %u has no such owner", r);
 	}
 	CU(cudaSetDevice(ctx->device));
-	DevBuf d_bounds, d_owners, tmp, d_abs;
+	DevBuf d_bounds, d_owners;
 	if (int rc = dev_alloc(d_bounds, (size_t)(nregions + 1) * 4)) return rc;
 	if (int rc = dev_alloc(d_owners, (size_t)nregions * 4)) return rc;
-	if (int rc = dev_alloc(tmp, n * 8)) return rc;
-	if (int rc = dev_alloc(d_abs, n * 4)) return rc;
 	CU(cudaMemcpyAsync(d_bounds.p, bounds, (size_t)(nregions + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
 	CU(cudaMemcpyAsync(d_owners.p, owners, (size_t)nregions * 4, cudaMemcpyHostToDevice, ctx->stream));
-	// pass A (before the destination chain is overwritten: it may own a region itself)
-	CU(cudaMemsetAsync(d_abs.p, 0xff, n * 4, ctx->stream));
+	CU(cudaMemsetAsync(dev_slab, 0, n * 8, ctx->stream));
+	CU(cudaMemsetAsync(dev_abs, 0, n * 4, ctx->stream));
+	// pass A: what every LONG_REP of the owners' regions stands for (distance + 1)
 	region_abs_reps_kernel<<<grid_for(nregions, 128, 1 << 20), 128, 0, ctx->stream>>>(
 	    an->d_slabs, (uint32_t)n, d_bounds.as<uint32_t>(), d_owners.as<uint32_t>(), nregions, an->d_ck, an->d_ck_meta, an->d_ck_live,
-	    (uint32_t)an->nck, an->nslots > 1 ? 1u : 0u, an->stride, d_abs.as<uint32_t>());
+	    (uint32_t)an->nck, an->nslots > 1 ? 1u : 0u, an->stride, static_cast<uint32_t*>(dev_abs));
 	CU(cudaGetLastError());
 	merge_regions_kernel<<<grid_for(nregions, 1, ctx->sm_count * 8), 256, 0, ctx->stream>>>(
-	    an->d_slabs, (uint32_t)n, d_bounds.as<uint32_t>(), d_owners.as<uint32_t>(), nregions, tmp.as<uint64_t>());
+	    an->d_slabs, (uint32_t)n, d_bounds.as<uint32_t>(), d_owners.as<uint32_t>(), nregions, static_cast<uint64_t*>(dev_slab));
 	CU(cudaGetLastError());
-	CU(cudaMemcpyAsync(an->d_slabs + (size_t)dst_chain * n, tmp.p, n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+	CU(cudaStreamSynchronize(ctx->stream));
+	return MG_OK;
+}
+
+extern "C" MG_API int mg_anneal_merge_import(mg_anneal* an, const void* dev_slab, const void* dev_abs, uint32_t dst_chain,
+                                      uint64_t* cost_out)
+{
+	if (!an || !dev_slab || !dev_abs || dst_chain >= an->p.chains) return fail(MG_EINVAL, "mg_anneal_merge_import: bad argument");
+	mg_ctx* ctx = an->ctx;
+	const size_t n = ctx->n;
+	CU(cudaSetDevice(ctx->device));
+	validate_kernel<<<grid_for(n, 256, ctx->sm_count * 4), 256, 0, ctx->stream>>>(static_cast<const uint64_t*>(dev_slab), ctx->n, an->d_bad);
+	CU(cudaGetLastError());
+	uint32_t bad = 0;
+	CU(cudaMemcpyAsync(&bad, an->d_bad, 4, cudaMemcpyDeviceToHost, ctx->stream));
+	CU(cudaMemcpyAsync(an->d_slabs + (size_t)dst_chain * n, dev_slab, n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
 	// the destination's bookkeeping no longer describes its slab: the forced pass below rebuilds it
 	ChainState st;
 	CU(cudaStreamSynchronize(ctx->stream));
+	if (bad) return fail(MG_ESLAB, "mg_anneal_merge_import: merged slab holds %u undecodable slot(s)", bad);
 	CU(cudaMemcpy(&st, an->d_state + dst_chain, sizeof(ChainState), cudaMemcpyDeviceToHost));
 	st.susp_slot = 0;
 	st.journal_count = 0;
@@ -1140,16 +1156,32 @@ extern "C" MG_API int mg_anneal_merge_regions(mg_anneal* an, uint32_t nregions, 
 	a.chains = 1;
 	a.chain_first = dst_chain;
 	a.repair_only = 1;
-	a.abs_dist = d_abs.as<uint32_t>();
+	a.abs_dist = static_cast<const uint32_t*>(dev_abs);
 	a.evals = 1;
 	a.max_attempts = 1;
 	anneal_kernel<<<1, CTA_THREADS, sizeof(CtaShared), ctx->stream>>>(a);
 	CU(cudaGetLastError());
 	CU(cudaStreamSynchronize(ctx->stream));
 	CU(cudaMemcpy(&st, an->d_state + dst_chain, sizeof(ChainState), cudaMemcpyDeviceToHost));
-	if (st.err) return fail(MG_ESLAB, "mg_anneal_merge_regions: merged slab: %s", walk_error(st.err));
+	if (st.err) return fail(MG_ESLAB, "mg_anneal_merge_import: merged slab: %s", walk_error(st.err));
+	an->have_slab[dst_chain] = 1;
 	if (cost_out) *cost_out = st.slab_cost;
 	return MG_OK;
+}
+
+extern "C" MG_API int mg_anneal_merge_regions(mg_anneal* an, uint32_t nregions, const uint32_t* bounds, const uint32_t* owners,
+                                       uint32_t dst_chain, uint64_t* cost_out)
+{
+	if (!an || !bounds || !owners || nregions == 0 || dst_chain >= an->p.chains)
+		return fail(MG_EINVAL, "mg_anneal_merge_regions: bad argument");
+	for (uint32_t r = 0; r < nregions; r++)
+		if (owners[r] == MG_NO_OWNER) return fail(MG_EINVAL, "mg_anneal_merge_regions: region %u has no owner", r);
+	CU(cudaSetDevice(an->ctx->device));
+	DevBuf slab, abs;
+	if (int rc = dev_alloc(slab, (size_t)an->ctx->n * 8)) return rc;
+	if (int rc = dev_alloc(abs, (size_t)an->ctx->n * 4)) return rc;
+	if (int rc = mg_anneal_merge_export(an, nregions, bounds, owners, slab.p, abs.p)) return rc;
+	return mg_anneal_merge_import(an, slab.p, abs.p, dst_chain, cost_out);
 }
 
 extern "C" MG_API int mg_anneal_broadcast_chain(mg_anneal* an, uint32_t src_chain)

@@ -639,7 +639,7 @@ __device__ __forceinline__ uint32_t walk(const uint32_t MODE, const WalkEnv& e, 
 					if (!good && e.abs_dist) {
 						// a merged slab: the rep distances in front of this region changed, but the distance
 						// the packet stood for in its owner chain is known - keep the match, as a MATCH
-						const uint32_t d = e.abs_dist[m.pos];
+						const uint32_t d = e.abs_dist[m.pos] - 1u;  // stored + 1; 0 = no entry -> 0xffffffff fails d < pos
 						if (d < m.pos && rep_matches(e.lane, e.data, m.pos, d, len)) {
 							type = T_MATCH;
 							dist = d;
@@ -875,7 +875,9 @@ __global__ void __launch_bounds__(CTA_THREADS, MG_ANNEAL_MIN_CTAS) anneal_kernel
 	CkMeta* ck_meta = a.ck_meta + (size_t)c * 2 * nck;
 	uint8_t* ck_live = a.ck_live + (size_t)c * nck;
 	ChainState st = a.state[c];
-	uint64_t rng = st.rng;
+	// the forced pass after a merge draws from a fixed generator: every process that repairs the same
+	// merged slab (multi-GPU merges) must make the same picks; the chain's own generator is left alone
+	uint64_t rng = a.repair_only ? 0x6D65726765ull : st.rng;
 	uint32_t parity = 0;
 	// Counters live in shared memory and are touched by lane 0 only: lanes of a warp are not
 	// guaranteed to run in lockstep, so a read-modify-write by all of them could count twice.
@@ -1316,7 +1318,7 @@ __global__ void __launch_bounds__(CTA_THREADS, MG_ANNEAL_MIN_CTAS) anneal_kernel
 		cs.evals = done;
 		cs.attempts = attempts;
 		cs.chain_cycles = (unsigned long long)(clock64() - t_start);
-		st.rng = rng;
+		if (!a.repair_only) st.rng = rng;
 		st.eval_index = first_eval + done;
 		a.state[c] = st;
 		a.stats[c] = ws->stats;
@@ -1518,6 +1520,7 @@ __global__ void region_abs_reps_kernel(const uint64_t* __restrict__ slabs, uint3
 	const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
 	if (r >= nregions) return;
 	const uint32_t c = owners[r], lo = bounds[r], hi = bounds[r + 1];
+	if (c == 0xffffffffu) return;  // owned by another process (multi-GPU merges)
 	const uint64_t* slab = slabs + (size_t)c * n;
 	uint32_t pos = 0, rep[4] = {0, 0, 0, 0};
 	if (has_ck) {
@@ -1544,7 +1547,7 @@ __global__ void region_abs_reps_kernel(const uint64_t* __restrict__ slabs, uint3
 			rep[0] = dist;
 		} else if (type == T_LONG_REP) {
 			const uint32_t idx = dist & 3, d = rep[idx];
-			if (pos >= lo) abs_dist[pos] = d;
+			if (pos >= lo) abs_dist[pos] = d + 1;  // 0 = no entry (the parts of several processes are summed)
 			for (uint32_t i = idx; i > 0; i--) rep[i] = rep[i - 1];  // src/lzma_state.c:67-81
 			rep[0] = d;
 		}
@@ -1557,6 +1560,7 @@ __global__ void merge_regions_kernel(const uint64_t* __restrict__ slabs, uint32_
                                      const uint32_t* __restrict__ owners, uint32_t nregions, uint64_t* __restrict__ dst)
 {
 	for (uint32_t r = blockIdx.x; r < nregions; r += gridDim.x) {
+		if (owners[r] == 0xffffffffu) continue;  // owned by another process: its slots stay 0
 		const uint64_t* src = slabs + (size_t)owners[r] * n;
 		for (uint32_t i = bounds[r] + threadIdx.x; i < bounds[r + 1]; i += blockDim.x) dst[i] = src[i];
 	}

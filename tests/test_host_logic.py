@@ -61,3 +61,19 @@ def test_region_plan_covers_the_input_and_balances_groups():
     a, _ = region_plan(65536, 4736, 8, 0)
     b, _ = region_plan(65536, 4736, 8, 50)
     assert not np.array_equal(a, b)
+
+
+def test_distributed_plan_gives_every_rank_its_own_regions():
+    from megalania_b200.cooperative import distributed_plan
+    for n, chains, world, group in ((1 << 20, 4736, 8, 8), (65536, 4736, 2, 8), (4096, 64, 4, 4)):
+        bounds, owner_rank, regions_of_chains = distributed_plan(n, chains, world, group, 4242)
+        nreg = bounds.size - 1
+        assert bounds[0] == 0 and bounds[-1] == n and (np.diff(bounds.astype(np.int64)) > 0).all()
+        assert owner_rank.size == nreg and set(owner_rank.tolist()) <= set(range(world))
+        seen = np.zeros(nreg, dtype=bool)
+        for rank in range(world):
+            mine = regions_of_chains(rank)
+            assert mine.size == chains
+            assert (owner_rank[mine] == rank).all()      # a rank only anneals regions it owns
+            seen[np.unique(mine)] = True
+        assert seen.all()                                 # every region is annealed by someone
