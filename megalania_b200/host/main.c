@@ -24,7 +24,7 @@ static void usage(const char* argv0)
 {
 	fprintf(stderr,
 	        "usage: %s [--chains N] [--iters N] [--epochs N] [--steps N] [--seed N] [--device N] [--top-k N]\n"
-	        "          [--rounds N [--round-ms N] [--group N] [--temp T]] filename\n",
+	        "          [--rounds N | --time SECONDS] [--round-ms N] [--group N] [--temp T] filename\n",
 	        argv0);
 }
 
@@ -38,6 +38,7 @@ int main(int argc, char** argv)
 {
 	unsigned chains = 1184, iters = 0, epochs = 2, steps = 3, device = 0, top_k = 20;
 	unsigned rounds = 0, round_ms = 250, group = 8, temp0 = 4096; /* --temp: 1/2048 bit, cooled linearly to 0 */
+	unsigned time_s = 0;                                          /* --time: annealing budget in seconds of SM time */
 	unsigned long long seed = 1673551; /* src/main.c:68 */
 	const char* filename = NULL;
 	for (int i = 1; i < argc; i++) {
@@ -53,6 +54,7 @@ int main(int argc, char** argv)
 		else if (!strcmp(a, "--round-ms")) target = &round_ms;
 		else if (!strcmp(a, "--group")) target = &group;
 		else if (!strcmp(a, "--temp")) target = &temp0;
+		else if (!strcmp(a, "--time")) target = &time_s;
 		if (target) {
 			if (++i >= argc) { usage(argv[0]); return -1; }
 			*target = (unsigned)strtoul(argv[i], NULL, 10);
@@ -69,6 +71,7 @@ int main(int argc, char** argv)
 			return -1;
 		}
 	}
+	if (time_s > 0 && round_ms > 0) rounds = (time_s * 1000u + round_ms - 1) / round_ms;
 	if (filename == NULL || chains == 0 || (rounds == 0 && (steps == 0 || epochs == 0))) {
 		usage(argv[0]);
 		return -1;

@@ -76,3 +76,43 @@ def test_region_confined_chains_only_start_edits_inside(mg, port, corpora):
             assert ctx.score_slab(slab) == port.slab_cost(data, slab)
         assert moved >= 4  # at temperature 0 a chain only keeps moves that do not raise the cost
         an.close()
+
+
+def test_merge_in_two_halves_equals_the_one_call(mg, port, corpora):
+    """mg_anneal_merge_export + mg_anneal_merge_import (the multi-GPU halves, with the parts of two 'processes'
+    summed in between) build the same slab at the same cost as mg_anneal_merge_regions."""
+    import torch
+    from megalania_b200.cooperative import region_plan
+    n = 8192
+    data = corpora("mixed", n)
+    greedy = port.greedy_slab(data)
+    with mg.Context(data) as ctx:
+        an = mg.Annealer(ctx, 64, seed=12, checkpoint_stride=512)
+        an.set_slab(greedy)
+        bounds, region_of_chain = region_plan(n, 64, 4, 1234)
+        nreg = bounds.size - 1
+        regions = np.stack([bounds[region_of_chain], bounds[region_of_chain + 1]], axis=1).astype(np.uint32)
+        an.run(200, schedule=mg.SCHEDULE_TEMPERATURE, temperatures=np.zeros(64, dtype=np.float32), regions=regions)
+        cur, _ = an.costs()
+        owners = np.array([np.nonzero(region_of_chain == r)[0][np.argmin(cur[region_of_chain == r])] for r in range(nreg)],
+                          dtype=np.uint32)
+        # the whole in one call, into chain 62
+        whole = an.merge_regions(bounds, owners, dst_chain=62)
+        slab_whole = an.get_slab(62)
+        # the same as two parts (even / odd regions), summed, into chain 63
+        parts = []
+        for parity in (0, 1):
+            o = owners.copy()
+            o[np.arange(nreg) % 2 != parity] = mg.NO_OWNER
+            s = torch.zeros(n, dtype=torch.int64, device="cuda")
+            a = torch.zeros(n, dtype=torch.int32, device="cuda")
+            an.merge_export(bounds, o, s.data_ptr(), a.data_ptr())
+            parts.append((s, a))
+        s = parts[0][0] + parts[1][0]
+        a = parts[0][1] + parts[1][1]
+        torch.cuda.synchronize()
+        halves = an.merge_import(s.data_ptr(), a.data_ptr(), dst_chain=63)
+        assert halves == whole == port.slab_cost(data, slab_whole)
+        got = an.get_slab(63)
+        assert (got["type"] == slab_whole["type"]).all() and (got["dist"] == slab_whole["dist"]).all() and (got["len"] == slab_whole["len"]).all()
+        an.close()
