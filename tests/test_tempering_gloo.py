@@ -76,3 +76,48 @@ def test_world_size_two_gloo(tmp_path):
     assert int(r0["best"]) == int(r1["best"]) == 800
     assert (r0["got"] == 2).all() and r0["got"].size == 512  # rank 0 received rank 1's slab
     assert r1["got"].size == 0                               # the source keeps its own
+
+
+def _merge_worker(rank, world, port, out_dir):
+    """The exchange step of the multi-GPU cooperative merge, on CPU tensors: every rank fills the slots of
+    the regions it owns, the parts are summed (gloo all-reduce) and must cover every slot exactly once."""
+    import torch
+    import torch.distributed as dist
+    from megalania_b200.cooperative import distributed_plan
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        n, chains = 5000, 24
+        rng = np.random.default_rng(1)  # the same generator state on every rank, as in the driver
+        parts = []
+        for _ in range(3):
+            shift = int(rng.integers(0, n))
+            bounds, owner_rank, regions_of_chains = distributed_plan(n, chains, world, 4, shift)
+            slots = torch.zeros(n, dtype=torch.int64)
+            count = torch.zeros(n, dtype=torch.int64)
+            for r in np.unique(regions_of_chains(rank)):
+                assert owner_rank[r] == rank
+                slots[bounds[r]:bounds[r + 1]] = (rank + 1) * 1000 + int(r)   # stands for the winner's packed slots
+                count[bounds[r]:bounds[r + 1]] = 1
+            dist.all_reduce(slots, op=dist.ReduceOp.SUM)
+            dist.all_reduce(count, op=dist.ReduceOp.SUM)
+            expect = np.zeros(n, dtype=np.int64)
+            for r in range(bounds.size - 1):
+                expect[bounds[r]:bounds[r + 1]] = (int(owner_rank[r]) + 1) * 1000 + r
+            parts.append((slots.numpy().copy(), count.numpy().copy(), expect))
+        np.savez(os.path.join(out_dir, f"merge{rank}.npz"), slots=np.stack([p[0] for p in parts]),
+                 count=np.stack([p[1] for p in parts]), expect=np.stack([p[2] for p in parts]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_cooperative_merge_exchange_gloo(tmp_path):
+    import torch.multiprocessing as mp
+    world = 2
+    mp.spawn(_merge_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    r0 = np.load(tmp_path / "merge0.npz")
+    r1 = np.load(tmp_path / "merge1.npz")
+    assert (r0["count"] == 1).all() and (r1["count"] == 1).all()      # disjoint parts, nothing left out
+    assert (r0["slots"] == r0["expect"]).all()                          # the sum IS the merged whole
+    assert (r0["slots"] == r1["slots"]).all()                           # and every rank holds the same
