@@ -69,3 +69,27 @@ def test_product_never_touches_the_oracle():
             if f.endswith((".py", ".c", ".h", ".cu", ".cuh")):
                 text = open(os.path.join(base, f)).read()
                 assert "oracle_lib" not in text and "mg_oracle" not in text and "libmegalania_ref" not in text, f
+
+
+def test_cli_usage_and_error_exit_status(tmp_path):
+    """The drop-in CLI keeps the reference's contract (src/main.c:29-38): one positional filename, progress and
+    errors on stderr, exit status 255 on usage or I/O errors - and, here, when no CUDA device is present
+    (there is no CPU fallback)."""
+    import subprocess
+    from megalania_b200 import build
+    cli = build.build_cli() or build.CLI
+    assert os.path.exists(cli)
+    r = subprocess.run([cli], capture_output=True)
+    assert r.returncode == 255 and b"usage:" in r.stderr and r.stdout == b""
+    r = subprocess.run([cli, "--rounds"], capture_output=True)
+    assert r.returncode == 255 and b"usage:" in r.stderr
+    r = subprocess.run([cli, "--no-such-flag", "x"], capture_output=True)
+    assert r.returncode == 255 and b"usage:" in r.stderr
+    r = subprocess.run([cli, str(tmp_path / "missing.bin")], capture_output=True)
+    assert r.returncode == 255 and r.stdout == b""
+    import torch
+    if not torch.cuda.is_available():
+        f = tmp_path / "in.bin"
+        f.write_bytes(b"hello hello hello")
+        r = subprocess.run([cli, "--time", "1", str(f)], capture_output=True)
+        assert r.returncode == 255 and r.stdout == b"" and b"mg_ctx_create" in r.stderr
