@@ -7,6 +7,7 @@
 #include <cstring>
 #include <new>
 #include <vector>
+#include <unistd.h>
 
 #include "../../include/megalania_cuda.h"
 #include "mg_kernels.cuh"
@@ -135,8 +136,18 @@ extern "C" MG_API int mg_ctx_create(const uint8_t* data, size_t n, LZMAPropertie
 	if (props.lc || props.lp || props.pb) return fail(MG_EINVAL, "only lc = lp = pb = 0 is supported (as in the reference)");
 	if (n >= 0x7fffff00ull) return fail(MG_EINVAL, "inputs of 2 GiB and more are not supported");
 	int count = 0;
-	if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
-		return fail(MG_ECUDA, "no CUDA device available (this library has no CPU path)");
+	cudaError_t probe = cudaErrorUnknown;
+	for (int attempt = 0; attempt < 5; attempt++) {
+		// back-to-back processes on one GPU: the driver can answer "unavailable" for a moment while the
+		// previous process is still being torn down
+		probe = cudaGetDeviceCount(&count);
+		if (probe == cudaSuccess && count > 0) break;
+		if (probe == cudaErrorNoDevice || probe == cudaErrorInsufficientDriver) break;
+		cudaGetLastError();
+		usleep(200 * 1000);
+	}
+	if (probe != cudaSuccess || count == 0)
+		return fail(MG_ECUDA, "no CUDA device available (this library has no CPU path): %s", cudaGetErrorString(probe));
 	if (device < 0 || device >= count) return fail(MG_EINVAL, "device %d out of range (%d devices)", device, count);
 	CU(cudaSetDevice(device));
 	mg_ctx* ctx = new (std::nothrow) mg_ctx;
