@@ -149,21 +149,23 @@ typedef struct {
 	                          MG_CONTINUE_EVALS to carry each chain's own count on from its last run */
 	const float* temperatures; /* MG_SCHEDULE_TEMPERATURE: host array [chains], 1/2048-bit units */
 	uint64_t packet_budget; /* 0 = none; else a chain also stops after the evaluation that brings the
-	                           packets it priced in this call to this many (time-boxed steps: every
-	                           warp then finishes at about the same moment whatever its suffix lengths) */
+	                           packets it priced in this call to this many (see `suspend` for an exact
+	                           budget): a reproducible way to box a step */
 	uint32_t no_early_exit; /* != 0: always price a proposal to the end of the slab.  By default a
 	                           proposal stops at the first checkpoint where its whole model (every
 	                           probability, automaton state, rep distances, position) is bit-identical
 	                           to the checkpoint the current slab left there: the rest is priced
 	                           exactly as for the current slab, so the full cost is still exact */
-	uint32_t suspend;       /* != 0 (needs packet_budget): the budget is exact.  A proposal that crosses it is
+	uint32_t suspend;       /* != 0 (with packet_budget and / or cycle_budget): the budget is exact.  A proposal that crosses it is
 	                           suspended at the next checkpoint it writes and carried on by the next
 	                           mg_anneal_run on the same chains, so every warp ends a step at the same
 	                           moment even when one evaluation is a large part of the step (1 MiB slabs).
 	                           Trajectories do not depend on where proposals are suspended.  Replacing a
 	                           chain's slab (set_slab, swap, broadcast) drops its suspended proposal */
 	uint64_t cycle_budget;  /* 0 = none; else SM clocks after which the chains stop: at the end of the evaluation
-	                           in flight, or (with suspend) at the next checkpoint it writes.  A wall-clock box:
+	                           in flight, or (with suspend) at the next checkpoint it writes; with suspend the
+	                           match finder also gives a long bucket up at the deadline and the proposal is
+	                           drawn again, from the same generator state, by the next call.  A wall-clock box:
 	                           how many evaluations fit is not reproducible, each chain's trajectory still is */
 	const uint32_t* regions; /* NULL, or host array [chains][2]: chain c only mutates packets that START in the byte range
 	                           [regions[2c], regions[2c+1]) (it still re-prices everything after them).  Instead of
