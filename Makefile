@@ -16,8 +16,8 @@ $(LIB): $(CSRC)/mg_api.cu $(CSRC)/mg_device.cuh $(CSRC)/mg_finder.cuh $(CSRC)/mg
 	mkdir -p $(OUT)
 	$(NVCC) -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 --shared -Xcompiler -fPIC -Xcompiler -fvisibility=hidden -o $@ $<
 
-$(CLI): $(HOST)/main.c $(HOST)/file_output.c $(HOST)/memory_mapper.c $(LIB)
-	$(CC) -O2 -std=gnu11 -Wall -Wextra -Iinclude -o $@ $(HOST)/main.c $(HOST)/file_output.c $(HOST)/memory_mapper.c -L$(OUT) -lmegalania_cuda -Wl,-rpath,'$$ORIGIN' -lm
+$(CLI): $(HOST)/main.c $(HOST)/host_io.c $(LIB)
+	$(CC) -O2 -std=gnu11 -Wall -Wextra -Iinclude -o $@ $(HOST)/main.c $(HOST)/host_io.c -L$(OUT) -lmegalania_cuda -Wl,-rpath,'$$ORIGIN' -lm
 
 oracle:
 	$(MAKE) -C oracle

@@ -21,7 +21,7 @@ CLI = os.path.join(OUT, "megalania")
 CUDA_SOURCES = [os.path.join(PKG, "csrc", "mg_api.cu")]
 CUDA_DEPS = [os.path.join(PKG, "csrc", f) for f in ("mg_device.cuh", "mg_finder.cuh", "mg_kernels.cuh")] + [
     os.path.join(ROOT, "include", f) for f in ("megalania_cuda.h", "output_interface.h", "encoder_interface.h")]
-HOST_SOURCES = [os.path.join(PKG, "host", f) for f in ("main.c", "file_output.c", "memory_mapper.c")]
+HOST_SOURCES = [os.path.join(PKG, "host", f) for f in ("main.c", "host_io.c")]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]

@@ -16,9 +16,8 @@
 #include <stdlib.h>
 #include <string.h>
 
-#include "file_output.h"
+#include "host_io.h"
 #include "megalania_cuda.h"
-#include "memory_mapper.h"
 
 static void usage(const char* argv0)
 {
@@ -77,10 +76,10 @@ int main(int argc, char** argv)
 		return -1;
 	}
 
-	const uint8_t* file_data;
-	size_t file_size;
-	if (map_file(filename, &file_data, &file_size) < 0) return -1;
-	if (file_size == 0) return 0;
+	InputFile input;
+	if (input_file_open(&input, filename) < 0) return -1;
+	const uint8_t* file_data = input.data;
+	const size_t file_size = input.size;
 	if (iters == 0) iters = file_size < 2000 ? (unsigned)file_size : 2000;
 
 	LZMAProperties properties = { 0, 0, 0 };
@@ -225,13 +224,17 @@ int main(int argc, char** argv)
 	}
 
 	OutputInterface output;
-	file_output_new(&output, stdout);
+	StreamSink sink;
+	stream_sink_init(&output, &sink, stdout);
 	if (mg_encode_slab(ctx, packets_best, &output)) return die("mg_encode_slab");
-	fflush(stdout);
+	if (fflush(stdout) != 0 || sink.failed) {
+		fprintf(stderr, "could not write the output stream\n");
+		return -1;
+	}
 
 	free(best_costs);
 	free(packets_best);
 	mg_ctx_destroy(ctx);
-	if (unmap(file_data, file_size) < 0) return -1;
+	input_file_close(&input);
 	return 0;
 }
