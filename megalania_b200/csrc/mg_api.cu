@@ -1145,6 +1145,7 @@ extern "C" MG_API int mg_anneal_merge_import(mg_anneal* an, const void* dev_slab
 	mg_ctx* ctx = an->ctx;
 	const size_t n = ctx->n;
 	CU(cudaSetDevice(ctx->device));
+	CU(cudaMemsetAsync(an->d_bad, 0, 4, ctx->stream));
 	validate_kernel<<<grid_for(n, 256, ctx->sm_count * 4), 256, 0, ctx->stream>>>(static_cast<const uint64_t*>(dev_slab), ctx->n, an->d_bad);
 	CU(cudaGetLastError());
 	uint32_t bad = 0;
