@@ -121,6 +121,9 @@ MG_API int mg_encode_slab(mg_ctx* ctx, const LZMAPacket* slab, OutputInterface* 
 /* Same, into a caller buffer; *out_len receives the stream length (may exceed cap: then
  * nothing past cap was written and the call returns MG_EINVAL). */
 MG_API int mg_encode_slab_buffer(mg_ctx* ctx, const LZMAPacket* slab, uint8_t* out, size_t cap, size_t* out_len);
+/* Device time (CUDA events around the range-coder kernel) and events coded (modelled bits + direct-bit groups)
+ * by the last mg_encode_slab / mg_encode_slab_buffer on ctx. */
+MG_API int mg_encode_stats(const mg_ctx* ctx, double* kernel_ms, uint64_t* events);
 
 /* ---- the annealing loop ---------------------------------------------------------------- */
 
@@ -194,6 +197,8 @@ typedef struct {
 	uint64_t chain_cycles;     /* SM clocks each chain's warp was busy, summed over chains */
 	uint64_t finder_chunks;    /* 32-occurrence steps of the match finder */
 	uint64_t max_chain_cycles; /* the longest-running chain: chain_cycles / (chains * this) = how evenly the step ended */
+	uint64_t finder_gave_up;   /* clock-boxed steps: proposals taken back because the deadline passed inside the match
+	                              finder (redrawn by the next call from the same generator state) */
 	double kernel_ms;          /* device time of the launch(es), CUDA events */
 	uint32_t launches;         /* kernels launched by this call */
 } mg_anneal_stats;
@@ -287,6 +292,10 @@ typedef struct {
 	uint64_t cost;
 } mg_model_dump;
 MG_API int mg_debug_model_after_prefix(mg_ctx* ctx, const LZMAPacket* slab, size_t stop, mg_model_dump* out);
+/* The device-built bigram index (replaces memoize_bigram_positions, src/substring_enumerator.c:26-47):
+ * occ_start[65537] = bucket offsets for key (data[i] << 8) | data[i+1], occ[n-1] = positions 0..n-2 sorted by
+ * key, ascending inside a bucket - the order substring_enumerator_for_each walks (src/substring_enumerator.c:85-105). */
+MG_API int mg_debug_index(mg_ctx* ctx, uint32_t* occ_start, uint32_t* occ);
 
 #ifdef __cplusplus
 }

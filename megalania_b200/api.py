@@ -61,7 +61,7 @@ class AnnealStats(C.Structure):
     _fields_ = [(name, C.c_uint64) for name in (
         "evals", "attempts", "accepted", "new_best", "packets_scored", "bits_scored", "slab_bytes_read",
         "checkpoint_bytes", "finder_calls", "finder_candidates", "edits", "log_overflows", "rejoined", "finder_cycles", "chain_cycles",
-        "finder_chunks", "max_chain_cycles")] + [
+        "finder_chunks", "max_chain_cycles", "finder_gave_up")] + [
         ("kernel_ms", C.c_double), ("launches", C.c_uint32)]
 
     def as_dict(self) -> dict:
@@ -83,7 +83,7 @@ EXPORTS = [
     "mg_anneal_get_slab", "mg_anneal_get_trace", "mg_anneal_swap_chains", "mg_anneal_device_slab",
     "mg_anneal_refresh_chain", "mg_anneal_oneshot", "mg_debug_model_after_prefix", "mg_anneal_export_slab",
     "mg_anneal_import_slab", "mg_anneal_merge_regions", "mg_anneal_broadcast_chain", "mg_find_topk_stats",
-    "mg_anneal_merge_export", "mg_anneal_merge_import",
+    "mg_anneal_merge_export", "mg_anneal_merge_import", "mg_debug_index", "mg_encode_stats",
 ]
 
 _lib = None
@@ -141,6 +141,8 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
     L.mg_anneal_oneshot.argtypes = [vp, C.POINTER(AnnealParams), C.POINTER(AnnealRunParams), vp, vp,
                                     C.POINTER(u64), C.POINTER(AnnealStats)]
     L.mg_debug_model_after_prefix.argtypes = [vp, vp, sz, vp]
+    L.mg_debug_index.argtypes = [vp, vp, vp]
+    L.mg_encode_stats.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(u64)]
     _lib = L
     return L
 
@@ -249,6 +251,11 @@ class Context:
         _check(self._lib.mg_encode_slab(self._h, _slab_ptr(slab, self.n), C.byref(iface)))
         return b"".join(chunks)
 
+    def encode_stats(self) -> dict:
+        ms, ev = C.c_double(0), C.c_uint64(0)
+        _check(self._lib.mg_encode_stats(self._h, C.byref(ms), C.byref(ev)))
+        return {"kernel_ms": ms.value, "events": int(ev.value)}
+
     def encode_slab_buffer(self, slab: np.ndarray) -> bytes:
         cap = self.n * 2 + 8192
         out = np.zeros(cap, dtype=np.uint8)
@@ -262,6 +269,13 @@ class Context:
         _check(self._lib.mg_debug_model_after_prefix(self._h, _slab_ptr(slab, self.n), stop,
                                                      out.ctypes.data_as(C.c_void_p)))
         return out[0]
+
+    def bigram_index(self):
+        """(occ_start[65537], occ[n-1]): the device-built index of src/substring_enumerator.c:26-47."""
+        start = np.zeros(65537, dtype=np.uint32)
+        occ = np.zeros(max(1, self.n - 1), dtype=np.uint32)
+        _check(self._lib.mg_debug_index(self._h, start.ctypes.data_as(C.c_void_p), occ.ctypes.data_as(C.c_void_p)))
+        return start, occ[:max(0, self.n - 1)]
 
     def chain_bytes(self, **params) -> int:
         p = AnnealParams(**params)

@@ -51,6 +51,8 @@ struct mg_ctx {
 	std::vector<mg_anneal*> annealers;  // live chain populations on this context (destroyed with it)
 	double last_topk_ms = 0;          // mg_find_topk: device time and candidates of the last call
 	unsigned long long last_topk_candidates = 0;
+	double last_encode_ms = 0;        // mg_encode_slab*: device time and events of the last call
+	unsigned long long last_encode_events = 0;
 };
 
 struct DevBuf {
@@ -225,6 +227,23 @@ extern "C" MG_API int mg_find_topk_stats(const mg_ctx* ctx, double* kernel_ms, u
 	return MG_OK;
 }
 extern "C" MG_API int mg_ctx_device(const mg_ctx* ctx) { return ctx ? ctx->device : -1; }
+extern "C" MG_API int mg_encode_stats(const mg_ctx* ctx, double* kernel_ms, uint64_t* events)
+{
+	if (!ctx) return fail(MG_EINVAL, "mg_encode_stats: null context");
+	if (kernel_ms) *kernel_ms = ctx->last_encode_ms;
+	if (events) *events = ctx->last_encode_events;
+	return MG_OK;
+}
+
+extern "C" MG_API int mg_debug_index(mg_ctx* ctx, uint32_t* occ_start, uint32_t* occ)
+{
+	if (!ctx || !occ_start || !occ) return fail(MG_EINVAL, "mg_debug_index: null argument");
+	CU(cudaSetDevice(ctx->device));
+	CU(cudaMemcpyAsync(occ_start, ctx->d_occ_start, sizeof(uint32_t) * (INDEX_KEYS + 1), cudaMemcpyDeviceToHost, ctx->stream));
+	if (ctx->n > 1) CU(cudaMemcpyAsync(occ, ctx->d_occ, sizeof(uint32_t) * (size_t)(ctx->n - 1), cudaMemcpyDeviceToHost, ctx->stream));
+	CU(cudaStreamSynchronize(ctx->stream));
+	return MG_OK;
+}
 
 // Upload `count` host packets (12 B each) and pack them into dst (device, u64 each).
 static int upload_packed(mg_ctx* ctx, const LZMAPacket* host, size_t count, uint64_t* dst)
@@ -504,7 +523,7 @@ static int encode_to_host(mg_ctx* ctx, const LZMAPacket* slab, std::vector<uint8
 	DevBuf packed, out, len, err;
 	if (int rc = dev_alloc(packed, (size_t)n * 8)) return rc;
 	if (int rc = dev_alloc(out, cap)) return rc;
-	if (int rc = dev_alloc(len, 4)) return rc;
+	if (int rc = dev_alloc(len, 8)) return rc;
 	if (int rc = dev_alloc(err, 4)) return rc;
 	if (int rc = upload_packed(ctx, slab, n, packed.as<uint64_t>())) return rc;
 	EncodeArgs a;
@@ -515,13 +534,28 @@ static int encode_to_host(mg_ctx* ctx, const LZMAPacket* slab, std::vector<uint8
 	a.cap = cap;
 	a.out_len = len.as<uint32_t>();
 	a.out_err = err.as<uint32_t>();
+	a.out_events = len.as<uint32_t>() + 1;
 	a.tables = ctx->tables;
-	encode_kernel<<<1, 32, 0, ctx->stream>>>(a);
+	cudaEvent_t t0, t1;
+	CU(cudaEventCreate(&t0));
+	CU(cudaEventCreate(&t1));
+	CU(cudaEventRecord(t0, ctx->stream));
+	encode_kernel<<<1, 64, 0, ctx->stream>>>(a);
+	CU(cudaEventRecord(t1, ctx->stream));
 	CU(cudaGetLastError());
-	uint32_t hlen = 0, herr = 0;
-	CU(cudaMemcpyAsync(&hlen, len.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+	uint32_t hlen2[2] = {0, 0}, herr = 0;
+	CU(cudaMemcpyAsync(hlen2, len.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
 	CU(cudaMemcpyAsync(&herr, err.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
 	CU(cudaStreamSynchronize(ctx->stream));
+	{
+		float ms = 0;
+		cudaEventElapsedTime(&ms, t0, t1);
+		ctx->last_encode_ms = ms;
+		ctx->last_encode_events = hlen2[1];
+		cudaEventDestroy(t0);
+		cudaEventDestroy(t1);
+	}
+	const uint32_t hlen = hlen2[0];
 	if (herr) return fail(MG_ESLAB, "mg_encode_slab: %s", walk_error(herr));
 	payload.resize(hlen);
 	CU(cudaMemcpyAsync(payload.data(), out.p, hlen, cudaMemcpyDeviceToHost, ctx->stream));
@@ -981,6 +1015,7 @@ extern "C" MG_API int mg_anneal_run(mg_anneal* an, const mg_anneal_run_params* r
 			stats->rejoined += cs[c].rejoined;
 			stats->finder_cycles += cs[c].find_cycles;
 			stats->finder_chunks += cs[c].chunks;
+			stats->finder_gave_up += cs[c].gave_up;
 			stats->chain_cycles += cs[c].chain_cycles;
 			if (cs[c].chain_cycles > stats->max_chain_cycles) stats->max_chain_cycles = cs[c].chain_cycles;
 		}

@@ -17,7 +17,7 @@ constexpr uint32_t RECIP_ENTRIES = 288;
 
 struct ChainStats {
 	unsigned long long evals, attempts, accepted, new_best, packets, bits, slab_bytes, ck_bytes, finds, candidates,
-	    edits, overflows, rejoined, find_cycles, chain_cycles, chunks;
+	    edits, overflows, rejoined, find_cycles, chain_cycles, chunks, gave_up;
 };
 
 struct ChainState {
@@ -882,7 +882,7 @@ __global__ void __launch_bounds__(CTA_THREADS, MG_ANNEAL_MIN_CTAS) anneal_kernel
 	// Counters live in shared memory and are touched by lane 0 only: lanes of a warp are not
 	// guaranteed to run in lockstep, so a read-modify-write by all of them could count twice.
 	ChainStats& cs = ws->stats;
-	if (lane == 0) cs = ChainStats{0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+	if (lane == 0) cs = ChainStats{0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 	const long long t_start = clock64();
 	unsigned long long packets_done = 0;  // uniform copy of cs.packets for the budget test
 	EditLog lg;
@@ -1170,6 +1170,7 @@ __global__ void __launch_bounds__(CTA_THREADS, MG_ANNEAL_MIN_CTAS) anneal_kernel
 			// state, nothing committed) and the next launch draws it again
 			rng = rng_at_start;
 			attempts--;
+			if (lane == 0) cs.gave_up++;
 			break;
 		}
 		if (suspended) {
@@ -1335,6 +1336,7 @@ struct EncodeArgs {
 	uint32_t cap;
 	uint32_t* out_len;
 	uint32_t* out_err;
+	uint32_t* out_events;  // events coded (modelled bits + direct-bit groups)
 	Tables tables;
 };
 
@@ -1399,29 +1401,86 @@ __device__ __forceinline__ void rc_direct(RangeCoder& rc, uint32_t bits, uint32_
 	}
 }
 
-// Two phases per batch of packets: (A) the warp prices packets exactly as the scorer does and appends
-// their (bit, probability) events - in the reference's coding order, direct bits included - to a queue
-// in shared memory; (B) lane 0 runs the range coder's carry / shift-low recurrence over the queue in
-// one tight loop.  (Interleaving A and B per packet cost 3000 cycles per packet.)
-constexpr uint32_t ENCODE_QUEUE = 2048;
-__global__ void __launch_bounds__(32) encode_kernel(EncodeArgs a)
+// One CTA of two warps joined by a ring of events in shared memory:
+//   warp 0 (producer) walks the slab with the model exactly as the scorer does and appends each packet's
+//          (bit, probability) events - in the reference's coding order, direct bits included - to the ring;
+//          plain literals (nine events from nine lanes, no cross-lane traffic) take a short path;
+//   warp 1 (consumer), lane 0, runs the range coder's carry / shift-low recurrence (src/range_encoder.c:18-64)
+//          over the ring.  That recurrence is the one strictly sequential part of the whole path: its critical
+//          chain per event is range -> range >> 11 -> multiply-add -> normalise, everything else (low, cache,
+//          output bytes) hangs off it.  Events are pre-digested by the producer for it: q = the probability of
+//          the coded bit (p or 2048 - p), so that the new range is (range >> 11) * q + (bit ? range & 2047 : 0)
+//          for either bit value - one multiply-add, no select.
+// The two warps sit on different schedulers of the SM, so the model walk (50-100 cycles per packet) hides
+// behind the recurrence (round 1 ran them back to back on one warp: 1.2 s per MiB).
+constexpr uint32_t ENC_RING = 8192;  // events; a packet appends at most 28
+constexpr uint32_t ENC_DIRECT = 0x80000000u;
+
+struct EncodeShared {
+	Record rec;
+	uint32_t ring[ENC_RING];
+	unsigned char stage[STAGE_BYTES];
+	uint32_t head;  // events produced so far (producer writes, consumer reads)
+	uint32_t tail;  // events consumed so far
+	uint32_t done;  // 1 = producer finished, 2 = producer stopped on an error
+	uint32_t err;
+};
+
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p)
 {
-	__shared__ __align__(16) Record rec;
-	__shared__ uint32_t queue[ENCODE_QUEUE];  // bit << 15 | prob, or 1 << 31 | nbits << 26 | direct bits
-	__shared__ __align__(16) unsigned char stage[STAGE_BYTES];
-	const int lane = threadIdx.x;
+	uint32_t v;
+	asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+	return v;
+}
+__device__ __forceinline__ void st_release_u32(uint32_t* p, uint32_t v)
+{
+	asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+}
+
+// event word of a modelled bit coded at probability p (of a zero): q | bit << 15
+__device__ __forceinline__ uint32_t enc_event(uint32_t p, uint32_t bit) { return (bit ? 2048u - p : p) | (bit << 15); }
+
+__device__ __forceinline__ void encode_produce(EncodeShared* sh, const EncodeArgs& a, int lane)
+{
 	Model m;
-	model_init(lane, SmemU16{smem_u32(rec.probs)}, m);
-	RangeCoder rc = {0, 0xFFFFFFFFu, 0, 1, a.out, a.cap, 0};
+	const SmemU16 probs{smem_u32(sh->rec.probs)};
+	model_init(lane, probs, m);
 	Window w;
 	w.base = WINDOW_NONE;
 	w.pf_base = WINDOW_NONE;
-	uint32_t err = 0;
-	while (m.pos < a.n && !err) {
-		uint32_t qn = 0;
-		while (m.pos < a.n && qn + 28 <= ENCODE_QUEUE) {
-			window_seek(lane, w, a.slab, a.data, a.n, m.pos, smem_u32(stage));
-			const uint32_t meta = window_meta(w, m.pos);
+	uint32_t head = 0, tail_seen = 0, err = 0;
+	const uint32_t ring = smem_u32(sh->ring);
+	const uint32_t stage = smem_u32(sh->stage);
+	// literal lanes: lane 0 is_match, lanes 1..8 tree depth 0..7
+	const uint32_t depth = lane >= 1 && lane <= 8 ? (uint32_t)lane - 1 : 0;
+	while (m.pos < a.n) {
+		// room for the largest packet (28 events)?
+		while (head + 28 - tail_seen > ENC_RING) {
+			tail_seen = ld_acquire_u32(&sh->tail);
+			if (head + 28 - tail_seen > ENC_RING) __nanosleep(64);
+		}
+		window_seek(lane, w, a.slab, a.data, a.n, m.pos, stage);
+		const uint32_t meta = window_meta(w, m.pos);
+		uint32_t count;
+		if ((meta & 0xffffu) == META_LITERAL && m.ctx < 7) {
+			// plain literal (src/lzma_packet_encoder.c:106-121)
+			const uint32_t byte = (meta >> 16) & 0xff;
+			uint32_t slot, bit;
+			lit_event(depth, byte, false, 0, slot, bit);
+			if (lane == 0) {
+				slot = S_ISMATCH + m.ctx;
+				bit = 0;
+			}
+			if (lane <= 8) {
+				const uint32_t p = probs.get(slot);
+				sts_u32(ring + 4u * ((head + (uint32_t)lane) & (ENC_RING - 1)), enc_event(p, bit));
+				probs.set(slot, bit ? p - (p >> 5) : p + ((2048u - p) >> 5));
+			}
+			count = 9;
+			m.ctx = m.ctx < 4 ? 0 : m.ctx - 3;
+			m.pos += 1;
+			m.pidx += 1;
+		} else {
 			const uint32_t type = meta_type(meta), len = meta_len(meta), dist = window_dist(w, m.pos);
 			const uint32_t byte = meta_byte(meta) & 0xff;
 			if (!packet_ok(m, a.n, type, len, dist)) {
@@ -1440,36 +1499,87 @@ __global__ void __launch_bounds__(32) encode_kernel(EncodeArgs a)
 			const uint32_t has_direct = dp.direct ? 1u : 0u;
 			const uint32_t before_direct = __popc(mask & ((1u << FIRST_REVTREE_LANE) - 1u));
 			if (active) {
-				uint32_t p = rec.probs[slot];
-				const uint32_t rank = __popc(mask & ((1u << lane) - 1u));
-				queue[qn + rank + (lane >= FIRST_REVTREE_LANE ? has_direct : 0u)] = (bit << 15) | p;
-				p = bit ? p - (p >> 5) : p + ((2048u - p) >> 5);
-				rec.probs[slot] = (uint16_t)p;
+				const uint32_t p = probs.get(slot);
+				const uint32_t rank = __popc(mask & ((1u << lane) - 1u)) + (lane >= FIRST_REVTREE_LANE ? has_direct : 0u);
+				sts_u32(ring + 4u * ((head + rank) & (ENC_RING - 1)), enc_event(p, bit));
+				probs.set(slot, bit ? p - (p >> 5) : p + ((2048u - p) >> 5));
 			}
 			if (lane == 0 && has_direct)
-				queue[qn + before_direct] = 0x80000000u | (dp.direct << 26) | ((dist & ((1u << dp.nlow) - 1u)) >> 4);
-			qn += __popc(mask) + has_direct;
-			__syncwarp();
+				sts_u32(ring + 4u * ((head + before_direct) & (ENC_RING - 1)),
+				        ENC_DIRECT | (dp.direct << 26) | ((dist & ((1u << dp.nlow) - 1u)) >> 4));
+			count = __popc(mask) + has_direct;
 			model_advance(m, type, len, dist);
 		}
-		__syncwarp();
-		if (lane == 0) {
-			for (uint32_t i = 0; i < qn; i++) {
-				const uint32_t e = queue[i];
-				if (e >> 31)
-					rc_direct(rc, e & 0x3ffffffu, (e >> 26) & 31u);
-				else
-					rc_bit(rc, e >> 15, e & 0x7fffu);
-			}
-		}
-		__syncwarp();
+		head += count;
+		__syncwarp();  // every lane's events are in the ring before lane 0 publishes them
+		if (lane == 0) st_release_u32(&sh->head, head);
 	}
 	asm volatile("cp.async.wait_group 0;" ::: "memory");
+	__syncwarp();
 	if (lane == 0) {
-		for (int i = 0; i < 5; i++) rc_shift_low(rc);  // src/range_encoder.c:40-45
-		*a.out_len = rc.len;
-		*a.out_err = err | (rc.len > rc.cap ? ERR_OUTPUT_FULL : 0);
+		sh->err = err;
+		st_release_u32(&sh->done, err ? 2u : 1u);
 	}
+}
+
+__device__ __forceinline__ void encode_consume(EncodeShared* sh, const EncodeArgs& a)
+{
+	RangeCoder rc = {0, 0xFFFFFFFFu, 0, 1, a.out, a.cap, 0};
+	uint32_t tail = 0;
+	const uint32_t ring = smem_u32(sh->ring);
+	for (;;) {
+		uint32_t head = ld_acquire_u32(&sh->head);
+		if (head == tail) {
+			if (ld_acquire_u32(&sh->done) == 0) {
+				__nanosleep(32);
+				continue;
+			}
+			head = ld_acquire_u32(&sh->head);  // published before `done`
+			if (head == tail) break;
+		}
+		// a bounded batch, so that the producer sees the ring drain while a long backlog is coded
+		if (head - tail > ENC_RING / 4) head = tail + ENC_RING / 4;
+		while (tail != head) {
+			const uint32_t e = lds_u32(ring + 4u * (tail & (ENC_RING - 1)));
+			tail++;
+			if (e & ENC_DIRECT) {
+				rc_direct(rc, e & 0x3ffffffu, (e >> 26) & 31u);
+				continue;
+			}
+			// src/range_encoder.c:47-64 with bound = (range >> 11) * p:
+			//   bit 0: range' = bound                     = (range >> 11) * q              (q = p)
+			//   bit 1: range' = range - bound, low += bound = (range >> 11) * q + (range & 2047)  (q = 2048 - p)
+			const uint32_t q = e & 0x7fffu, bit = e >> 15;
+			const uint32_t keep = bit ? 2047u : 0u;
+			const uint32_t next = (rc.range >> 11) * q + (rc.range & keep);
+			if (bit) rc.low += rc.range - next;
+			rc.range = next;
+			// p stays within [31, 2017] (src/probability_model.c:5-15), so one shift always suffices
+			if ((next & 0xFF000000u) == 0) {
+				rc.range = next << 8;
+				rc_shift_low(rc);
+			}
+		}
+		st_release_u32(&sh->tail, tail);
+	}
+	for (int i = 0; i < 5; i++) rc_shift_low(rc);  // src/range_encoder.c:40-45
+	const uint32_t err = sh->err;
+	*a.out_len = rc.len;
+	*a.out_err = err | (rc.len > rc.cap ? ERR_OUTPUT_FULL : 0);
+	*a.out_events = tail;
+}
+
+__global__ void __launch_bounds__(64) encode_kernel(EncodeArgs a)
+{
+	__shared__ __align__(16) EncodeShared sh;
+	if (threadIdx.x == 0) {
+		sh.head = sh.tail = sh.done = sh.err = 0;
+	}
+	__syncthreads();
+	if (threadIdx.x < 32)
+		encode_produce(&sh, a, (int)threadIdx.x);
+	else if (threadIdx.x == 32)
+		encode_consume(&sh, a);
 }
 
 // ---- slab format conversion: host LZMAPacket (12 B) <-> packed u64 ----------------------------------
