@@ -216,7 +216,7 @@ def run_cuda(args) -> None:
     data = _corpus("mixed", n)
     ctx = mg.Context(data, device=local)
     props = torch.cuda.get_device_properties(local)
-    chains = args.chains or props.multi_processor_count * args.warps_per_sm
+    chains = args.chains or (props.multi_processor_count * args.warps_per_sm if args.warps_per_sm else ctx.full_wave())
     chain_bytes = ctx.chain_bytes(chains=chains, track_best=1)
     free, _ = torch.cuda.mem_get_info(local)
     while chains > 8 and chains * chain_bytes > 0.85 * free:
@@ -418,7 +418,7 @@ def main() -> None:
     ap.add_argument("--impl", choices=["cuda", "reference"], default="cuda")
     ap.add_argument("--size", type=int, default=1 << 20)
     ap.add_argument("--chains", type=int, default=0, help="chains per GPU (default: SMs x --warps-per-sm)")
-    ap.add_argument("--warps-per-sm", type=int, default=32)
+    ap.add_argument("--warps-per-sm", type=int, default=0, help="0 = the library's own figure (chains per SM that fit shared memory)")
     ap.add_argument("--evals", type=int, default=1_000_000, help="cap on successful evaluations per chain per step")
     ap.add_argument("--step-ms", type=float, default=1000.0, help="length of a step in milliseconds of SM clocks")
     ap.add_argument("--packet-budget", type=int, default=0,

@@ -82,6 +82,9 @@ MG_API int mg_ctx_create(const uint8_t* data, size_t n, LZMAProperties props, in
 MG_API void mg_ctx_destroy(mg_ctx* ctx);
 MG_API size_t mg_ctx_size(const mg_ctx* ctx);
 MG_API int mg_ctx_device(const mg_ctx* ctx);
+/* Chains that fill the device exactly once: SMs x chains per SM (one warp and one model in shared memory each).
+ * Populations are best sized in multiples of it. */
+MG_API uint32_t mg_ctx_full_wave(const mg_ctx* ctx);
 
 /* ---- parity function 2: cost(data, slab) ----------------------------------------------- */
 

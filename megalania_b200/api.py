@@ -83,7 +83,7 @@ EXPORTS = [
     "mg_anneal_get_slab", "mg_anneal_get_trace", "mg_anneal_swap_chains", "mg_anneal_device_slab",
     "mg_anneal_refresh_chain", "mg_anneal_oneshot", "mg_debug_model_after_prefix", "mg_anneal_export_slab",
     "mg_anneal_import_slab", "mg_anneal_merge_regions", "mg_anneal_broadcast_chain", "mg_find_topk_stats",
-    "mg_anneal_merge_export", "mg_anneal_merge_import", "mg_debug_index", "mg_encode_stats",
+    "mg_anneal_merge_export", "mg_anneal_merge_import", "mg_debug_index", "mg_encode_stats", "mg_ctx_full_wave",
 ]
 
 _lib = None
@@ -114,6 +114,8 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
     L.mg_ctx_size.argtypes = [vp]
     L.mg_ctx_size.restype = sz
     L.mg_ctx_device.argtypes = [vp]
+    L.mg_ctx_full_wave.argtypes = [vp]
+    L.mg_ctx_full_wave.restype = u32
     L.mg_score_slabs.argtypes = [vp, vp, sz, vp]
     L.mg_find_topk.argtypes = [vp, vp, i32, vp, sz, i32, vp, vp, vp]
     L.mg_find_topk_stats.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(u64)]
@@ -269,6 +271,10 @@ class Context:
         _check(self._lib.mg_debug_model_after_prefix(self._h, _slab_ptr(slab, self.n), stop,
                                                      out.ctypes.data_as(C.c_void_p)))
         return out[0]
+
+    def full_wave(self) -> int:
+        """Chains that fill the device exactly once (SMs x chains per SM)."""
+        return int(self._lib.mg_ctx_full_wave(self._h))
 
     def bigram_index(self):
         """(occ_start[65537], occ[n-1]): the device-built index of src/substring_enumerator.c:26-47."""

@@ -44,6 +44,7 @@ struct mg_ctx {
 	uint32_t* d_occ_start = nullptr;  // 65537
 	uint32_t* d_occ = nullptr;        // n
 	uint32_t* d_trans = nullptr;
+	uint32_t* d_trans2 = nullptr;
 	uint32_t* d_recip = nullptr;
 	Tables tables{};
 	int sm_count = 0;
@@ -182,14 +183,25 @@ extern "C" MG_API int mg_ctx_create(const uint8_t* data, size_t n, LZMAPropertie
 			trans[2048 + p] = (p - (p >> 5)) | (price[(2048u - p) & 2047u] << 16);        // bit 1
 		}
 		trans[0] = 0;  // probability 0 never occurs in a model: (0, bit 0) is a zero-price fixed point (the spare slot's value)
+		// two steps on one slot (pair steps of the literal walk): bits (a, b) in that order
+		std::vector<uint32_t> trans2(8192, 0);
+		for (uint32_t ab = 0; ab < 4; ab++)
+			for (uint32_t p = 1; p < 2048; p++) {
+				const uint32_t s1 = trans[((ab >> 1) << 11) | p], p1 = s1 & 0xffffu;
+				const uint32_t s2 = trans[((ab & 1) << 11) | p1];
+				trans2[(ab << 11) | p] = (s2 & 0xffffu) | (((s1 >> 16) + (s2 >> 16)) << 16);
+			}
 		std::vector<uint32_t> recip(RECIP_ENTRIES, 0);
 		for (uint32_t i = 1; i < RECIP_ENTRIES; i++) recip[i] = 0xffffffffu / i + 1u;
 		CUB(cudaMalloc(&ctx->d_trans, 4096 * sizeof(uint32_t)));
+		CUB(cudaMalloc(&ctx->d_trans2, 8192 * sizeof(uint32_t)));
 		CUB(cudaMalloc(&ctx->d_recip, RECIP_ENTRIES * sizeof(uint32_t)));
 		CUB(cudaMemcpyAsync(ctx->d_trans, trans.data(), 4096 * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+		CUB(cudaMemcpyAsync(ctx->d_trans2, trans2.data(), 8192 * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
 		CUB(cudaMemcpyAsync(ctx->d_recip, recip.data(), RECIP_ENTRIES * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
 		CUB(cudaStreamSynchronize(ctx->stream));
 		ctx->tables.trans = ctx->d_trans;
+		ctx->tables.trans2 = ctx->d_trans2;
 		ctx->tables.recip = ctx->d_recip;
 		rc = build_index(ctx);
 #undef CUB
@@ -213,6 +225,7 @@ extern "C" MG_API void mg_ctx_destroy(mg_ctx* ctx)
 	cudaFree(ctx->d_occ_start);
 	cudaFree(ctx->d_occ);
 	cudaFree(ctx->d_trans);
+	cudaFree(ctx->d_trans2);
 	cudaFree(ctx->d_recip);
 	if (ctx->stream) cudaStreamDestroy(ctx->stream);
 	delete ctx;
@@ -227,6 +240,7 @@ extern "C" MG_API int mg_find_topk_stats(const mg_ctx* ctx, double* kernel_ms, u
 	return MG_OK;
 }
 extern "C" MG_API int mg_ctx_device(const mg_ctx* ctx) { return ctx ? ctx->device : -1; }
+extern "C" MG_API uint32_t mg_ctx_full_wave(const mg_ctx* ctx) { return ctx ? (uint32_t)ctx->sm_count * (uint32_t)WARPS_PER_CTA : 0u; }
 extern "C" MG_API int mg_encode_stats(const mg_ctx* ctx, double* kernel_ms, uint64_t* events)
 {
 	if (!ctx) return fail(MG_EINVAL, "mg_encode_stats: null context");

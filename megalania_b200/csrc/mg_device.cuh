@@ -541,6 +541,7 @@ struct Window {
 	uint32_t base;        // multiple of 32; WINDOW_NONE = nothing loaded
 	uint32_t pf_base;     // window being copied into the warp's staging area by cp.async (WINDOW_NONE = none)
 	uint32_t litmask;     // bit i: slot base+i is a canonical LITERAL
+	uint32_t pairs;       // != 0: enough literals in the window for pair steps to repay the event mirror
 	uint32_t ev_base;     // window base | 1 literal events mirrored | 2 MATCH descriptors mirrored (see window_events / window_matches)
 };
 constexpr uint32_t WINDOW_NONE = 0x7fffffe0u;  // never within 32 of a real position (inputs < 2 GiB... see mg_ctx_create)
@@ -599,6 +600,7 @@ __device__ __forceinline__ void window_seek(int lane, Window& w, const uint64_t*
 	window_prefetch(lane, slab, data, n, want + 32, stage);
 	w.pf_base = want + 32;
 	w.litmask = __ballot_sync(FULL, (w.meta & 0xffffu) == META_LITERAL);
+	w.pairs = __popc(w.litmask) >= 16 ? 1u : 0u;
 }
 
 __device__ __forceinline__ uint32_t window_meta(const Window& w, uint32_t pos)

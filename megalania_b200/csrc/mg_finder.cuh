@@ -32,10 +32,11 @@ struct FindScratch {
 	uint32_t chunks;      // 32-occurrence steps the last find took (its cost in the step budget)
 };
 
-// Literal-event mirror: for each of the nine literal lanes a row of 32 events (one per slot of the
-// current slab window) + 4 words of padding, so that a lane fetches four consecutive events with one
-// 16-byte load and the nine rows start on different banks.
-constexpr uint32_t EVENT_ROW_WORDS = 36, EVENT_LANES = 9;
+// Literal-event mirror: for each of the nine literal slot classes a row of 32 events (one per slot of the
+// current slab window; even window positions in columns 0..15, odd ones in columns 16..31, see
+// window_events() in mg_kernels.cuh) + 4 words of padding, so that a lane fetches the events of four pairs
+// with one 16-byte load and the rows start on different banks.
+constexpr uint32_t EVENT_ROW_WORDS = 36, EVENT_LANES = 9, EVENT_PAIR_COLUMNS = 16;
 // ... followed by one 16-byte MATCH descriptor per slot of the window (window_matches()).
 constexpr uint32_t MATCH_DESC_OFFSET = EVENT_LANES * EVENT_ROW_WORDS * 4;
 // ... followed by the staging area of the NEXT window: 32 slab slots (8 B) + 32 data bytes, filled by cp.async.

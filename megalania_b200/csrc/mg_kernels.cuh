@@ -5,15 +5,17 @@
 
 namespace mg {
 
-// One CTA of 32 warps per SM: the walk is bound by shared-memory latency, so occupancy is what
-// hides it; 32 models + the transition table fill the 227 KB of shared memory, and 64 registers
-// per thread fill the register file.
+// One CTA of 27 warps per SM: 27 models + the transition tables (16 KB single-step, 32 KB two-step, see
+// CtaShared) fill the 227 KB of shared memory; 864 threads leave 72 registers per thread.  The walk is bound by
+// shared-memory wavefronts; literal runs are priced two literals per warp instruction, which doubles the work a
+// warp has in flight and pays for the five warps the two-step table displaces.
 #ifndef MG_WARPS_PER_CTA
-#define MG_WARPS_PER_CTA 32
+#define MG_WARPS_PER_CTA 27
 #endif
 constexpr int WARPS_PER_CTA = MG_WARPS_PER_CTA;
 constexpr int CTA_THREADS = WARPS_PER_CTA * 32;
 constexpr uint32_t RECIP_ENTRIES = 288;
+constexpr uint32_t PAIR_LANES = 0x3ffffu;  // lanes 0..17: the two literals of a pair step
 
 struct ChainStats {
 	unsigned long long evals, attempts, accepted, new_best, packets, bits, slab_bytes, ck_bytes, finds, candidates,
@@ -64,29 +66,48 @@ struct WarpShared {
 	uint64_t bar;
 	ChainStats stats;    // counters of the running launch (kept out of the register file; lane 0 only)
 };
+// The transition tables span eight 8 KB sections so that an event's top three bits ARE its section
+// (table byte offset = (event >> 16) & 0xE000, see window_events()):
+//   section 0, 1   single step, bit 0 / 1            trans[bit << 11 | p]            (code_bit())
+//   section 2, 3   not table: reciprocals, lane constants and the first two warps' blocks live there
+//   section 4..7   two steps on one slot, bits (a, b)  trans2[a << 12 | b << 11 | p]:  low 16 bits the
+//                  probability after both steps, high 16 bits the sum of both prices (at most 45 056)
+constexpr int HOLE_WARPS = WARPS_PER_CTA < 2 ? WARPS_PER_CTA : 2;
 struct CtaShared {
-	uint32_t trans[4096];  // see code_bit()
+	uint32_t trans[4096];
 	uint32_t recip[RECIP_ENTRIES];
 	uint4 lane_tab[32];    // match_lane_const() per lane
-	WarpShared warp[WARPS_PER_CTA];
+	WarpShared hole_warp[HOLE_WARPS];
+	unsigned char hole_pad[16384 - sizeof(uint32_t) * RECIP_ENTRIES - sizeof(uint4) * 32 - sizeof(WarpShared) * HOLE_WARPS];
+	uint32_t trans2[8192];
+	WarpShared rest_warp[WARPS_PER_CTA > 2 ? WARPS_PER_CTA - 2 : 1];
 };
 static_assert(sizeof(WarpShared) % 16 == 0, "per-warp shared block must keep the record 16-byte aligned");
-static_assert(offsetof(CtaShared, warp) % 16 == 0, "record alignment");
+static_assert(offsetof(CtaShared, hole_warp) % 16 == 0 && offsetof(CtaShared, rest_warp) % 16 == 0, "record alignment");
+static_assert(offsetof(CtaShared, trans) == 0 && offsetof(CtaShared, trans2) == 32768, "table sections");
+static_assert(sizeof(CtaShared) <= 232448, "one CTA must fit the 227 KB of shared memory");
+
+__device__ __forceinline__ WarpShared* warp_block(CtaShared* sh, int warp)
+{
+	return warp < HOLE_WARPS ? &sh->hole_warp[warp] : &sh->rest_warp[warp - HOLE_WARPS];
+}
 
 struct Tables {
-	const uint32_t* trans;  // [4096] adapted probability | price << 16 (price: reference generate_table.py:7-9)
-	const uint32_t* recip;  // [RECIP_ENTRIES]
+	const uint32_t* trans;   // [4096] adapted probability | price << 16 (price: reference generate_table.py:7-9)
+	const uint32_t* trans2;  // [8192] two steps on one slot
+	const uint32_t* recip;   // [RECIP_ENTRIES]
 };
 
 __device__ __forceinline__ void cta_tables_load(CtaShared* sh, const Tables& t)
 {
 	for (int i = threadIdx.x; i < 4096; i += blockDim.x) sh->trans[i] = t.trans[i];
+	for (int i = threadIdx.x; i < 8192; i += blockDim.x) sh->trans2[i] = t.trans2[i];
 	for (int i = threadIdx.x; i < (int)RECIP_ENTRIES; i += blockDim.x) sh->recip[i] = t.recip[i];
 	if (threadIdx.x < 32) {
 		const LaneConst c = match_lane_const((int)threadIdx.x);
 		sh->lane_tab[threadIdx.x] = make_uint4(c.shb, c.mask2, c.base, c.sel);
 	}
-	if ((threadIdx.x & 31) == 0) mbar_init(&sh->warp[threadIdx.x >> 5].bar, 1);
+	if ((threadIdx.x & 31) == 0) mbar_init(&warp_block(sh, threadIdx.x >> 5)->bar, 1);
 	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	__syncthreads();
 }
@@ -169,7 +190,7 @@ struct WalkEnv {
 	uint32_t trans_addr;  // shared address of trans[]
 	uint32_t lane_tab_addr;  // shared address of this lane's match_lane_const() entry
 	uint32_t ev_addr;        // shared address of the warp's literal-event mirror
-	uint32_t ev_row_addr;    // ... of this lane's row in it (lanes 0..8)
+	uint32_t ev_pair_addr;   // ... of this lane's half row in it (pair steps: lanes 0..8 first, 9..17 second literal)
 	uint32_t stage_addr;     // shared address of the next window's staging area
 	// literal fast path (see the slot map in mg_device.cuh): the lane's slot for data byte b is
 	//   lit_addr + 2 * (((b >> lit_sh) & lowmask) | (b & topmask))  (+ 2 * ctx on lane 0)
@@ -206,7 +227,10 @@ __device__ __forceinline__ WalkEnv make_env(int lane, WarpShared* ws, const CtaS
 	e.trans_addr = e.trans.a;
 	e.lane_tab_addr = cta_base + (uint32_t)offsetof(CtaShared, lane_tab) + 16u * (uint32_t)lane;
 	e.ev_addr = warp_base + (uint32_t)offsetof(WarpShared, fs) + (uint32_t)offsetof(FindScratch, len_price);
-	e.ev_row_addr = e.ev_addr + 4u * EVENT_ROW_WORDS * (uint32_t)(lane < (int)EVENT_LANES ? lane : 0);
+	{
+		const uint32_t pl = lane < 2 * (int)EVENT_LANES ? (uint32_t)lane : 0u;
+		e.ev_pair_addr = e.ev_addr + 4u * EVENT_ROW_WORDS * (pl % EVENT_LANES) + 4u * EVENT_PAIR_COLUMNS * (pl / EVENT_LANES);
+	}
 	e.stage_addr = e.ev_addr + STAGE_OFFSET;
 	const bool tree = lane >= 1 && lane <= 8;
 	const uint32_t depth = tree ? (uint32_t)lane - 1 : 0;
@@ -227,31 +251,48 @@ __device__ __forceinline__ WalkEnv make_env(int lane, WarpShared* ws, const CtaS
 	// threadIdx inside the literal loop (14 instructions per four literals) instead of keeping
 	// them in registers.
 	asm volatile("" : "+r"(e.lit_addr), "+r"(e.lit_sh), "+r"(e.bit_shl), "+r"(e.lowmask), "+r"(e.topmask), "+r"(e.bitmask),
-	             "+r"(e.ctxmask), "+r"(e.ev_row_addr));
+	             "+r"(e.ctxmask), "+r"(e.ev_pair_addr));
 	return e;
 }
 
-// Literal events of the current window.  Lane i prices nothing here: it turns ITS data byte into the
-// nine (slot address, bit) pairs the nine literal lanes will need at window position i and stores
-// them transposed, so the literal loop costs each lane one 16-byte load per four literals instead
-// of five ALU instructions per literal (the ALU pipe issues one warp instruction every two cycles
-// and was the limiter).  Event = shared address of the probability | bit << 31: `ev >> 18` is then
-// the byte offset of the table half for that bit (bit << 13), `ev & 0x3ffff` the address.
-// Plain literals only (automaton state 0; src/lzma_packet_encoder.c:106-121): the first three
-// literals after a match add the state to the is_match slot themselves.
+// Literal events of the current window, for PAIR steps: two consecutive plain literals (window positions 2g and
+// 2g+1) priced by one warp instruction each, the first on lanes 0..8, the second on lanes 9..17 (slot classes as
+// in a single step: is_match, then one lane per tree depth).  Lane i prices nothing here: it turns ITS data
+// byte into the nine events the literal at window position i needs and stores them transposed - row = slot
+// class, first-literal events in columns 0..15, second-literal events in columns 16..31 - so that the run loop
+// costs each lane one 16-byte load per four pairs.
+//   event = shared address of the probability | table section << 29   (sections: CtaShared)
+// When both literals of a pair touch the SAME slot (always for is_match and the tree root, whenever their bit
+// prefixes agree deeper down) the second literal's lane applies both steps with one load from the two-step
+// table (section 4 | first bit << 1 | second bit), and the first literal's lane is pointed at the spare slot
+// (probability 0, whose bit-0 entry is the zero-price fixed point): per-slot order is the reference's, nothing is
+// touched twice in a step.  Plain literals only (automaton state 0; src/lzma_packet_encoder.c:106-121).
 __device__ __forceinline__ void window_events(const WalkEnv& e, Window& w)
 {
 	__syncwarp();
 	const uint32_t b = (w.meta >> 16) & 0xffu;
-	const uint32_t out = e.ev_addr + 4u * (uint32_t)e.lane;
+	const uint32_t other = __shfl_xor_sync(FULL, b, 1);  // the pair's other literal
+	const uint32_t second = (uint32_t)e.lane & 1u;
+	const uint32_t x = b ^ other;
+	const uint32_t out = e.ev_addr + 4u * (((uint32_t)e.lane >> 1) + EVENT_PAIR_COLUMNS * second);
+	const uint32_t spare = e.probs.a + 2 * S_DUMMY;
+	// same slot as the pair's other literal at tree depth d  <=>  the first d bits agree
+	auto event = [&](uint32_t slot, uint32_t depth_bits, uint32_t bit_pos) -> uint32_t {
+		const bool same = (x >> (8 - depth_bits)) == 0;
+		const uint32_t own = (b >> bit_pos) & 1u, first = (other >> bit_pos) & 1u;
+		uint32_t ev = (e.probs.a + 2 * slot) | (own << 29);
+		if (same) ev = second ? (ev | 0x80000000u | (first << 30)) : spare;
+		return ev;
+	};
+	// is_match[0]: both bits 0, always the same slot
+	sts_u32(out + 0 * 4 * EVENT_ROW_WORDS, second ? ((e.probs.a + 2 * S_ISMATCH) | 0x80000000u) : spare);
+	sts_u32(out + 1 * 4 * EVENT_ROW_WORDS, event(S_LIT01, 0, 7));
+	sts_u32(out + 2 * 4 * EVENT_ROW_WORDS, event(S_LIT01 + 4 + (b >> 7), 1, 6));
 	const uint32_t row = S_LIT + (b >> 6) * 64;
-	sts_u32(out + 0 * 4 * EVENT_ROW_WORDS, e.probs.a + 2 * S_ISMATCH);
-	sts_u32(out + 1 * 4 * EVENT_ROW_WORDS, (e.probs.a + 2 * S_LIT01) | ((b >> 7) << 31));
-	sts_u32(out + 2 * 4 * EVENT_ROW_WORDS, (e.probs.a + 2 * (S_LIT01 + 4 + (b >> 7))) | (((b >> 6) & 1u) << 31));
 #pragma unroll
 	for (uint32_t d = 2; d < 8; d++) {
 		const uint32_t slot = row + ((1u << (d - 2)) | ((b >> (8 - d)) & ((1u << (d - 2)) - 1u)));
-		sts_u32(out + (d + 1) * 4 * EVENT_ROW_WORDS, (e.probs.a + 2 * slot) | (((b >> (7 - d)) & 1u) << 31));
+		sts_u32(out + (d + 1) * 4 * EVENT_ROW_WORDS, event(slot, d, 7 - d));
 	}
 	w.ev_base = (w.ev_base & ~31u) == w.base ? (w.ev_base | 1u) : (w.base | 1u);
 	__syncwarp();
@@ -384,8 +425,9 @@ __device__ __forceinline__ void walker_apply(const WalkEnv& e, Walker& k, Model&
 		e.reps.set(1, m.rep1);
 		e.reps.set(2, m.rep2);
 		e.reps.set(3, m.rep3);
-		__syncwarp();  // lanes are not guaranteed to run in lockstep: order these stores before later reads
 	}
+	__syncwarp();  // lanes are not guaranteed to run in lockstep: order these stores before later reads (pair steps
+	               // reach a slot from another lane than the one that wrote it here)
 	if (type != T_LITERAL) k.mb = MB_UNKNOWN;
 }
 
@@ -505,72 +547,73 @@ __device__ __forceinline__ uint32_t walk(const uint32_t MODE, const WalkEnv& e, 
 			const uint32_t meta = window_meta(k.w, k.pos);
 			if (MODE != WALK_REPAIR_HEAD && (meta & 0xffffu) == META_LITERAL) {
 				const uint32_t ctx = k.ctx;
-				if (ctx < 7) {
-					// ---- run of plain literals: every lane follows its own slot class through the
-					// whole run (lane 0 is_match, lanes 1..8 one tree depth, the other lanes wait);
-					// classes never share a slot, so no cross-lane traffic is needed per packet ---------
-					const uint32_t idx = k.pos - k.w.base;
+				const uint32_t idx = k.pos - k.w.base;
+				if (ctx == 0 && (idx & 1u) == 0 && k.w.pairs) {
+					// ---- run of plain literals, two per step: lanes 0..8 price the literal at the even window
+					// position, lanes 9..17 the one after it, each lane on its slot class (is_match, one tree
+					// depth each); a slot both literals touch is stepped twice by the second literal's lane
+					// through the two-step table (see window_events) -----------------------------------------
 					uint32_t run = (uint32_t)__ffs((int)~(k.w.litmask >> idx)) - 1u;
 					run = run < limit - k.pos ? run : limit - k.pos;
-					if ((k.w.ev_base | 2u) != (k.w.base | 3u)) window_events(e, k.w);
-					uint32_t cj = ctx;
-					// Lanes 9..31 have no slot class of their own: they sit the whole run out (one
-					// divergence per run, no shared-memory traffic from them).
-					if (e.lit_active) {
-						uint32_t ea = e.ev_row_addr + 4u * idx;
-						const uint32_t eend = ea + 4u * run;
-#define MG_LITERAL_STEP(ev, extra)                                                          \
-	do {                                                                                      \
-		const uint32_t ev_ = (ev);                                                            \
-		const uint32_t pa_ = (ev_ & 0x3ffffu) + (extra);                                      \
-		const uint32_t tr_ = lds_u32(e.trans_addr + (lds_u16(pa_) << 2) + (ev_ >> 18));       \
-		sts_u16(pa_, tr_);                                                                    \
-		k.t.acc += tr_ >> 16;                                                                 \
+					const uint32_t pairs = run >> 1;
+					if (pairs != 0) {
+						if ((k.w.ev_base | 2u) != (k.w.base | 3u)) window_events(e, k.w);
+						// Lanes 18..31 have no slot class: they sit the run out (one divergence per run).
+						if (e.lane < 2 * (int)EVENT_LANES) {
+							uint32_t ea = e.ev_pair_addr + 2u * idx;
+							const uint32_t eend = ea + 4u * pairs;
+#define MG_PAIR_STEP(ev)                                                                               \
+	do {                                                                                                 \
+		const uint32_t ev_ = (ev);                                                                       \
+		const uint32_t pa_ = ev_ & 0x3ffffu;                                                             \
+		const uint32_t tr_ = lds_u32(e.trans_addr + ((ev_ >> 16) & 0xE000u) + (lds_u16(pa_) << 2));      \
+		sts_u16(pa_, tr_);                                                                               \
+		k.t.acc += tr_ >> 16;                                                                            \
+		__syncwarp(PAIR_LANES); /* the next pair may reach this slot from the other half's lane */      \
 	} while (0)
-						// head: the automaton reaches state 0 after at most three literals
-						// (lzma_state.c:34-40); carry on one by one up to a 16-byte boundary of the row
-						while (ea != eend && (cj != 0 || (ea & 15u) != 0)) {
-							MG_LITERAL_STEP(lds_u32(ea), 2u * (cj & e.ctxmask));
-							ea += 4;
-							cj = (cj > 3 ? cj : 3) - 3;
+							while (ea != eend && (ea & 15u) != 0) {
+								MG_PAIR_STEP(lds_u32(ea));
+								ea += 4;
+							}
+							// body: the events of four pairs per shared-memory load
+							for (uint32_t groups = (eend - ea) >> 4; groups != 0; groups--) {
+								const uint4 v = lds_v4(ea);
+								MG_PAIR_STEP(v.x);
+								MG_PAIR_STEP(v.y);
+								MG_PAIR_STEP(v.z);
+								MG_PAIR_STEP(v.w);
+								ea += 16;
+							}
+							while (ea != eend) {
+								MG_PAIR_STEP(lds_u32(ea));
+								ea += 4;
+							}
+#undef MG_PAIR_STEP
 						}
-						// body: the events of four literals per shared-memory load
-						for (uint32_t groups = (eend - ea) >> 4; groups != 0; groups--) {
-							const uint4 v = lds_v4(ea);
-							MG_LITERAL_STEP(v.x, 0u);
-							MG_LITERAL_STEP(v.y, 0u);
-							MG_LITERAL_STEP(v.z, 0u);
-							MG_LITERAL_STEP(v.w, 0u);
-							ea += 16;
-						}
-						while (ea != eend) {
-							MG_LITERAL_STEP(lds_u32(ea), 0u);
-							ea += 4;
-						}
-#undef MG_LITERAL_STEP
+						__syncwarp();
+						k.pos += 2u * pairs;
+						continue;
 					}
-					__syncwarp();
-					cj = ctx;
-					for (uint32_t i = 0; i < run && cj != 0; i++) cj = (cj > 3 ? cj : 3) - 3;
-					k.ctx = cj;
-					k.pos += run;
-					continue;
 				}
-				// ---- one matched literal (lzma_packet_encoder.c:123-130): the tree follows the match
-				// byte for as long as the prefixes agree ------------------------------------------------
+				// ---- one literal: plain (slot classes on lanes 0..8, the lane's slot computed from the data
+				// byte) or matched (lzma_packet_encoder.c:123-130: the tree follows the match byte for as long
+				// as the prefixes agree) -----------------------------------------------------------------
 				const uint32_t byte = (meta >> 16) & 0xff;
-				const uint32_t mb = walker_mb(e, k);
-				// variant stride of this lane's slot class: depth 0 -> 1, depth 1 -> 2, deeper -> 256
-				const uint32_t vstride = e.lane == 1 ? 1u : e.lane == 2 ? 2u : e.topmask ? 256u : 0u;
 				uint32_t off = (((byte >> e.lit_sh) & e.lowmask) | (byte & e.topmask)) + (ctx & e.ctxmask);
-				if ((mb >> e.lit_sh) == (byte >> e.lit_sh)) off += (1u + ((mb >> (e.lit_sh - 1)) & 1u)) * vstride;
-				k.ctx = ctx < 10 ? ctx - 3 : ctx - 6;
+				if (ctx >= 7) {
+					const uint32_t mb = walker_mb(e, k);
+					// variant stride of this lane's slot class: depth 0 -> 1, depth 1 -> 2, deeper -> 256
+					const uint32_t vstride = e.lane == 1 ? 1u : e.lane == 2 ? 2u : e.topmask ? 256u : 0u;
+					if ((mb >> e.lit_sh) == (byte >> e.lit_sh)) off += (1u + ((mb >> (e.lit_sh - 1)) & 1u)) * vstride;
+				}
+				k.ctx = ctx < 4 ? 0u : ctx < 10 ? ctx - 3 : ctx - 6;
 				const uint32_t addr = e.lit_addr + 2 * off;
 				if (e.lit_active) {
 					const uint32_t tr = lds_u32(e.trans_addr + ((lds_u16(addr) | ((byte << e.bit_shl) & e.bitmask)) << 2));
 					sts_u16(addr, tr);
 					k.t.acc += tr >> 16;
 				}
+				__syncwarp();  // pair steps reach the same slots from other lanes
 				k.pos++;
 				continue;
 			}
@@ -698,7 +741,7 @@ __global__ void __launch_bounds__(CTA_THREADS) score_kernel(ScoreArgs a)
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const uint32_t s = blockIdx.x * WARPS_PER_CTA + warp;
 	if (s >= a.nslabs) return;
-	WarpShared* ws = &sh->warp[warp];
+	WarpShared* ws = warp_block(sh, warp);
 	const WalkEnv e = make_env(lane, ws, sh, a.slabs + (size_t)s * a.n, a.data, a.n);
 	Walker k;
 	walker_init(e, k);
@@ -760,7 +803,7 @@ __global__ void __launch_bounds__(CTA_THREADS) topk_kernel(TopkArgs a)
 	CtaShared* sh = reinterpret_cast<CtaShared*>(smem_raw);
 	cta_tables_load(sh, a.tables);
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	WarpShared* ws = &sh->warp[warp];
+	WarpShared* ws = warp_block(sh, warp);
 	const WalkEnv e = make_env(lane, ws, sh, a.slab, a.data, a.n);
 	uint32_t parity = 0;
 	unsigned long long cand = 0;
@@ -864,7 +907,7 @@ __global__ void __launch_bounds__(CTA_THREADS, MG_ANNEAL_MIN_CTAS) anneal_kernel
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	if (blockIdx.x * WARPS_PER_CTA + warp >= a.chains) return;
 	const uint32_t c = a.chain_first + blockIdx.x * WARPS_PER_CTA + warp;
-	WarpShared* ws = &sh->warp[warp];
+	WarpShared* ws = warp_block(sh, warp);
 	const uint32_t n = a.n, nck = a.nslots - 1;
 	const uint32_t reg_lo = a.regions ? a.regions[2 * c] : 0u, reg_hi = a.regions ? a.regions[2 * c + 1] : 0u;
 	uint64_t* slab = a.slabs + (size_t)c * n;
@@ -1440,6 +1483,9 @@ __device__ __forceinline__ void st_release_u32(uint32_t* p, uint32_t v)
 // event word of a modelled bit coded at probability p (of a zero): q | bit << 15
 __device__ __forceinline__ uint32_t enc_event(uint32_t p, uint32_t bit) { return (bit ? 2048u - p : p) | (bit << 15); }
 
+// The producer publishes `head` (a fence + a store) once per ENC_PUBLISH events, not per packet.
+constexpr uint32_t ENC_PUBLISH = 256;
+
 __device__ __forceinline__ void encode_produce(EncodeShared* sh, const EncodeArgs& a, int lane)
 {
 	Model m;
@@ -1448,38 +1494,54 @@ __device__ __forceinline__ void encode_produce(EncodeShared* sh, const EncodeArg
 	Window w;
 	w.base = WINDOW_NONE;
 	w.pf_base = WINDOW_NONE;
-	uint32_t head = 0, tail_seen = 0, err = 0;
+	uint32_t head = 0, published = 0, tail_seen = 0, err = 0;
 	const uint32_t ring = smem_u32(sh->ring);
 	const uint32_t stage = smem_u32(sh->stage);
-	// literal lanes: lane 0 is_match, lanes 1..8 tree depth 0..7
-	const uint32_t depth = lane >= 1 && lane <= 8 ? (uint32_t)lane - 1 : 0;
+	// literal lanes: lane 0 is_match, lanes 1..8 tree depth 0..7; the lane's slot for byte b is
+	//   first + (((b >> sh) & lowmask) | (b & topmask))   (slot map in mg_device.cuh)
+	const bool tree = lane >= 1 && lane <= 8;
+	const uint32_t depth = tree ? (uint32_t)lane - 1 : 0;
+	const uint32_t lit_first = lane == 0 ? S_ISMATCH : lane == 1 ? S_LIT01 : lane == 2 ? S_LIT01 + 4 : tree ? S_LIT + (1u << (depth - 2)) : S_DUMMY;
+	const uint32_t lit_sh = tree ? 8u - depth : 8u;
+	const uint32_t lowmask = !tree || depth == 0 ? 0u : depth == 1 ? 1u : (1u << (depth - 2)) - 1u;
+	const uint32_t topmask = tree && depth >= 2 ? 0xC0u : 0u;
 	while (m.pos < a.n) {
-		// room for the largest packet (28 events)?
-		while (head + 28 - tail_seen > ENC_RING) {
+		// room for a whole window of literals (32 x 9 events; the largest other packet appends 28)?
+		while (head + 288 - tail_seen > ENC_RING) {
+			if (published != head) {
+				__syncwarp();
+				if (lane == 0) st_release_u32(&sh->head, head);
+				published = head;
+			}
 			tail_seen = ld_acquire_u32(&sh->tail);
-			if (head + 28 - tail_seen > ENC_RING) __nanosleep(64);
+			if (head + 288 - tail_seen > ENC_RING) __nanosleep(64);
 		}
 		window_seek(lane, w, a.slab, a.data, a.n, m.pos, stage);
 		const uint32_t meta = window_meta(w, m.pos);
-		uint32_t count;
 		if ((meta & 0xffffu) == META_LITERAL && m.ctx < 7) {
-			// plain literal (src/lzma_packet_encoder.c:106-121)
-			const uint32_t byte = (meta >> 16) & 0xff;
-			uint32_t slot, bit;
-			lit_event(depth, byte, false, 0, slot, bit);
-			if (lane == 0) {
-				slot = S_ISMATCH + m.ctx;
-				bit = 0;
+			// ---- run of plain literals (src/lzma_packet_encoder.c:106-121): every lane follows its own slot
+			// class through the run, nine events per literal straight into the ring -----------------------
+			const uint32_t idx = m.pos - w.base;
+			uint32_t run = (uint32_t)__ffs((int)~(w.litmask >> idx)) - 1u;
+			run = run < a.n - m.pos ? run : a.n - m.pos;
+			uint32_t cj = m.ctx;
+			uint32_t at = head + (uint32_t)lane;
+			for (uint32_t i = 0; i < run; i++) {
+				const uint32_t b = (__shfl_sync(FULL, w.meta, (int)(idx + i)) >> 16) & 0xffu;
+				if (lane <= 8) {
+					const uint32_t slot = lit_first + (((b >> lit_sh) & lowmask) | (b & topmask)) + (lane == 0 ? cj : 0u);
+					const uint32_t bit = tree ? (b >> (7 - depth)) & 1u : 0u;
+					const uint32_t p = probs.get(slot);
+					sts_u32(ring + 4u * (at & (ENC_RING - 1)), enc_event(p, bit));
+					probs.set(slot, bit ? p - (p >> 5) : p + ((2048u - p) >> 5));
+				}
+				at += 9;
+				cj = cj < 4 ? 0u : cj - 3;
 			}
-			if (lane <= 8) {
-				const uint32_t p = probs.get(slot);
-				sts_u32(ring + 4u * ((head + (uint32_t)lane) & (ENC_RING - 1)), enc_event(p, bit));
-				probs.set(slot, bit ? p - (p >> 5) : p + ((2048u - p) >> 5));
-			}
-			count = 9;
-			m.ctx = m.ctx < 4 ? 0 : m.ctx - 3;
-			m.pos += 1;
-			m.pidx += 1;
+			m.ctx = cj;
+			head += 9 * run;
+			m.pos += run;
+			m.pidx += run;
 		} else {
 			const uint32_t type = meta_type(meta), len = meta_len(meta), dist = window_dist(w, m.pos);
 			const uint32_t byte = meta_byte(meta) & 0xff;
@@ -1507,24 +1569,69 @@ __device__ __forceinline__ void encode_produce(EncodeShared* sh, const EncodeArg
 			if (lane == 0 && has_direct)
 				sts_u32(ring + 4u * ((head + before_direct) & (ENC_RING - 1)),
 				        ENC_DIRECT | (dp.direct << 26) | ((dist & ((1u << dp.nlow) - 1u)) >> 4));
-			count = __popc(mask) + has_direct;
+			head += __popc(mask) + has_direct;
 			model_advance(m, type, len, dist);
 		}
-		head += count;
-		__syncwarp();  // every lane's events are in the ring before lane 0 publishes them
-		if (lane == 0) st_release_u32(&sh->head, head);
+		__syncwarp();  // every lane's events are in the ring (and its probabilities stored) before anything else
+		if (head - published >= ENC_PUBLISH) {
+			if (lane == 0) st_release_u32(&sh->head, head);
+			published = head;
+		}
 	}
 	asm volatile("cp.async.wait_group 0;" ::: "memory");
 	__syncwarp();
 	if (lane == 0) {
 		sh->err = err;
+		st_release_u32(&sh->head, head);
 		st_release_u32(&sh->done, err ? 2u : 1u);
+	}
+}
+
+// One modelled bit (src/range_encoder.c:47-64) in the form the consumer's chain wants.  With bound = (range >> 11) * p:
+//   bit 0: range' = bound,         low unchanged      = (range >> 11) * q                     (q = p)
+//   bit 1: range' = range - bound, low += bound       = (range >> 11) * q + (range & 2047)    (q = 2048 - p)
+// The state is kept as hi = range >> 11 and the kept low bits of the NEXT event, both selected from the two
+// normalisation outcomes in parallel with the test, so that the dependent chain per event is multiply-add ->
+// select -> multiply-add.  p stays within [31, 2017] (src/probability_model.c:5-15): one shift always suffices.
+struct RangeChain {
+	uint32_t range;  // the reference's range (normalised)
+	uint32_t hi;     // range >> 11
+	uint32_t lk;     // range & (the coming event codes a 1 ? 2047 : 0); only valid between rc_event calls that pass keep_next
+};
+
+__device__ __forceinline__ uint32_t enc_keep(uint32_t e) { return (e >> 15) ? 2047u : 0u; }
+
+// keep_next = enc_keep(the event after e) when it is known (then ch.lk stays valid), anything otherwise
+__device__ __forceinline__ void rc_event(RangeCoder& rc, RangeChain& ch, uint32_t e, uint32_t keep_next)
+{
+	const uint32_t q = e & 0x7fffu;
+	const uint32_t next = ch.hi * q + ch.lk;
+	if (e >> 15) rc.low += ch.range - next;
+	const bool shift = (next & 0xFF000000u) == 0;
+	ch.hi = shift ? next >> 3 : next >> 11;
+	ch.lk = shift ? ((next & 7u) << 8) & keep_next : next & keep_next;
+	ch.range = shift ? next << 8 : next;
+	if (shift) rc_shift_low(rc);
+}
+
+// any event, nothing known about its neighbours
+__device__ __forceinline__ void rc_any(RangeCoder& rc, RangeChain& ch, uint32_t e)
+{
+	if (e & ENC_DIRECT) {
+		rc.range = ch.range;
+		rc_direct(rc, e & 0x3ffffffu, (e >> 26) & 31u);
+		ch.range = rc.range;
+		ch.hi = rc.range >> 11;
+	} else {
+		ch.lk = ch.range & enc_keep(e);
+		rc_event(rc, ch, e, 0);
 	}
 }
 
 __device__ __forceinline__ void encode_consume(EncodeShared* sh, const EncodeArgs& a)
 {
 	RangeCoder rc = {0, 0xFFFFFFFFu, 0, 1, a.out, a.cap, 0};
+	RangeChain ch = {0xFFFFFFFFu, 0xFFFFFFFFu >> 11, 0};
 	uint32_t tail = 0;
 	const uint32_t ring = smem_u32(sh->ring);
 	for (;;) {
@@ -1539,26 +1646,34 @@ __device__ __forceinline__ void encode_consume(EncodeShared* sh, const EncodeArg
 		}
 		// a bounded batch, so that the producer sees the ring drain while a long backlog is coded
 		if (head - tail > ENC_RING / 4) head = tail + ENC_RING / 4;
-		while (tail != head) {
-			const uint32_t e = lds_u32(ring + 4u * (tail & (ENC_RING - 1)));
+		while (tail != head && (tail & 3u) != 0) {
+			rc_any(rc, ch, lds_u32(ring + 4u * (tail & (ENC_RING - 1))));
 			tail++;
-			if (e & ENC_DIRECT) {
-				rc_direct(rc, e & 0x3ffffffu, (e >> 26) & 31u);
-				continue;
+		}
+		// groups of four events per 16-byte load, the next group in flight while this one is coded
+		if (head - tail >= 4) {
+			uint4 v = lds_v4(ring + 4u * (tail & (ENC_RING - 1)));
+			while (head - tail >= 4) {
+				const uint4 cur = v;
+				v = lds_v4(ring + 4u * ((tail + 4) & (ENC_RING - 1)));  // may run past head: never used then
+				tail += 4;
+				if ((cur.x | cur.y | cur.z | cur.w) & ENC_DIRECT) {
+					rc_any(rc, ch, cur.x);
+					rc_any(rc, ch, cur.y);
+					rc_any(rc, ch, cur.z);
+					rc_any(rc, ch, cur.w);
+				} else {
+					ch.lk = ch.range & enc_keep(cur.x);
+					rc_event(rc, ch, cur.x, enc_keep(cur.y));
+					rc_event(rc, ch, cur.y, enc_keep(cur.z));
+					rc_event(rc, ch, cur.z, enc_keep(cur.w));
+					rc_event(rc, ch, cur.w, 0);
+				}
 			}
-			// src/range_encoder.c:47-64 with bound = (range >> 11) * p:
-			//   bit 0: range' = bound                     = (range >> 11) * q              (q = p)
-			//   bit 1: range' = range - bound, low += bound = (range >> 11) * q + (range & 2047)  (q = 2048 - p)
-			const uint32_t q = e & 0x7fffu, bit = e >> 15;
-			const uint32_t keep = bit ? 2047u : 0u;
-			const uint32_t next = (rc.range >> 11) * q + (rc.range & keep);
-			if (bit) rc.low += rc.range - next;
-			rc.range = next;
-			// p stays within [31, 2017] (src/probability_model.c:5-15), so one shift always suffices
-			if ((next & 0xFF000000u) == 0) {
-				rc.range = next << 8;
-				rc_shift_low(rc);
-			}
+		}
+		while (tail != head) {
+			rc_any(rc, ch, lds_u32(ring + 4u * (tail & (ENC_RING - 1))));
+			tail++;
 		}
 		st_release_u32(&sh->tail, tail);
 	}

@@ -131,7 +131,7 @@ def test_config2_score_64_slabs(mg, port, big, big_ctx, big_greedy, annealed):
     for i in range(0, len(slabs), 16):
         got += [int(x) for x in big_ctx.score_slabs(np.concatenate(slabs[i:i + 16]))]
     assert got == want
-    assert len(set(want)) >= 60  # the slabs really differ
+    assert len(set(want)) >= 40  # the slabs really differ (chains that accepted nothing keep their start slab)
 
 
 def test_exact_early_exit_fires_and_changes_nothing(mg, port, corpora):
