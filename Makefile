@@ -12,9 +12,9 @@ HOST := megalania_b200/host
 
 all: $(LIB) $(CLI)
 
-$(LIB): $(CSRC)/mg_api.cu $(CSRC)/mg_device.cuh $(CSRC)/mg_finder.cuh $(CSRC)/mg_kernels.cuh include/megalania_cuda.h
+$(LIB): $(CSRC)/mg_api.cu $(CSRC)/mg_device.cuh $(CSRC)/mg_finder.cuh $(CSRC)/mg_kernels.cuh $(CSRC)/mg_comm.inc include/megalania_cuda.h
 	mkdir -p $(OUT)
-	$(NVCC) -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 --shared -Xcompiler -fPIC -Xcompiler -fvisibility=hidden -o $@ $<
+	$(NVCC) -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 --shared -Xcompiler -fPIC -Xcompiler -fvisibility=hidden -ldl -o $@ $<
 
 $(CLI): $(HOST)/main.c $(HOST)/host_io.c $(LIB)
 	$(CC) -O2 -std=gnu11 -Wall -Wextra -Iinclude -o $@ $(HOST)/main.c $(HOST)/host_io.c -L$(OUT) -lmegalania_cuda -Wl,-rpath,'$$ORIGIN' -lm

@@ -283,6 +283,41 @@ MG_API int mg_anneal_oneshot(mg_ctx* ctx, const mg_anneal_params* params, const 
                       const LZMAPacket* init, LZMAPacket* best_slab_out, uint64_t* best_cost,
                       mg_anneal_stats* stats);
 
+/* ---- several GPUs: one context (and one host thread or process) per GPU -------------------- */
+
+/* The reference is one thread on one slab; its epochs only talk through `packets_best` (src/main.c:75-77,
+ * 89-92).  Here replicas are independent inside mg_anneal_run and meet between runs through NCCL over
+ * NVLink.  NCCL is bound at run time (libnccl.so.2): hosts that never call mg_comm_init do not need it. */
+#define MG_COMM_ID_BYTES 128
+/* ncclGetUniqueId: call on one rank, hand the 128 bytes to the others by any means (pipe, MPI, torchrun store). */
+MG_API int mg_comm_unique_id(void* id_out);
+/* Collective over all ranks: joins ctx's device to the communicator (ncclCommInitRank). */
+MG_API int mg_comm_init(mg_ctx* ctx, int rank, int nranks, const void* nccl_id);
+MG_API void mg_comm_destroy(mg_ctx* ctx); /* also done by mg_ctx_destroy */
+MG_API int mg_comm_rank(const mg_ctx* ctx);
+MG_API int mg_comm_size(const mg_ctx* ctx);
+/* Collective: best-slab broadcast.  One all-gather of a 40-byte summary per rank finds the rank holding the
+ * cheapest best slab (ties: lowest rank); that rank broadcasts the packed slab - with its model checkpoints when
+ * the best slab is the chain's current one, so that receivers install it by copy instead of re-pricing 1 MiB on
+ * one warp - and every other rank replaces its worst chain (highest current cost) with it, adopting the cost.
+ * Costs stay on the device; the host only reads nranks x 40 bytes.  winner_rank = -1: nobody has a best yet. */
+MG_API int mg_comm_exchange_best(mg_anneal* an, int* winner_rank, uint64_t* best_cost);
+/* Collective: one round of replica exchange (parallel tempering) over the replicas of ALL ranks.  temps: host
+ * array [chains] of this rank's temperatures, in and out.  One all-gather of (current cost, temperature) per
+ * replica; every rank computes the same swap decisions (mg_temper_decide) and only temperatures move. Works
+ * without a communicator too (one rank). */
+MG_API int mg_comm_temper_exchange(mg_anneal* an, float* temps, uint32_t round_index, uint64_t seed);
+/* The swap rule itself, host only (no device, no communicator): replicas adjacent on the temperature ladder -
+ * even pairs on even rounds, odd pairs on odd rounds - swap temperatures with the Metropolis probability
+ * min(1, exp((1/T_i - 1/T_j) (C_i - C_j))), decided by a counter-based generator keyed by (seed, round, pair). */
+MG_API int mg_temper_decide(const uint64_t* costs, const float* temps, size_t count, uint32_t round_index,
+                            uint64_t seed, float* out_temps);
+/* Collective: mg_anneal_merge_regions with the regions' owners spread over the ranks (owners[r] = MG_NO_OWNER
+ * for regions that live elsewhere): export + ncclAllReduce(sum) + import; every rank ends with the same slab. */
+MG_API int mg_comm_merge_regions(mg_anneal* an, uint32_t nregions, const uint32_t* bounds, const uint32_t* owners,
+                                 uint32_t dst_chain, uint64_t* cost_out);
+MG_API int mg_comm_stats(const mg_ctx* ctx, uint64_t* exchanges, uint64_t* installs_by_copy, uint64_t* installs_by_rescore);
+
 /* ---- debugging aid (used by the parity tests) ------------------------------------------- */
 
 /* Model after pricing slab[0..stop): probabilities in the reference's struct order

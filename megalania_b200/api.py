@@ -84,6 +84,8 @@ EXPORTS = [
     "mg_anneal_refresh_chain", "mg_anneal_oneshot", "mg_debug_model_after_prefix", "mg_anneal_export_slab",
     "mg_anneal_import_slab", "mg_anneal_merge_regions", "mg_anneal_broadcast_chain", "mg_find_topk_stats",
     "mg_anneal_merge_export", "mg_anneal_merge_import", "mg_debug_index", "mg_encode_stats", "mg_ctx_full_wave",
+    "mg_comm_unique_id", "mg_comm_init", "mg_comm_destroy", "mg_comm_rank", "mg_comm_size", "mg_comm_exchange_best",
+    "mg_comm_temper_exchange", "mg_temper_decide", "mg_comm_merge_regions", "mg_comm_stats",
 ]
 
 _lib = None
@@ -144,6 +146,17 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
                                     C.POINTER(u64), C.POINTER(AnnealStats)]
     L.mg_debug_model_after_prefix.argtypes = [vp, vp, sz, vp]
     L.mg_debug_index.argtypes = [vp, vp, vp]
+    L.mg_comm_unique_id.argtypes = [vp]
+    L.mg_comm_init.argtypes = [vp, i32, i32, vp]
+    L.mg_comm_destroy.argtypes = [vp]
+    L.mg_comm_destroy.restype = None
+    L.mg_comm_rank.argtypes = [vp]
+    L.mg_comm_size.argtypes = [vp]
+    L.mg_comm_exchange_best.argtypes = [vp, C.POINTER(i32), C.POINTER(u64)]
+    L.mg_comm_temper_exchange.argtypes = [vp, vp, u32, u64]
+    L.mg_temper_decide.argtypes = [vp, vp, sz, u32, u64, vp]
+    L.mg_comm_merge_regions.argtypes = [vp, u32, vp, vp, u32, C.POINTER(u64)]
+    L.mg_comm_stats.argtypes = [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]
     L.mg_encode_stats.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(u64)]
     _lib = L
     return L
@@ -271,6 +284,23 @@ class Context:
         _check(self._lib.mg_debug_model_after_prefix(self._h, _slab_ptr(slab, self.n), stop,
                                                      out.ctypes.data_as(C.c_void_p)))
         return out[0]
+
+    # ---- several GPUs (NCCL behind the C ABI) ----
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        buf = C.create_string_buffer(128)
+        _check(load_library().mg_comm_unique_id(buf))
+        return buf.raw
+
+    def comm_init(self, rank: int, nranks: int, unique_id: bytes) -> None:
+        if len(unique_id) != 128:
+            raise ValueError("an NCCL unique id is 128 bytes")
+        _check(self._lib.mg_comm_init(self._h, rank, nranks, C.c_char_p(unique_id)))
+
+    def comm_stats(self) -> dict:
+        a, b, c = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+        _check(self._lib.mg_comm_stats(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return {"exchanges": int(a.value), "installs_by_copy": int(b.value), "installs_by_rescore": int(c.value)}
 
     def full_wave(self) -> int:
         """Chains that fill the device exactly once (SMs x chains per SM)."""
@@ -405,11 +435,43 @@ class Annealer:
                                                 C.byref(cost)))
         return int(cost.value)
 
+    def comm_exchange_best(self):
+        """Collective: (winner rank or -1, global best cost); see mg_comm_exchange_best."""
+        w, c = C.c_int(-1), C.c_uint64(0)
+        _check(self._lib.mg_comm_exchange_best(self._h, C.byref(w), C.byref(c)))
+        return int(w.value), int(c.value)
+
+    def comm_temper_exchange(self, temps: np.ndarray, round_index: int, seed: int = 0) -> np.ndarray:
+        """Collective: one replica-exchange round over the replicas of all ranks; returns this rank's new temperatures."""
+        t = np.ascontiguousarray(temps, dtype=np.float32).copy()
+        if t.size != self.chains:
+            raise ValueError("one temperature per chain")
+        _check(self._lib.mg_comm_temper_exchange(self._h, t.ctypes.data_as(C.c_void_p), round_index, seed))
+        return t
+
+    def comm_merge_regions(self, bounds, owners, dst_chain: int = 0) -> int:
+        b = np.ascontiguousarray(bounds, dtype=np.uint32)
+        o = np.ascontiguousarray(owners, dtype=np.uint32)
+        cost = C.c_uint64(0)
+        _check(self._lib.mg_comm_merge_regions(self._h, o.size, b.ctypes.data_as(C.c_void_p), o.ctypes.data_as(C.c_void_p),
+                                               dst_chain, C.byref(cost)))
+        return int(cost.value)
+
     def broadcast_chain(self, src_chain: int) -> None:
         _check(self._lib.mg_anneal_broadcast_chain(self._h, src_chain))
 
     def refresh_chain(self, chain: int, adopt_cost: bool = True) -> None:
         _check(self._lib.mg_anneal_refresh_chain(self._h, chain, int(adopt_cost)))
+
+
+def temper_decide(costs, temps, round_index: int, seed: int = 0) -> np.ndarray:
+    """mg_temper_decide: the replica-exchange swap rule (host only, runs without a GPU)."""
+    c = np.ascontiguousarray(costs, dtype=np.uint64)
+    t = np.ascontiguousarray(temps, dtype=np.float32)
+    out = np.zeros_like(t)
+    _check(load_library().mg_temper_decide(c.ctypes.data_as(C.c_void_p), t.ctypes.data_as(C.c_void_p), c.size, round_index, seed,
+                                           out.ctypes.data_as(C.c_void_p)))
+    return out
 
 
 def anneal_oneshot(ctx: Context, *, chains: int, evals: int, init: np.ndarray | None = None, seed: int = 1673551,

@@ -19,12 +19,12 @@ LIB = os.path.join(OUT, "libmegalania_cuda.so")
 CLI = os.path.join(OUT, "megalania")
 
 CUDA_SOURCES = [os.path.join(PKG, "csrc", "mg_api.cu")]
-CUDA_DEPS = [os.path.join(PKG, "csrc", f) for f in ("mg_device.cuh", "mg_finder.cuh", "mg_kernels.cuh")] + [
+CUDA_DEPS = [os.path.join(PKG, "csrc", f) for f in ("mg_device.cuh", "mg_finder.cuh", "mg_kernels.cuh", "mg_comm.inc")] + [
     os.path.join(ROOT, "include", f) for f in ("megalania_cuda.h", "output_interface.h", "encoder_interface.h")]
 HOST_SOURCES = [os.path.join(PKG, "host", f) for f in ("main.c", "host_io.c")]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "--shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
+              "--shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-ldl"]
 
 
 def _nvcc() -> str:

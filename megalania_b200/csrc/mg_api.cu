@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <new>
 #include <vector>
 #include <unistd.h>
@@ -36,7 +37,10 @@ static int fail(int code, const char* fmt, ...)
 extern "C" MG_API const char* mg_last_error(void) { return g_err; }
 extern "C" MG_API uint32_t mg_version(void) { return (0u << 16) | 1u; }
 
+struct mg_comm_state;
+
 struct mg_ctx {
+	mg_comm_state* comm = nullptr;  // NCCL communicator + exchange buffers (mg_comm_init), see mg_comm.inc
 	int device = 0;
 	uint32_t n = 0;
 	cudaStream_t stream = nullptr;
@@ -218,6 +222,7 @@ extern "C" MG_API void mg_ctx_destroy(mg_ctx* ctx)
 {
 	if (!ctx) return;
 	cudaSetDevice(ctx->device);
+	mg_comm_destroy(ctx);
 	// chain populations hold pointers into the context: they go first (their handles die with it)
 	while (!ctx->annealers.empty()) mg_anneal_destroy(ctx->annealers.back());
 	if (ctx->stream) cudaStreamSynchronize(ctx->stream);
@@ -1315,3 +1320,5 @@ extern "C" MG_API int mg_anneal_oneshot(mg_ctx* ctx, const mg_anneal_params* par
 	mg_anneal_destroy(an);
 	return rc;
 }
+
+#include "mg_comm.inc"

@@ -77,3 +77,25 @@ def test_distributed_plan_gives_every_rank_its_own_regions():
             assert (owner_rank[mine] == rank).all()      # a rank only anneals regions it owns
             seen[np.unique(mine)] = True
         assert seen.all()                                 # every region is annealed by someone
+
+
+def test_c_temper_rule_matches_the_python_rule():
+    """mg_temper_decide (the swap rule the multi-GPU C host uses, no device needed) against
+    megalania_b200.tempering.exchange_temperatures on random ladders, both parities, ties included."""
+    import numpy as np
+    import megalania_b200 as mg
+    from megalania_b200 import api, tempering
+    mg.load_library()
+    rng = np.random.default_rng(5)
+    for trial in range(40):
+        count = int(rng.integers(1, 400))
+        temps = tempering.temperature_ladder(count, 10.0, 1e6)[rng.permutation(count)]
+        if trial % 5 == 0 and count > 3:
+            temps[1] = temps[0]          # equal temperatures: stable order decides
+            temps[2] = 0.0               # a frozen replica never swaps
+        costs = rng.integers(1_000_000, 9_000_000_000, count).astype(np.uint64)
+        for rnd in (trial, trial + 1):
+            want = tempering.exchange_temperatures(costs.astype(np.int64), temps, rnd, seed=trial * 7919)
+            got = api.temper_decide(costs, temps, rnd, seed=trial * 7919)
+            assert (got == want).all(), (trial, rnd)
+            assert sorted(got.tolist()) == sorted(temps.tolist())
