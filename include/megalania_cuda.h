@@ -72,6 +72,11 @@ MG_API const char* mg_last_error(void);
 /* Library/ABI version, (major << 16) | minor. */
 MG_API uint32_t mg_version(void);
 
+/* Device memory released by the library is kept (per device) for its next request of the same size, so that
+ * repeated one-shot calls do not pay cudaMalloc / cudaFree of ~90 GB each time; this hands it all back to the driver
+ * (the library also does so by itself when an allocation fails). */
+MG_API void mg_pool_trim(void);
+
 /* ---- context ------------------------------------------------------------------------- */
 
 /* Replaces lzma_state_init (src/lzma_state.c:16-27), packet_enumerator_new
@@ -316,6 +321,11 @@ MG_API int mg_temper_decide(const uint64_t* costs, const float* temps, size_t co
  * for regions that live elsewhere): export + ncclAllReduce(sum) + import; every rank ends with the same slab. */
 MG_API int mg_comm_merge_regions(mg_anneal* an, uint32_t nregions, const uint32_t* bounds, const uint32_t* owners,
                                  uint32_t dst_chain, uint64_t* cost_out);
+/* Collective: rank `root`'s chain src_chain (current slab, its checkpoints and cost) becomes chain dst_chain of every
+ * other rank, by copy.  src_chain is only read on root, dst_chain only on the others. */
+MG_API int mg_comm_broadcast_chain(mg_anneal* an, int root, uint32_t src_chain, uint32_t dst_chain);
+/* Collective: one host value per rank, out[r] = rank r's (out holds mg_comm_size entries). */
+MG_API int mg_comm_allgather_u64(mg_ctx* ctx, uint64_t value, uint64_t* out);
 MG_API int mg_comm_stats(const mg_ctx* ctx, uint64_t* exchanges, uint64_t* installs_by_copy, uint64_t* installs_by_rescore);
 
 /* ---- debugging aid (used by the parity tests) ------------------------------------------- */

@@ -85,7 +85,8 @@ EXPORTS = [
     "mg_anneal_import_slab", "mg_anneal_merge_regions", "mg_anneal_broadcast_chain", "mg_find_topk_stats",
     "mg_anneal_merge_export", "mg_anneal_merge_import", "mg_debug_index", "mg_encode_stats", "mg_ctx_full_wave",
     "mg_comm_unique_id", "mg_comm_init", "mg_comm_destroy", "mg_comm_rank", "mg_comm_size", "mg_comm_exchange_best",
-    "mg_comm_temper_exchange", "mg_temper_decide", "mg_comm_merge_regions", "mg_comm_stats",
+    "mg_comm_temper_exchange", "mg_temper_decide", "mg_comm_merge_regions", "mg_comm_stats", "mg_pool_trim",
+    "mg_comm_broadcast_chain", "mg_comm_allgather_u64",
 ]
 
 _lib = None
@@ -146,6 +147,7 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
                                     C.POINTER(u64), C.POINTER(AnnealStats)]
     L.mg_debug_model_after_prefix.argtypes = [vp, vp, sz, vp]
     L.mg_debug_index.argtypes = [vp, vp, vp]
+    L.mg_pool_trim.restype = None
     L.mg_comm_unique_id.argtypes = [vp]
     L.mg_comm_init.argtypes = [vp, i32, i32, vp]
     L.mg_comm_destroy.argtypes = [vp]
@@ -157,6 +159,8 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
     L.mg_temper_decide.argtypes = [vp, vp, sz, u32, u64, vp]
     L.mg_comm_merge_regions.argtypes = [vp, u32, vp, vp, u32, C.POINTER(u64)]
     L.mg_comm_stats.argtypes = [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]
+    L.mg_comm_broadcast_chain.argtypes = [vp, i32, u32, u32]
+    L.mg_comm_allgather_u64.argtypes = [vp, u64, vp]
     L.mg_encode_stats.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(u64)]
     _lib = L
     return L
@@ -296,6 +300,12 @@ class Context:
         if len(unique_id) != 128:
             raise ValueError("an NCCL unique id is 128 bytes")
         _check(self._lib.mg_comm_init(self._h, rank, nranks, C.c_char_p(unique_id)))
+
+    def comm_allgather(self, value: int) -> np.ndarray:
+        size = int(self._lib.mg_comm_size(self._h))
+        out = np.zeros(size, dtype=np.uint64)
+        _check(self._lib.mg_comm_allgather_u64(self._h, int(value), out.ctypes.data_as(C.c_void_p)))
+        return out
 
     def comm_stats(self) -> dict:
         a, b, c = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
@@ -440,6 +450,9 @@ class Annealer:
         w, c = C.c_int(-1), C.c_uint64(0)
         _check(self._lib.mg_comm_exchange_best(self._h, C.byref(w), C.byref(c)))
         return int(w.value), int(c.value)
+
+    def comm_broadcast_chain(self, root: int, src_chain: int, dst_chain: int) -> None:
+        _check(self._lib.mg_comm_broadcast_chain(self._h, root, src_chain, dst_chain))
 
     def comm_temper_exchange(self, temps: np.ndarray, round_index: int, seed: int = 0) -> np.ndarray:
         """Collective: one replica-exchange round over the replicas of all ranks; returns this rank's new temperatures."""

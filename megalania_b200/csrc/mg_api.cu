@@ -35,6 +35,93 @@ static int fail(int code, const char* fmt, ...)
 	} while (0)
 
 extern "C" MG_API const char* mg_last_error(void) { return g_err; }
+// ---- device memory pool -----------------------------------------------------------------------------------
+// A one-shot call (mg_ctx_create + mg_anneal_oneshot) allocates and frees ~90 GB of chain state; cudaMalloc and
+// cudaFree of that size cost 0.15 s per call, more than a tenth of a one-second annealing step.  Blocks released
+// by the library are kept per device and handed back to the next request of the same size; everything cached is
+// returned to the driver when an allocation fails, and by mg_pool_trim().
+#include <map>
+#include <mutex>
+#include <unordered_map>
+namespace {
+struct DevicePool {
+	std::mutex lock;
+	std::unordered_map<void*, std::pair<int, size_t>> live;       // pointer -> (device, bytes)
+	std::multimap<std::pair<int, size_t>, void*> cached;          // (device, bytes) -> pointer
+};
+DevicePool& pool()
+{
+	static DevicePool* p = new DevicePool;  // leaked on purpose: contexts may be destroyed from static destructors
+	return *p;
+}
+void pool_release_device(int device)
+{
+	DevicePool& P = pool();
+	for (auto it = P.cached.begin(); it != P.cached.end();) {
+		if (device < 0 || it->first.first == device) {
+			cudaFree(it->second);
+			it = P.cached.erase(it);
+		} else {
+			++it;
+		}
+	}
+}
+}  // namespace
+
+static cudaError_t pool_malloc_raw(void** out, size_t bytes)
+{
+	if (bytes == 0) bytes = 16;
+	int device = 0;
+	cudaError_t e = cudaGetDevice(&device);
+	if (e != cudaSuccess) return e;
+	DevicePool& P = pool();
+	std::lock_guard<std::mutex> g(P.lock);
+	auto hit = P.cached.find({device, bytes});
+	if (hit != P.cached.end()) {
+		*out = hit->second;
+		P.cached.erase(hit);
+	} else {
+		e = cudaMalloc(out, bytes);
+		if (e == cudaErrorMemoryAllocation) {
+			cudaGetLastError();
+			pool_release_device(device);
+			e = cudaMalloc(out, bytes);
+		}
+		if (e != cudaSuccess) return e;
+	}
+	P.live[*out] = {device, bytes};
+	return cudaSuccess;
+}
+template <class T> static cudaError_t pool_malloc(T** out, size_t bytes) { return pool_malloc_raw(reinterpret_cast<void**>(out), bytes); }
+
+static void pool_free(void* p)
+{
+	if (!p) return;
+	DevicePool& P = pool();
+	std::lock_guard<std::mutex> g(P.lock);
+	auto it = P.live.find(p);
+	if (it == P.live.end()) {
+		cudaFree(p);
+		return;
+	}
+	P.cached.insert({it->second, p});
+	P.live.erase(it);
+}
+
+extern "C" MG_API void mg_pool_trim(void)
+{
+	DevicePool& P = pool();
+	std::lock_guard<std::mutex> g(P.lock);
+	int device = 0;
+	cudaGetDevice(&device);
+	for (auto it = P.cached.begin(); it != P.cached.end();) {
+		cudaSetDevice(it->first.first);
+		pool_free(it->second);
+		it = P.cached.erase(it);
+	}
+	cudaSetDevice(device);
+}
+
 extern "C" MG_API uint32_t mg_version(void) { return (0u << 16) | 1u; }
 
 struct mg_comm_state;
@@ -62,13 +149,13 @@ struct mg_ctx {
 
 struct DevBuf {
 	void* p = nullptr;
-	~DevBuf() { if (p) cudaFree(p); }
+	~DevBuf() { if (p) pool_free(p); }
 	template <class T> T* as() { return static_cast<T*>(p); }
 };
 
 static int dev_alloc(DevBuf& b, size_t bytes)
 {
-	CU(cudaMalloc(&b.p, bytes ? bytes : 16));
+	CU(pool_malloc(&b.p, bytes ? bytes : 16));
 	return 0;
 }
 
@@ -98,8 +185,8 @@ static int set_smem_attrs()
 static int build_index(mg_ctx* ctx)
 {
 	const uint32_t n = ctx->n;
-	CU(cudaMalloc(&ctx->d_occ_start, sizeof(uint32_t) * (INDEX_KEYS + 1)));
-	CU(cudaMalloc(&ctx->d_occ, sizeof(uint32_t) * (size_t)(n ? n : 1)));
+	CU(pool_malloc(&ctx->d_occ_start, sizeof(uint32_t) * (INDEX_KEYS + 1)));
+	CU(pool_malloc(&ctx->d_occ, sizeof(uint32_t) * (size_t)(n ? n : 1)));
 	if (n < 2) {
 		CU(cudaMemsetAsync(ctx->d_occ_start, 0, sizeof(uint32_t) * (INDEX_KEYS + 1), ctx->stream));
 		return 0;
@@ -173,7 +260,7 @@ extern "C" MG_API int mg_ctx_create(const uint8_t* data, size_t n, LZMAPropertie
 		break;                                                                    \
 	}
 		CUB(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-		CUB(cudaMalloc(&ctx->d_data, n + 32));
+		CUB(pool_malloc(&ctx->d_data, n + 32));
 		CUB(cudaMemsetAsync(ctx->d_data + n, 0, 32, ctx->stream));
 		CUB(cudaMemcpyAsync(ctx->d_data, data, n, cudaMemcpyHostToDevice, ctx->stream));
 		// price table: reference generate_table.py:7-9, -int(log2(i/2048.)*2048); fused with the
@@ -197,9 +284,9 @@ extern "C" MG_API int mg_ctx_create(const uint8_t* data, size_t n, LZMAPropertie
 			}
 		std::vector<uint32_t> recip(RECIP_ENTRIES, 0);
 		for (uint32_t i = 1; i < RECIP_ENTRIES; i++) recip[i] = 0xffffffffu / i + 1u;
-		CUB(cudaMalloc(&ctx->d_trans, 4096 * sizeof(uint32_t)));
-		CUB(cudaMalloc(&ctx->d_trans2, 8192 * sizeof(uint32_t)));
-		CUB(cudaMalloc(&ctx->d_recip, RECIP_ENTRIES * sizeof(uint32_t)));
+		CUB(pool_malloc(&ctx->d_trans, 4096 * sizeof(uint32_t)));
+		CUB(pool_malloc(&ctx->d_trans2, 8192 * sizeof(uint32_t)));
+		CUB(pool_malloc(&ctx->d_recip, RECIP_ENTRIES * sizeof(uint32_t)));
 		CUB(cudaMemcpyAsync(ctx->d_trans, trans.data(), 4096 * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
 		CUB(cudaMemcpyAsync(ctx->d_trans2, trans2.data(), 8192 * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
 		CUB(cudaMemcpyAsync(ctx->d_recip, recip.data(), RECIP_ENTRIES * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
@@ -226,12 +313,12 @@ extern "C" MG_API void mg_ctx_destroy(mg_ctx* ctx)
 	// chain populations hold pointers into the context: they go first (their handles die with it)
 	while (!ctx->annealers.empty()) mg_anneal_destroy(ctx->annealers.back());
 	if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-	cudaFree(ctx->d_data);
-	cudaFree(ctx->d_occ_start);
-	cudaFree(ctx->d_occ);
-	cudaFree(ctx->d_trans);
-	cudaFree(ctx->d_trans2);
-	cudaFree(ctx->d_recip);
+	pool_free(ctx->d_data);
+	pool_free(ctx->d_occ_start);
+	pool_free(ctx->d_occ);
+	pool_free(ctx->d_trans);
+	pool_free(ctx->d_trans2);
+	pool_free(ctx->d_recip);
 	if (ctx->stream) cudaStreamDestroy(ctx->stream);
 	delete ctx;
 }
@@ -691,23 +778,23 @@ extern "C" MG_API void mg_anneal_destroy(mg_anneal* an)
 	}
 	cudaSetDevice(an->ctx->device);
 	cudaStreamSynchronize(an->ctx->stream);
-	cudaFree(an->d_regions);
-	cudaFree(an->d_slabs);
-	cudaFree(an->d_bests);
-	cudaFree(an->d_ck);
-	cudaFree(an->d_ck_meta);
-	cudaFree(an->d_ck_live);
-	cudaFree(an->d_logs);
-	cudaFree(an->d_journal);
-	cudaFree(an->d_state);
-	cudaFree(an->d_stats);
-	cudaFree(an->d_trace);
-	cudaFree(an->d_attempts);
-	cudaFree(an->d_temps);
-	cudaFree(an->d_cost);
-	cudaFree(an->d_count);
-	cudaFree(an->d_err);
-	cudaFree(an->d_bad);
+	pool_free(an->d_regions);
+	pool_free(an->d_slabs);
+	pool_free(an->d_bests);
+	pool_free(an->d_ck);
+	pool_free(an->d_ck_meta);
+	pool_free(an->d_ck_live);
+	pool_free(an->d_logs);
+	pool_free(an->d_journal);
+	pool_free(an->d_state);
+	pool_free(an->d_stats);
+	pool_free(an->d_trace);
+	pool_free(an->d_attempts);
+	pool_free(an->d_temps);
+	pool_free(an->d_cost);
+	pool_free(an->d_count);
+	pool_free(an->d_err);
+	pool_free(an->d_bad);
 	if (an->e0) cudaEventDestroy(an->e0);
 	if (an->e1) cudaEventDestroy(an->e1);
 	delete an;
@@ -733,7 +820,7 @@ extern "C" MG_API int mg_anneal_create(mg_ctx* ctx, const mg_anneal_params* para
 	int rc = 0;
 #define A(ptr, bytes)                                                                              \
 	if (!rc) {                                                                                     \
-		cudaError_t e_ = cudaMalloc((void**)&(ptr), (bytes));                                      \
+		cudaError_t e_ = pool_malloc(&(ptr), (bytes));                                      \
 		if (e_ != cudaSuccess) rc = fail(e_ == cudaErrorMemoryAllocation ? MG_ENOMEM : MG_ECUDA,  \
 		                                 "cudaMalloc(%zu bytes for %s): %s", (size_t)(bytes), #ptr, cudaGetErrorString(e_)); \
 	}
@@ -998,7 +1085,7 @@ extern "C" MG_API int mg_anneal_run(mg_anneal* an, const mg_anneal_run_params* r
 		for (uint32_t c = 0; c < C; c++)
 			if (run->regions[2 * c] >= run->regions[2 * c + 1] || run->regions[2 * c + 1] > ctx->n)
 				return fail(MG_EINVAL, "mg_anneal_run: chain %u has an empty or out-of-range region", c);
-		if (!an->d_regions) CU(cudaMalloc(&an->d_regions, (size_t)C * 8));
+		if (!an->d_regions) CU(pool_malloc(&an->d_regions, (size_t)C * 8));
 		CU(cudaMemcpyAsync(an->d_regions, run->regions, (size_t)C * 8, cudaMemcpyHostToDevice, ctx->stream));
 		a.regions = an->d_regions;
 	}
