@@ -17,7 +17,7 @@ $(LIB): $(CSRC)/mg_api.cu $(CSRC)/mg_device.cuh $(CSRC)/mg_finder.cuh $(CSRC)/mg
 	$(NVCC) -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 --shared -Xcompiler -fPIC -Xcompiler -fvisibility=hidden -ldl -o $@ $<
 
 $(CLI): $(HOST)/main.c $(HOST)/host_io.c $(LIB)
-	$(CC) -O2 -std=gnu11 -Wall -Wextra -Iinclude -o $@ $(HOST)/main.c $(HOST)/host_io.c -L$(OUT) -lmegalania_cuda -Wl,-rpath,'$$ORIGIN' -lm
+	$(CC) -O2 -std=gnu11 -Wall -Wextra -Iinclude -o $@ $(HOST)/main.c $(HOST)/host_io.c -L$(OUT) -lmegalania_cuda -Wl,-rpath,'$$ORIGIN' -lm -lpthread
 
 oracle:
 	$(MAKE) -C oracle

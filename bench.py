@@ -13,9 +13,17 @@ evaluations of ALL chains on ALL GPUs per second of device time (CUDA events on 
 launch stream, max over ranks).  `e2e` is the same metric through the one-shot host call with
 host buffers in and out (input upload, index build, chain allocation, best slab read-back).
 
-Under torchrun (N > 1) every rank owns its own chains (weak scaling, no collective on the data
-path); after each step the ranks all-gather their best costs and the best slab is broadcast from
-the arg-min rank over NCCL (the reference's restart-from-best, src/main.c:75-77).
+Under torchrun (N > 1) the timed arm is BASELINE.json configs[3]: the replicas of all ranks form one
+temperature ladder (parallel tempering); every rank owns its own chains (weak scaling, no collective
+inside a step); after EVERY step the ranks all-gather (cost, temperature) of every replica and swap
+temperatures (mg_comm_temper_exchange), and every --exchange-every steps the cheapest best slab is
+broadcast with its checkpoints and installed by copy (mg_comm_exchange_best).  The collectives are the
+library's own NCCL calls behind the C ABI; torch.distributed only carries the rendezvous (NCCL id,
+barriers, the final reductions of the timing numbers).
+
+Rank 0 at N = 1 also reports, outside the timed region: `size` (the second half of the metric: .lzma bytes
+after a fixed wall budget through the drop-in CLI, beside the reference harness on one core at the same
+budget and xz -9e), `config3` (4 KiB exec-like input, thousands of chains) and `encode` (range-coder pass).
 """
 from __future__ import annotations
 
@@ -191,6 +199,122 @@ def run_reference(args) -> None:
 
 
 # ------------------------------------------------------------------------------------------------
+# the second half of the metric: .lzma bytes at equal wall time (rank 0, N = 1, outside the timed region)
+# ------------------------------------------------------------------------------------------------
+def _reference_size(kind: str, n: int, wall_s: float) -> dict:
+    """The reference's own loop (src/main.c:78-102, step 0, from the all-literal slab) on ONE host core for
+    `wall_s` seconds, then its range coder: bytes of the stream it would write."""
+    from oracle import oracle_lib as ol
+    which = cpu_kind()
+    lib = ol.Ref() if which == "reference" else ol.Port()
+    data = _corpus(kind, n)
+    slab = ol.literal_slab(n)
+    best = slab.copy()
+    kw = {} if which == "reference" else {"rng_mode": 0}
+    t0 = time.perf_counter()
+    probe = 4
+    _, bc, cc, *_ = lib.anneal_epoch(data, slab, best, 0, 0, seed=1673551, evals=probe, **kw)
+    dt = max(1e-3, time.perf_counter() - t0)
+    evals = probe
+    rate = probe / dt
+    remaining = wall_s - dt
+    if remaining > 0:
+        more = max(1, int(rate * remaining * 0.9))
+        _, bc, cc, *_ = lib.anneal_epoch(data, slab, best, bc, cc, reseed=0, evals=more, **kw)
+        evals += more
+    used = time.perf_counter() - t0
+    stream = lib.encode_slab(data, best if bc else slab)
+    import lzma
+    return {"bytes": len(stream), "evals": evals, "wall_s": used, "cores": 1, "kind": which,
+            "round_trip": lzma.decompress(stream, format=lzma.FORMAT_ALONE) == data}
+
+
+def size_leg(mg, wave: int, budget_s: float, device: int) -> list:
+    import lzma
+    import tempfile
+    from megalania_b200 import build
+    cli = build.build_cli() or build.CLI
+    out = []
+    for name, kind, n, chains in (("config 1: 64 KiB synthetic English-like text", "text", 65536, wave),
+                                  ("config 2: 1 MiB synthetic mixed text/binary", "mixed", 1 << 20, wave),
+                                  ("config 3: 4 KiB synthetic executable-like binary", "binary", 4096, max(4096, wave))):
+        data = _corpus(kind, n)
+        with tempfile.NamedTemporaryFile(suffix=".bin") as f:
+            f.write(data)
+            f.flush()
+            cmd = [cli, "--chains", str(chains), "--time", str(int(budget_s)), "--round-ms", "250", "--device", str(device), f.name]
+            t0 = time.perf_counter()
+            r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+            wall = time.perf_counter() - t0
+        rec = {"config": name, "input_bytes": n, "chains": chains, "wall_s": wall,
+               "command": "megalania --chains %d --time %d --round-ms 250 <file>  (drop-in C CLI: cooperative regions, "
+                          "final range-coder pass on the device)" % (chains, int(budget_s))}
+        if r.returncode != 0:
+            rec["error"] = r.stderr.decode(errors="replace")[-300:]
+            out.append(rec)
+            continue
+        rec["bytes"] = len(r.stdout)
+        try:
+            rec["round_trip"] = lzma.decompress(r.stdout, format=lzma.FORMAT_ALONE) == data
+        except lzma.LZMAError:
+            rec["round_trip"] = False
+        rec["xz_9e_bytes"] = len(lzma.compress(data, format=lzma.FORMAT_ALONE, preset=9 | lzma.PRESET_EXTREME))
+        rec["reference_same_wall"] = _reference_size(kind, n, wall)
+        rec["no_larger_than_reference"] = rec["bytes"] <= rec["reference_same_wall"]["bytes"]
+        rec["smaller_than_xz_9e"] = rec["bytes"] < rec["xz_9e_bytes"]
+        out.append(rec)
+    return out
+
+
+def config3_leg(mg, wave: int, seconds: float, sm_khz: int, device: int) -> dict:
+    """BASELINE configs[2]: 4 KiB executable-like binary, thousands of chains, all-literal start."""
+    n = 4096
+    data = _corpus("binary", n)
+    chains = max(4096, wave)
+    chains = (chains + wave - 1) // wave * wave
+    ctx = mg.Context(data, device=device)
+    an = mg.Annealer(ctx, chains, seed=7)
+    an.set_slab(None)
+    budget = int(250 * sm_khz)
+    for _ in range(2):
+        an.run(1_000_000, first_eval=mg.CONTINUE_EVALS, cycle_budget=budget, suspend=True)
+    evals, ms, steps = 0, 0.0, 0
+    while ms < seconds * 1e3:
+        st = an.run(1_000_000, first_eval=mg.CONTINUE_EVALS, cycle_budget=budget, suspend=True)
+        evals += st["evals"]
+        ms += st["kernel_ms"]
+        steps += 1
+    cur, best = an.costs()
+    an.close()
+    ctx.close()
+    return {"workload": "4 KiB synthetic executable-like binary (tools/corpus.py binary, seed 7), all-literal start, reference schedule",
+            "chains": chains, "evals_per_s": evals / (ms / 1e3), "evals_per_chain": evals / chains, "device_s": ms / 1e3,
+            "steps": steps, "best_bytes_estimate": 18 + int(best[best > 0].min()) / 16384.0}
+
+
+def encode_leg(mg, data: bytes, best_slab, device: int) -> dict:
+    """The final range-coder pass (src/main.c:110-119) on the device beside the reference's CPU pass."""
+    from oracle import oracle_lib as ol
+    n = len(data)
+    ctx = mg.Context(data, device=device)
+    cpu = ol.Ref() if cpu_kind() == "reference" else ol.Port()
+    out = {}
+    for name, slab in (("all_literal", mg.literal_slab(n)), ("annealed_best", best_slab)):
+        if slab is None:
+            continue
+        ctx.encode_slab_buffer(slab)
+        stream = ctx.encode_slab_buffer(slab)
+        st = ctx.encode_stats()
+        t0 = time.perf_counter()
+        want = cpu.encode_slab(data, slab)
+        cpu_ms = 1e3 * (time.perf_counter() - t0)
+        out[name] = {"bytes": len(stream), "events": st["events"], "device_ms": st["kernel_ms"], "cpu_ms": cpu_ms,
+                     "identical_to_cpu": stream == want}
+    ctx.close()
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
 # the CUDA arm
 # ------------------------------------------------------------------------------------------------
 def run_cuda(args) -> None:
@@ -223,40 +347,42 @@ def run_cuda(args) -> None:
         chains //= 2
     an = mg.Annealer(ctx, chains, seed=args.seed + 1000003 * rank)
     an.set_slab(None)
-    import_buf = torch.empty(n * 8, dtype=torch.uint8, device=f"cuda:{local}") if world > 1 else None
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    from megalania_b200.tempering import ReplicaExchange
-    rex = ReplicaExchange(dist, device=f"cuda:{local}", seed=args.seed)
-
-    def exchange():
-        """best-slab broadcast between steps (no collective inside a step): all-gather of the
-        ranks' best costs, NCCL broadcast of the winner's packed slab, the other ranks re-seed
-        their worst chain with it."""
-        if dist is None:
-            return
-        cur, best = an.costs()
-        nz = best[best > 0]
-        rex.broadcast_best(int(nz.min()) if nz.size else 0,
-                           lambda buf: an.export_slab(int(np.where(best > 0, best, np.iinfo(np.uint64).max).argmin()), True, buf.data_ptr()),
-                           lambda buf: an.import_slab(int(cur.argmax()), buf.data_ptr(), adopt_cost=True),
-                           import_buf)
+    temps = None
+    if dist is not None:
+        # the library's own communicator (NCCL behind the C ABI); torch.distributed only carries the id
+        box = [mg.Context.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        ctx.comm_init(rank, world, box[0])
+        from megalania_b200.tempering import temperature_ladder
+        ladder = temperature_ladder(world * chains, args.t_min, args.t_max)
+        temps = ladder[rank::world].copy()  # every rank holds rungs from the whole ladder
 
     step_no = [0]
+    exchange_ms = [0.0]
 
     sm_khz = int(getattr(props, "clock_rate", 0) or peaks()[0].get("sm_max_mhz", 1965.0) * 1000)
     cycle_budget = 0 if args.packet_budget else int(args.step_ms * sm_khz)
 
     def step(first_eval):
-        st = an.run(args.evals, schedule=mg.SCHEDULE_REFERENCE, step=0, first_eval=mg.CONTINUE_EVALS,
-                    packet_budget=args.packet_budget, cycle_budget=cycle_budget, suspend=True)
+        nonlocal temps
+        if dist is None:
+            st = an.run(args.evals, schedule=mg.SCHEDULE_REFERENCE, step=0, first_eval=mg.CONTINUE_EVALS,
+                        packet_budget=args.packet_budget, cycle_budget=cycle_budget, suspend=True)
+        else:
+            st = an.run(args.evals, schedule=mg.SCHEDULE_TEMPERATURE, temperatures=temps, first_eval=mg.CONTINUE_EVALS,
+                        packet_budget=args.packet_budget, cycle_budget=cycle_budget, suspend=True)
+            t0 = time.perf_counter()
+            temps = an.comm_temper_exchange(temps, step_no[0], seed=args.seed)       # every step
+            if (step_no[0] + 1) % args.exchange_every == 0:
+                an.comm_exchange_best()                                              # best-slab broadcast
+            exchange_ms[0] += 1e3 * (time.perf_counter() - t0)
         step_no[0] += 1
-        if step_no[0] % args.exchange_every == 0:
-            exchange()
         return st
 
     first_eval = 0
@@ -265,6 +391,7 @@ def run_cuda(args) -> None:
         first_eval += args.evals
     sampler = ClockSampler(local)
     barrier()
+    exchange_ms[0] = 0.0
     sampler.start()
     t0 = time.perf_counter()
     agg = None
@@ -326,6 +453,13 @@ def run_cuda(args) -> None:
                               "shared-memory instruction useful); the slot-class design issues ~4.9 shared-memory wavefronts per "
                               "9-bit literal, i.e. its own ceiling is one wavefront per cycle per SM = ~5.3e11 bits/s (DESIGN.md 5)"}
 
+    ctx_comm_stats = ctx.comm_stats() if dist is not None else None
+    best_slab = None
+    if rank == 0 and world == 1 and not args.no_size:
+        _, bestc = an.costs()
+        if (bestc > 0).any():
+            best_slab = an.get_slab(int(np.where(bestc > 0, bestc, np.iinfo(np.uint64).max).argmin()), best=True)
+
     # ---- end to end through the one-shot host call (host buffers in and out) -------------------
     e2e = None
     if not args.no_e2e:
@@ -380,6 +514,19 @@ def run_cuda(args) -> None:
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu = cpu_baseline(n, args.cpu_evals)
 
+    size = config3 = encode = None
+    if rank == 0 and world == 1 and not args.no_size:
+        wave = props.multi_processor_count * 27
+        try:
+            c0 = mg.Context(b"wave probe wave probe", device=local)
+            wave = c0.full_wave()
+            c0.close()
+        except mg.MegalaniaError:
+            pass
+        encode = encode_leg(mg, data, best_slab, local)
+        config3 = config3_leg(mg, wave, args.config3_seconds, sm_khz, local)
+        size = size_leg(mg, wave, args.size_budget, local)
+
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True,
@@ -391,12 +538,21 @@ def run_cuda(args) -> None:
                                    "; a proposal cut by the budget is suspended at a checkpoint and finished by the next step",
                            "top_k": 20, "l2": "inputs_exceed_l2",
                            "per_gpu_slab_bytes": chains * n * 8,
-                           "multi_gpu": f"independent chains per rank; all-gather of best costs + NCCL broadcast of the best slab every {args.exchange_every} steps"},
+                           "multi_gpu": (None if world == 1 else
+                                         f"BASELINE configs[3]: parallel tempering, one geometric ladder of {world * chains} temperatures "
+                                         f"({args.t_min}..{args.t_max} in 1/2048 bit) over the replicas of all ranks; after every step an NCCL "
+                                         f"all-gather of (cost, temperature) per replica and temperature swaps (mg_comm_temper_exchange); every "
+                                         f"{args.exchange_every} steps the cheapest best slab is broadcast with its checkpoints and installed by copy "
+                                         f"(mg_comm_exchange_best); collectives are the library's own NCCL calls behind the C ABI"),
+                           "schedule": "reference rule src/main.c:86 (step 0)" if world == 1 else "Metropolis at the replica's ladder temperature"},
                 "device_ms_per_step": 1e3 * device_s / args.steps,
                 "timing": "value = evaluations / wall clock between barrier+cudaDeviceSynchronize brackets, max over ranks; "
                           "device_ms_per_step = CUDA events around the kernel on the library's launch stream",
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
+                "exchange_ms_per_step": exchange_ms[0] / args.steps if world > 1 else None,
+                "comm": ctx_comm_stats,
                 "roofline": roofline, "roofline_issue": roofline_issue, "finder": finder, "cpu_baseline": cpu,
+                "size": size, "config3": config3, "encode": encode,
                 "stats": {"evals": total_evals, "modelled_bits": total_bits, "packets": total_packets,
                           "attempts": agg["attempts"], "accepted": agg["accepted"],
                           "finder_candidates": agg["finder_candidates"], "log_overflows": agg["log_overflows"],
@@ -425,6 +581,8 @@ def main() -> None:
                     help="instead of --step-ms: a chain ends its step when it has priced this many packets (reproducible)")
     ap.add_argument("--seed", type=int, default=1673551)
     ap.add_argument("--exchange-every", type=int, default=4, help="multi-GPU: best-slab broadcast every this many steps")
+    ap.add_argument("--t-min", type=float, default=16.0, help="multi-GPU: coldest ladder temperature, 1/2048 bit")
+    ap.add_argument("--t-max", type=float, default=65536.0, help="multi-GPU: hottest ladder temperature, 1/2048 bit")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--e2e-step-factor", type=int, default=3,
                     help="an end-to-end call anneals for this many bench steps (a one-shot call allocates ~90 GB of chains: "
@@ -432,6 +590,9 @@ def main() -> None:
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-finder", action="store_true")
+    ap.add_argument("--no-size", action="store_true", help="skip the size / config 3 / encode legs")
+    ap.add_argument("--size-budget", type=float, default=8.0, help="seconds of annealing per size-leg config (each side)")
+    ap.add_argument("--config3-seconds", type=float, default=4.0)
     ap.add_argument("--cpu-evals", type=int, default=0, help="evaluations of the CPU sample (default: sized to ~15 s)")
     ap.add_argument("--cpu-procs", type=int, default=1 << 30)
     args = ap.parse_args()

@@ -305,8 +305,10 @@ MG_API int mg_comm_size(const mg_ctx* ctx);
  * cheapest best slab (ties: lowest rank); that rank broadcasts the packed slab - with its model checkpoints when
  * the best slab is the chain's current one, so that receivers install it by copy instead of re-pricing 1 MiB on
  * one warp - and every other rank replaces its worst chain (highest current cost) with it, adopting the cost.
- * Costs stay on the device; the host only reads nranks x 40 bytes.  winner_rank = -1: nobody has a best yet. */
-MG_API int mg_comm_exchange_best(mg_anneal* an, int* winner_rank, uint64_t* best_cost);
+ * Costs stay on the device; the host only reads nranks x 40 bytes.  winner_rank = -1: nobody has a best yet.
+ * chain_out (may be NULL): the chain of THIS rank that now holds the winning slab - as its best slab on the winner,
+ * as its current slab on every other rank. */
+MG_API int mg_comm_exchange_best(mg_anneal* an, int* winner_rank, uint64_t* best_cost, uint32_t* chain_out);
 /* Collective: one round of replica exchange (parallel tempering) over the replicas of ALL ranks.  temps: host
  * array [chains] of this rank's temperatures, in and out.  One all-gather of (current cost, temperature) per
  * replica; every rank computes the same swap decisions (mg_temper_decide) and only temperatures move. Works

@@ -154,7 +154,7 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
     L.mg_comm_destroy.restype = None
     L.mg_comm_rank.argtypes = [vp]
     L.mg_comm_size.argtypes = [vp]
-    L.mg_comm_exchange_best.argtypes = [vp, C.POINTER(i32), C.POINTER(u64)]
+    L.mg_comm_exchange_best.argtypes = [vp, C.POINTER(i32), C.POINTER(u64), C.POINTER(u32)]
     L.mg_comm_temper_exchange.argtypes = [vp, vp, u32, u64]
     L.mg_temper_decide.argtypes = [vp, vp, sz, u32, u64, vp]
     L.mg_comm_merge_regions.argtypes = [vp, u32, vp, vp, u32, C.POINTER(u64)]
@@ -446,10 +446,10 @@ class Annealer:
         return int(cost.value)
 
     def comm_exchange_best(self):
-        """Collective: (winner rank or -1, global best cost); see mg_comm_exchange_best."""
-        w, c = C.c_int(-1), C.c_uint64(0)
-        _check(self._lib.mg_comm_exchange_best(self._h, C.byref(w), C.byref(c)))
-        return int(w.value), int(c.value)
+        """Collective: (winner rank or -1, global best cost, this rank's chain holding the slab); see mg_comm_exchange_best."""
+        w, c, ch = C.c_int(-1), C.c_uint64(0), C.c_uint32(0)
+        _check(self._lib.mg_comm_exchange_best(self._h, C.byref(w), C.byref(c), C.byref(ch)))
+        return int(w.value), int(c.value), int(ch.value)
 
     def comm_broadcast_chain(self, root: int, src_chain: int, dst_chain: int) -> None:
         _check(self._lib.mg_comm_broadcast_chain(self._h, root, src_chain, dst_chain))

@@ -55,7 +55,7 @@ def build_cli(force: bool = False) -> str | None:
         return None
     if force or _stale(CLI, srcs + [LIB]):
         cmd = ["gcc", "-O2", "-std=gnu11", "-Wall", "-Wextra", "-I", os.path.join(ROOT, "include"), "-o", CLI] + srcs + [
-            "-L", OUT, "-lmegalania_cuda", "-Wl,-rpath,$ORIGIN", "-lm"]
+            "-L", OUT, "-lmegalania_cuda", "-Wl,-rpath,$ORIGIN", "-lm", "-lpthread"]
         subprocess.run(cmd, check=True)
     return CLI
 

@@ -320,6 +320,7 @@ __device__ __noinline__ uint32_t warp_find(int lane, SmemU16 probs, SmemU32 pric
 			const uint32_t root = full ? fs->hkey[0] >> 5 : 0xffffffffu;
 			uint32_t cheapest = 0xffffffffu;
 			uint32_t live_lens = 0;  // bit (len-2): some candidate of that length is at or below the root
+			uint32_t first_live = 2; // shortest length with such a candidate (what a replay of a match longer than 33 starts at)
 			if (valid) {
 				uint32_t rep_hdr_best = 0xffffffffu;
 				if (rep_mask & 1) rep_hdr_best = min(rep_hdr_best, hdr_r0);
@@ -340,14 +341,18 @@ __device__ __noinline__ uint32_t warp_find(int lane, SmemU16 probs, SmemU32 pric
 					cheapest = 0;
 					live_lens = 0xffffffffu;
 				} else if (bound <= root) {
+					first_live = 0xffffffffu;
 					for (uint32_t len = 2; len <= L; len++) {
 						const uint32_t b = len == 2 ? base2 : len == 3 ? base3 : len == 4 ? base4 : base5;
 						const uint32_t pm = per_byte(b + fs->len_price[0][len - 2], len, recip);
 						uint32_t pr = 0xffffffffu;
 						if (rep_mask) pr = per_byte(rep_hdr_best + fs->len_price[1][len - 2], len, recip);
 						cheapest = min(cheapest, min(pm, pr));
-						// lengths worth replaying (only meaningful while L <= 33, see the replay below)
-						if (min(pm, pr) <= root) live_lens |= 1u << ((len - 2) & 31);
+						// lengths worth replaying: a bit set while L <= 33, the first such length beyond (see the replay below)
+						if (min(pm, pr) <= root) {
+							live_lens |= 1u << ((len - 2) & 31);
+							first_live = min(first_live, len);
+						}
 					}
 				}
 				candidates += (L - 1) * (1 + __popc(rep_mask));
@@ -406,9 +411,11 @@ __device__ __noinline__ uint32_t warp_find(int lane, SmemU16 probs, SmemU32 pric
 				if (lane == who) {
 					// The root only falls while this lane replays, so lengths that were above it when
 					// the lane was priced can be skipped; heap_offer re-tests the rest against the
-					// live root.  (The bit set covers lengths 2..33; longer matches replay in full.)
+					// live root.  (The bit set covers lengths 2..33; a longer match replays from the first
+					// length that was at or below the root: prices per byte mostly fall with the length, so
+					// that is where the candidates worth offering start.)
 					uint32_t todo = L <= 33 ? live_lens : 0xffffffffu;
-					for (uint32_t len = 2; len <= L; len++) {
+					for (uint32_t len = L <= 33 ? 2u : first_live; len <= L; len++) {
 						if (L <= 33) {
 							if (todo == 0) break;
 							len = 2 + (uint32_t)__ffs((int)todo) - 1;

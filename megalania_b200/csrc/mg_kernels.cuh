@@ -1522,7 +1522,8 @@ __device__ __forceinline__ void encode_produce(EncodeShared* sh, const EncodeArg
 			// ---- run of plain literals (src/lzma_packet_encoder.c:106-121): every lane follows its own slot
 			// class through the run, nine events per literal straight into the ring -----------------------
 			const uint32_t idx = m.pos - w.base;
-			uint32_t run = (uint32_t)__ffs((int)~(w.litmask >> idx)) - 1u;
+			uint32_t run = (uint32_t)__ffs((int)~(w.litmask >> idx)) - 1u;  // 0xffffffff when every slot up to the window's end is one
+			run = run < 32u - idx ? run : 32u - idx;
 			run = run < a.n - m.pos ? run : a.n - m.pos;
 			uint32_t cj = m.ctx;
 			uint32_t at = head + (uint32_t)lane;

@@ -6,7 +6,7 @@ from tools import corpus
 n = 1 << 20
 data = corpus.make("mixed", n)
 ctx = mg.Context(data)
-an = mg.Annealer(ctx, 4736, seed=5)
+an = mg.Annealer(ctx, ctx.full_wave(), seed=5)
 an.set_slab(None)
 for it in range(2):
     st = an.run(1000, first_eval=mg.CONTINUE_EVALS, suspend=True, cycle_budget=300_000_000)
