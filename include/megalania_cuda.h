@@ -87,6 +87,14 @@ MG_API int mg_ctx_create(const uint8_t* data, size_t n, LZMAProperties props, in
 MG_API void mg_ctx_destroy(mg_ctx* ctx);
 MG_API size_t mg_ctx_size(const mg_ctx* ctx);
 MG_API int mg_ctx_device(const mg_ctx* ctx);
+/* Match-finder limits for inputs beyond the reference's reach.  The reference enumerates EVERY
+ * earlier occurrence of the bigram at a position (its window test is commented out, src/substring_enumerator.c:97,
+ * its index is O(n), :16-24): on run-heavy data one find walks 10^5..10^7 occurrences.  window = farthest match
+ * start in bytes before the position (0 = unlimited), max_occurrences = only the nearest that many earlier
+ * occurrences (0 = all).  Both default to 0 = the reference's semantics, which every parity claim is made under;
+ * with limits the candidate lists are the reference's lists restricted to the surviving occurrences, in the same
+ * order.  Applies to mg_find_topk and to chains created afterwards or already running. */
+MG_API int mg_ctx_set_finder_limits(mg_ctx* ctx, size_t window, uint32_t max_occurrences);
 /* Chains that fill the device exactly once: SMs x chains per SM (one warp and one model in shared memory each).
  * Populations are best sized in multiples of it. */
 MG_API uint32_t mg_ctx_full_wave(const mg_ctx* ctx);

@@ -86,7 +86,7 @@ EXPORTS = [
     "mg_anneal_merge_export", "mg_anneal_merge_import", "mg_debug_index", "mg_encode_stats", "mg_ctx_full_wave",
     "mg_comm_unique_id", "mg_comm_init", "mg_comm_destroy", "mg_comm_rank", "mg_comm_size", "mg_comm_exchange_best",
     "mg_comm_temper_exchange", "mg_temper_decide", "mg_comm_merge_regions", "mg_comm_stats", "mg_pool_trim",
-    "mg_comm_broadcast_chain", "mg_comm_allgather_u64",
+    "mg_comm_broadcast_chain", "mg_comm_allgather_u64", "mg_ctx_set_finder_limits",
 ]
 
 _lib = None
@@ -117,6 +117,7 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
     L.mg_ctx_size.argtypes = [vp]
     L.mg_ctx_size.restype = sz
     L.mg_ctx_device.argtypes = [vp]
+    L.mg_ctx_set_finder_limits.argtypes = [vp, sz, u32]
     L.mg_ctx_full_wave.argtypes = [vp]
     L.mg_ctx_full_wave.restype = u32
     L.mg_score_slabs.argtypes = [vp, vp, sz, vp]
@@ -311,6 +312,10 @@ class Context:
         a, b, c = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
         _check(self._lib.mg_comm_stats(self._h, C.byref(a), C.byref(b), C.byref(c)))
         return {"exchanges": int(a.value), "installs_by_copy": int(b.value), "installs_by_rescore": int(c.value)}
+
+    def set_finder_limits(self, window: int = 0, max_occurrences: int = 0) -> None:
+        """0, 0 = the reference's unbounded enumeration (the default)."""
+        _check(self._lib.mg_ctx_set_finder_limits(self._h, window, max_occurrences))
 
     def full_wave(self) -> int:
         """Chains that fill the device exactly once (SMs x chains per SM)."""

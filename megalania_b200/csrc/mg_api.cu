@@ -143,6 +143,7 @@ struct mg_ctx {
 	std::vector<mg_anneal*> annealers;  // live chain populations on this context (destroyed with it)
 	double last_topk_ms = 0;          // mg_find_topk: device time and candidates of the last call
 	unsigned long long last_topk_candidates = 0;
+	FindLimits limits{0, 0};          // mg_ctx_set_finder_limits (0, 0 = the reference's unbounded enumeration)
 	double last_encode_ms = 0;        // mg_encode_slab*: device time and events of the last call
 	unsigned long long last_encode_events = 0;
 };
@@ -332,6 +333,13 @@ extern "C" MG_API int mg_find_topk_stats(const mg_ctx* ctx, double* kernel_ms, u
 	return MG_OK;
 }
 extern "C" MG_API int mg_ctx_device(const mg_ctx* ctx) { return ctx ? ctx->device : -1; }
+extern "C" MG_API int mg_ctx_set_finder_limits(mg_ctx* ctx, size_t window, uint32_t max_occurrences)
+{
+	if (!ctx) return fail(MG_EINVAL, "mg_ctx_set_finder_limits: null context");
+	ctx->limits.window = window > 0xffffffffull ? 0xffffffffu : (uint32_t)window;
+	ctx->limits.max_occ = max_occurrences;
+	return MG_OK;
+}
 extern "C" MG_API uint32_t mg_ctx_full_wave(const mg_ctx* ctx) { return ctx ? (uint32_t)ctx->sm_count * (uint32_t)WARPS_PER_CTA : 0u; }
 extern "C" MG_API int mg_encode_stats(const mg_ctx* ctx, double* kernel_ms, uint64_t* events)
 {
@@ -575,6 +583,7 @@ extern "C" MG_API int mg_find_topk(mg_ctx* ctx, const LZMAPacket* slab, int stat
 	a.out_count = ocount.as<int32_t>();
 	a.out_err = oerr.as<uint32_t>();
 	a.candidates = cand.as<unsigned long long>();
+	a.limits = ctx->limits;
 	a.tables = ctx->tables;
 	size_t blocks = (npos + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
 	const size_t cap = (size_t)ctx->sm_count * 4 * 8;
@@ -1020,6 +1029,7 @@ static void anneal_common_args(mg_anneal* an, AnnealArgs& a)
 	a.occ_start = ctx->d_occ_start;
 	a.occ = ctx->d_occ;
 	a.tables = ctx->tables;
+	a.limits = ctx->limits;
 	a.chains = C;
 	a.k = an->p.top_k;
 	a.stride = an->stride;
@@ -1089,7 +1099,9 @@ extern "C" MG_API int mg_anneal_run(mg_anneal* an, const mg_anneal_run_params* r
 		CU(cudaMemcpyAsync(an->d_regions, run->regions, (size_t)C * 8, cudaMemcpyHostToDevice, ctx->stream));
 		a.regions = an->d_regions;
 	}
-	const int blocks = (int)((C + WARPS_PER_CTA - 1) / WARPS_PER_CTA);
+	// one CTA per SM while the population is at most one wave, then as many CTAs as the chains need
+	int blocks = (int)((C + WARPS_PER_CTA - 1) / WARPS_PER_CTA);
+	if (blocks < ctx->sm_count) blocks = (int)(C < (uint32_t)ctx->sm_count ? C : (uint32_t)ctx->sm_count);
 	CU(cudaEventRecord(an->e0, ctx->stream));
 	anneal_kernel<<<blocks, CTA_THREADS, sizeof(CtaShared), ctx->stream>>>(a);
 	CU(cudaEventRecord(an->e1, ctx->stream));

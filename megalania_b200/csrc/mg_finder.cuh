@@ -15,6 +15,11 @@
 namespace mg {
 
 constexpr int MAX_K = 32;
+// Optional limits beyond the reference (mg_ctx_set_finder_limits): 0 = none.
+struct FindLimits {
+	uint32_t window;   // farthest match start, bytes before the position
+	uint32_t max_occ;  // only the nearest max_occ earlier occurrences of the bigram
+};
 constexpr uint32_t FIND_GAVE_UP = 0xffffffffu;  // warp_find: the deadline passed inside a long bucket
 constexpr uint32_t MAX_MATCH = 273;  // src/packet_enumerator.c:6-7
 
@@ -178,7 +183,7 @@ __device__ __noinline__ uint32_t warp_find(int lane, SmemU16 probs, SmemU32 pric
                                            SmemU32 recip, FindScratch* fs, const uint8_t* __restrict__ data,
                                            uint32_t n, const uint32_t* __restrict__ occ_start,
                                            const uint32_t* __restrict__ occ, const Model m, uint64_t excluded,
-                                           uint32_t k, long long give_up_at = 0)
+                                           uint32_t k, long long give_up_at = 0, FindLimits limits = FindLimits{0, 0})
 {
 	uint32_t candidates = 0, chunks = 0;
 	// the length-price tables below share their memory with the walk's window mirrors: a window copy
@@ -218,7 +223,23 @@ __device__ __noinline__ uint32_t warp_find(int lane, SmemU16 probs, SmemU32 pric
 	// substring_enumerator.c:87-88
 	if (pos != 0 && pos != n - 1) {
 		const uint32_t key = ((uint32_t)byte << 8) | data[pos + 1];
-		const uint32_t begin = occ_start[key], end = occ_start[key + 1];
+		uint32_t begin = occ_start[key];
+		const uint32_t end = occ_start[key + 1];
+		if (limits.window | limits.max_occ) {
+			// the bucket is ascending: two binary searches bound the occurrences that may be offered
+			auto first_at_least = [&](uint32_t value) {
+				uint32_t lo = begin, hi = end;
+				while (lo < hi) {
+					const uint32_t mid = lo + (hi - lo) / 2;
+					if (occ[mid] < value) lo = mid + 1;
+					else hi = mid;
+				}
+				return lo;
+			};
+			const uint32_t upper = first_at_least(pos);  // occurrences at or after pos are never offered
+			if (limits.window != 0 && pos > limits.window) begin = first_at_least(pos - limits.window);
+			if (limits.max_occ != 0 && upper - begin > limits.max_occ) begin = upper - limits.max_occ;
+		}
 		const uint32_t max_len = n - pos < MAX_MATCH ? n - pos : MAX_MATCH;
 		uint32_t have_len[2] = {1, 1};  // len_price filled for lengths 2..have_len
 		uint32_t min_lp[2] = {0xffffffffu, 0xffffffffu};  // cheapest length price filled so far

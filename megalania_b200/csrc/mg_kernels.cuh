@@ -264,9 +264,10 @@ __device__ __forceinline__ WalkEnv make_env(int lane, WarpShared* ws, const CtaS
 //   event = shared address of the probability | table section << 29   (sections: CtaShared)
 // When both literals of a pair touch the SAME slot (always for is_match and the tree root, whenever their bit
 // prefixes agree deeper down) the second literal's lane applies both steps with one load from the two-step
-// table (section 4 | first bit << 1 | second bit), and the first literal's lane is pointed at the spare slot
-// (probability 0, whose bit-0 entry is the zero-price fixed point): per-slot order is the reference's, nothing is
-// touched twice in a step.  Plain literals only (automaton state 0; src/lzma_packet_encoder.c:106-121).
+// table (section 4 | first bit << 1 | second bit), and the first literal's lane sits the pair out (event 0: its
+// loads and store are predicated off - several lanes parked on one spare slot measured as a two-way bank conflict
+// on every 16-bit access): per-slot order is the reference's, nothing is touched twice in a step.
+// Plain literals only (automaton state 0; src/lzma_packet_encoder.c:106-121).
 __device__ __forceinline__ void window_events(const WalkEnv& e, Window& w)
 {
 	__syncwarp();
@@ -275,17 +276,17 @@ __device__ __forceinline__ void window_events(const WalkEnv& e, Window& w)
 	const uint32_t second = (uint32_t)e.lane & 1u;
 	const uint32_t x = b ^ other;
 	const uint32_t out = e.ev_addr + 4u * (((uint32_t)e.lane >> 1) + EVENT_PAIR_COLUMNS * second);
-	const uint32_t spare = e.probs.a + 2 * S_DUMMY;
-	// same slot as the pair's other literal at tree depth d  <=>  the first d bits agree
+	// same slot as the pair's other literal at tree depth d  <=>  the first d bits agree; the first literal's
+	// event is then 0 = "sit this pair out" (the second literal's lane steps the slot twice)
 	auto event = [&](uint32_t slot, uint32_t depth_bits, uint32_t bit_pos) -> uint32_t {
 		const bool same = (x >> (8 - depth_bits)) == 0;
 		const uint32_t own = (b >> bit_pos) & 1u, first = (other >> bit_pos) & 1u;
 		uint32_t ev = (e.probs.a + 2 * slot) | (own << 29);
-		if (same) ev = second ? (ev | 0x80000000u | (first << 30)) : spare;
+		if (same) ev = second ? (ev | 0x80000000u | (first << 30)) : 0u;
 		return ev;
 	};
 	// is_match[0]: both bits 0, always the same slot
-	sts_u32(out + 0 * 4 * EVENT_ROW_WORDS, second ? ((e.probs.a + 2 * S_ISMATCH) | 0x80000000u) : spare);
+	sts_u32(out + 0 * 4 * EVENT_ROW_WORDS, second ? ((e.probs.a + 2 * S_ISMATCH) | 0x80000000u) : 0u);
 	sts_u32(out + 1 * 4 * EVENT_ROW_WORDS, event(S_LIT01, 0, 7));
 	sts_u32(out + 2 * 4 * EVENT_ROW_WORDS, event(S_LIT01 + 4 + (b >> 7), 1, 6));
 	const uint32_t row = S_LIT + (b >> 6) * 64;
@@ -562,15 +563,37 @@ __device__ __forceinline__ uint32_t walk(const uint32_t MODE, const WalkEnv& e, 
 						if (e.lane < 2 * (int)EVENT_LANES) {
 							uint32_t ea = e.ev_pair_addr + 2u * idx;
 							const uint32_t eend = ea + 4u * pairs;
+	// No barrier between pairs: the 18 lanes run this loop converged (uniform trip counts, no lane-dependent branch,
+	// only predication), and a warp's shared-memory instructions are performed in issue order, so the store of one
+	// pair is visible to the load of the next whichever lane reaches the slot (a __syncwarp per pair cost 30 % of the
+	// step: R2UR + BRA.DIV).  One per group of four keeps the lanes together.
+	// One predicate guards the step's three shared-memory accesses and its add (event 0 = the lane sits the pair
+	// out): written as one PTX block, because the compiler turns `if (ev != 0)` into a divergent branch per step.
 #define MG_PAIR_STEP(ev)                                                                               \
-	do {                                                                                                 \
-		const uint32_t ev_ = (ev);                                                                       \
-		const uint32_t pa_ = ev_ & 0x3ffffu;                                                             \
-		const uint32_t tr_ = lds_u32(e.trans_addr + ((ev_ >> 16) & 0xE000u) + (lds_u16(pa_) << 2));      \
-		sts_u16(pa_, tr_);                                                                               \
-		k.t.acc += tr_ >> 16;                                                                            \
-		__syncwarp(PAIR_LANES); /* the next pair may reach this slot from the other half's lane */      \
-	} while (0)
+	asm volatile(                                                                                        \
+	    "{\n\t"                                                                                          \
+	    ".reg .pred p;\n\t"                                                                              \
+	    ".reg .b32 pa, ta, pv, tr;\n\t"                                                                  \
+	    ".reg .b16 h;\n\t"                                                                               \
+	    "setp.ne.u32 p, %1, 0;\n\t"                                                                      \
+	    "and.b32 pa, %1, 0x3ffff;\n\t"                                                                   \
+	    "shr.u32 ta, %1, 16;\n\t"                                                                        \
+	    "and.b32 ta, ta, 0xE000;\n\t"                                                                    \
+	    "add.u32 ta, ta, %2;\n\t"                                                                        \
+	    "mov.b16 h, 0;\n\t"                                                                              \
+	    "@p ld.shared.u16 h, [pa];\n\t"                                                                  \
+	    "cvt.u32.u16 pv, h;\n\t"                                                                         \
+	    "mad.lo.u32 ta, pv, 4, ta;\n\t"                                                                  \
+	    "mov.b32 tr, 0;\n\t"                                                                             \
+	    "@p ld.shared.u32 tr, [ta];\n\t"                                                                 \
+	    "cvt.u16.u32 h, tr;\n\t"                                                                         \
+	    "@p st.shared.u16 [pa], h;\n\t"                                                                  \
+	    "shr.u32 tr, tr, 16;\n\t"                                                                        \
+	    "add.u32 %0, %0, tr;\n\t"                                                                        \
+	    "}"                                                                                              \
+	    : "+r"(k.t.acc)                                                                                  \
+	    : "r"(ev), "r"(e.trans_addr)                                                                     \
+	    : "memory")
 							while (ea != eend && (ea & 15u) != 0) {
 								MG_PAIR_STEP(lds_u32(ea));
 								ea += 4;
@@ -583,6 +606,7 @@ __device__ __forceinline__ uint32_t walk(const uint32_t MODE, const WalkEnv& e, 
 								MG_PAIR_STEP(v.z);
 								MG_PAIR_STEP(v.w);
 								ea += 16;
+								__syncwarp(PAIR_LANES);
 							}
 							while (ea != eend) {
 								MG_PAIR_STEP(lds_u32(ea));
@@ -794,6 +818,7 @@ struct TopkArgs {
 	int32_t* out_count;    // [npos]
 	uint32_t* out_err;     // [npos]
 	unsigned long long* candidates;
+	FindLimits limits;
 	Tables tables;
 };
 
@@ -836,7 +861,7 @@ __global__ void __launch_bounds__(CTA_THREADS) topk_kernel(TopkArgs a)
 		uint32_t pops = 0;
 		if (!err) {
 			pops = warp_find(lane, e.probs, e.trans, e.recip, &ws->fs, a.data, a.n, a.occ_start, a.occ,
-			                 walker_model(e, k), a.slab[qpos], a.k);
+			                 walker_model(e, k), a.slab[qpos], a.k, 0, a.limits);
 			cand += ws->fs.candidates;
 			for (uint32_t i = lane; i < pops; i += 32) {
 				const uint32_t en = ws->fs.pop_order[i];
@@ -869,6 +894,7 @@ struct AnnealArgs {
 	const uint32_t* occ_start;
 	const uint32_t* occ;
 	Tables tables;
+	FindLimits limits;
 	uint32_t chains, k, stride, nslots, log_cap, track_best;
 	uint64_t* slabs;     // [chains][n]
 	uint64_t* bests;     // [chains][n] or null
@@ -905,8 +931,10 @@ __global__ void __launch_bounds__(CTA_THREADS, MG_ANNEAL_MIN_CTAS) anneal_kernel
 	CtaShared* sh = reinterpret_cast<CtaShared*>(smem_raw);
 	cta_tables_load(sh, a.tables);
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	if (blockIdx.x * WARPS_PER_CTA + warp >= a.chains) return;
-	const uint32_t c = a.chain_first + blockIdx.x * WARPS_PER_CTA + warp;
+	// chains are dealt round-robin over the CTAs, so that a population smaller than a full wave (huge inputs: a
+	// 16 MiB chain is 270 MB) still puts warps on every SM
+	if ((uint32_t)warp * gridDim.x + blockIdx.x >= a.chains) return;
+	const uint32_t c = a.chain_first + (uint32_t)warp * gridDim.x + blockIdx.x;
 	WarpShared* ws = warp_block(sh, warp);
 	const uint32_t n = a.n, nck = a.nslots - 1;
 	const uint32_t reg_lo = a.regions ? a.regions[2 * c] : 0u, reg_hi = a.regions ? a.regions[2 * c + 1] : 0u;
@@ -1142,7 +1170,7 @@ __global__ void __launch_bounds__(CTA_THREADS, MG_ANNEAL_MIN_CTAS) anneal_kernel
 				// proposal, so every launch makes progress
 				const uint32_t count = warp_find(lane, e.probs, e.trans, e.recip, &ws->fs, a.data, n, a.occ_start, a.occ,
 				                                 walker_model(e, k), excluded, a.k,
-				                                 (a.suspend && attempts > 1) ? deadline : 0);
+				                                 (a.suspend && attempts > 1) ? deadline : 0, a.limits);
 				k.w.ev_base = WINDOW_NONE;  // the finder's length tables share the window mirrors' memory
 				k.w.pf_base = WINDOW_NONE;  // ... and the staging area of the next window
 				if (count == FIND_GAVE_UP) {

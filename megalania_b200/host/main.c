@@ -28,12 +28,13 @@ static void usage(const char* argv0)
 {
 	fprintf(stderr,
 	        "usage: %s [--chains N] [--iters N] [--epochs N] [--steps N] [--seed N] [--device N] [--gpus N] [--top-k N]\n"
-	        "          [--rounds N | --time SECONDS] [--round-ms N] [--group N] [--temp T] [--sm-khz N] filename\n",
+	        "          [--rounds N | --time SECONDS] [--round-ms N] [--group N] [--temp T] [--sm-khz N]\n"
+	        "          [--window BYTES] [--max-occ N] filename\n",
 	        argv0);
 }
 
 typedef struct {
-	unsigned chains, iters, epochs, steps, device, top_k, rounds, round_ms, group, temp0, gpus, sm_khz;
+	unsigned chains, iters, epochs, steps, device, top_k, rounds, round_ms, group, temp0, gpus, sm_khz, window, max_occ;
 	unsigned long long seed;
 	const uint8_t* data;
 	size_t size;
@@ -265,6 +266,10 @@ static void* worker_main(void* arg)
 			die(w, "mg_ctx_create");
 			break;
 		}
+		if ((c->window || c->max_occ) && mg_ctx_set_finder_limits(w->ctx, c->window, c->max_occ)) {
+			die(w, "mg_ctx_set_finder_limits");
+			break;
+		}
 		if (c->gpus > 1 && mg_comm_init(w->ctx, w->rank, (int)c->gpus, w->nccl_id)) {
 			die(w, "mg_comm_init");
 			break;
@@ -324,6 +329,8 @@ int main(int argc, char** argv)
 		else if (!strcmp(a, "--temp")) target = &cfg.temp0;
 		else if (!strcmp(a, "--time")) target = &time_s;
 		else if (!strcmp(a, "--sm-khz")) target = &cfg.sm_khz;
+		else if (!strcmp(a, "--window")) target = &cfg.window;   /* match-finder limits for huge inputs; 0 = the */
+		else if (!strcmp(a, "--max-occ")) target = &cfg.max_occ; /* reference's unbounded enumeration */
 		if (target) {
 			if (++i >= argc) { usage(argv[0]); return -1; }
 			*target = (unsigned)strtoul(argv[i], NULL, 10);

@@ -694,6 +694,15 @@ static MgoPacket mk(unsigned type, unsigned dist, unsigned len)
 	return p;
 }
 
+/* Finder limits for inputs beyond the reference's reach: 0 = none = the reference's semantics. */
+static size_t g_finder_window = 0;
+static uint32_t g_finder_max_occ = 0;
+void mgo_set_finder_limits(size_t window, uint32_t max_occ)
+{
+	g_finder_window = window;
+	g_finder_max_occ = max_occ;
+}
+
 /* top_k_packet_finder.c:95-118 */
 static void consider(TopK* t, const Model* m, MgoPacket excluded, MgoPacket pk)
 {
@@ -712,9 +721,18 @@ static void find_candidates(TopK* t, const Index* ix, const Model* m, MgoPacket 
 	if (pos > 0 && data[pos] == data[pos - m->rep[0] - 1]) consider(t, m, excluded, mk(T_SHORT_REP, 0, 1));
 	if (pos == 0 || pos == n - 1) return;
 	unsigned key = (unsigned)data[pos] << 8 | data[pos + 1];
-	for (uint32_t i = ix->start[key]; i < ix->start[key + 1]; i++) {
+	uint32_t first = ix->start[key];
+	if (g_finder_max_occ != 0) {
+		/* only the nearest max_occ earlier occurrences (an extension beyond the reference, off by default) */
+		uint32_t upper = first;
+		while (upper < ix->start[key + 1] && ix->occ[upper] < pos) upper++;
+		if (upper - first > g_finder_max_occ) first = upper - g_finder_max_occ;
+	}
+	for (uint32_t i = first; i < ix->start[key + 1]; i++) {
 		size_t o = ix->occ[i];
 		if (o >= pos) break;
+		/* the window limit the reference leaves commented out (src/substring_enumerator.c:97), off by default */
+		if (g_finder_window != 0 && pos - o > g_finder_window) continue;
 		unsigned dist = (unsigned)(pos - o - 1);
 		for (size_t len = 2; len <= 273 && pos + len <= n; len++) {
 			if (len > 2 && data[pos + len - 1] != data[o + len - 1]) break;

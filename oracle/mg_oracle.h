@@ -100,6 +100,11 @@ size_t mgo_live_count(const MgoPacket* slab, size_t n);
 /* 1 if every live packet of the slab is decodable (matches/reps reproduce the data). */
 int mgo_slab_valid(const uint8_t* data, size_t n, const MgoPacket* slab);
 
+/* Finder limits beyond the reference (it has none: its window test is commented out, src/substring_enumerator.c:97):
+ * window = farthest match start in bytes (0 = unlimited), max_occ = only the nearest max_occ earlier occurrences of
+ * the bigram (0 = all).  Process-global, off by default; checks mg_ctx_set_finder_limits. */
+void mgo_set_finder_limits(size_t window, uint32_t max_occ);
+
 #ifdef __cplusplus
 }
 #endif

@@ -157,6 +157,12 @@ class Port(_Lib):
         L.mgo_live_count.argtypes = [vp, sz]
         L.mgo_slab_valid.restype = i32
         L.mgo_slab_valid.argtypes = [vp, sz, vp]
+        L.mgo_set_finder_limits.restype = None
+        L.mgo_set_finder_limits.argtypes = [sz, C.c_uint32]
+
+    def set_finder_limits(self, window: int = 0, max_occ: int = 0) -> None:
+        """Process-global: 0, 0 restores the reference's semantics."""
+        self.lib.mgo_set_finder_limits(window, max_occ)
 
     def price_table(self) -> np.ndarray:
         p = self.lib.mgo_price_table()

@@ -265,3 +265,40 @@ def test_device_bigram_index(mg, corpora, port, kind, n):
                 ln += 1
             total += max(0, ln - 1)
         assert total == port.substring_count(data, pos)
+
+
+@pytest.mark.parametrize("window,max_occ", [(1500, 0), (0, 40), (3000, 64)])
+def test_finder_limits_match_the_restricted_oracle(mg, port, corpora, window, max_occ):
+    """a real window limit (src/substring_enumerator.c:97 is commented out in the reference) and a cap
+    on the occurrences walked.  With limits the lists are the reference's lists restricted to the surviving
+    occurrences; whole annealing trajectories under limits equal the oracle's under the same limits."""
+    n = 16384
+    data = corpora("mixed", n)
+    lit = mg.literal_slab(n)
+    try:
+        port.set_finder_limits(window, max_occ)
+        with mg.Context(data) as ctx:
+            ctx.set_finder_limits(window, max_occ)
+            pos = np.arange(n, dtype=np.uint64)
+            pops, prices, counts = ctx.find_topk(lit, pos, state_mode=0)
+            wp, wprice, wc = port.topk_many_priced(data, lit, 0, pos)
+            assert (counts == wc).all() and same_packets(pops, wp) and (prices == wprice).all()
+            chains, evals, seed = 3, 120, 55
+            an = mg.Annealer(ctx, chains, trace_capacity=evals * 64 + 1024, seed=seed, checkpoint_stride=512)
+            an.set_slab(None)
+            an.run(evals)
+            cur, best = an.costs()
+            for c in range(chains):
+                slab, bslab = lit.copy(), lit.copy()
+                attempts, bc, cc, _, trace = port.anneal_epoch(data, slab, bslab, 0, 0, rng_mode=1,
+                                                               rng_state=port.chain_seed(seed, c), evals=evals)
+                got = an.trace(c)
+                assert len(got) == attempts and (got["cost"] == trace["cost"]).all() and (got["flags"] == trace["flags"]).all()
+                assert int(cur[c]) == cc and int(best[c]) == bc
+            an.close()
+            # the limits really bite: the unrestricted lists differ somewhere
+            ctx.set_finder_limits(0, 0)
+            pops0, prices0, counts0 = ctx.find_topk(lit, pos, state_mode=0)
+            assert not ((counts0 == counts).all() and (prices0 == prices).all())
+    finally:
+        port.set_finder_limits(0, 0)
