@@ -22,6 +22,10 @@ struct FindLimits {
 };
 constexpr uint32_t FIND_GAVE_UP = 0xffffffffu;  // warp_find: the deadline passed inside a long bucket
 constexpr uint32_t MAX_MATCH = 273;  // src/packet_enumerator.c:6-7
+#ifndef MG_FINDER_PM
+#define MG_FINDER_PM 1  // 0 switches the running-maximum filter off (kernel experiments)
+#endif
+constexpr uint32_t PM_MIN_LEN = 16;  // matches at least this long go through the running-maximum filter of warp_find
 
 struct FindScratch {
 	uint64_t ent_pk[MAX_K];
@@ -244,6 +248,8 @@ __device__ __noinline__ uint32_t warp_find(int lane, SmemU16 probs, SmemU32 pric
 		uint32_t have_len[2] = {1, 1};  // len_price filled for lengths 2..have_len
 		uint32_t min_lp[2] = {0xffffffffu, 0xffffffffu};  // cheapest length price filled so far
 		uint32_t slot_cached = 0xffffffffu, slot_price2 = 0, slot_price3 = 0, slot_price4 = 0, slot_price5 = 0;
+		int32_t pm_prefix = INT32_MAX;  // see the running-maximum filter below
+		uint32_t pm_root = 0xffffffffu, pm_have = 0;
 		// align tree prices (src/lzma_packet_encoder.c:97-102): value i on lane i
 		DistParts ap;
 		ap.pslot = 14;
@@ -339,6 +345,32 @@ __device__ __noinline__ uint32_t warp_find(int lane, SmemU16 probs, SmemU32 pric
 			// cheapest candidate of this lane (lower bound test against the heap root)
 			const bool full = fs->count >= k;
 			const uint32_t root = full ? fs->hkey[0] >> 5 : 0xffffffffu;
+			// Long matches (zero runs: every occurrence matches 273 bytes) would price 272 lengths each just to learn
+			// that none beats the root.  floor((b + lp[len]) / len) <= root  <=>  b <= (root + 1) * len - 1 - lp[len], so a
+			// running maximum of the right-hand side over the lengths answers "can ANY length of this occurrence enter
+			// the heap" with one comparison.  It is kept in registers, nine lengths per lane (lane j: lengths up to
+			// 10 + 9 j), looked up by shuffle; the bucket's upper end only makes it pass more, never less:
+			// occurrences that pass are priced length by length as before.
+			const bool any_long = MG_FINDER_PM && __any_sync(FULL, valid && L >= PM_MIN_LEN && rep_mask == 0);
+			if (full && any_long && (root != pm_root || have_len[0] != pm_have)) {
+				int32_t q = INT32_MIN;
+				if (root < 0x400000u) {
+					for (uint32_t j = 0; j < 9; j++) {
+						const uint32_t len = 2u + 9u * (uint32_t)lane + j;
+						if (len <= have_len[0]) q = max(q, (int32_t)((root + 1u) * len - 1u) - (int32_t)fs->len_price[0][len - 2]);
+					}
+				} else {
+					q = INT32_MAX;
+				}
+				for (int o = 1; o < 32; o <<= 1) {
+					const int32_t t = __shfl_up_sync(FULL, q, o);
+					if (lane >= o) q = max(q, t);
+				}
+				pm_prefix = q;
+				pm_root = root;
+				pm_have = have_len[0];
+			}
+			const int32_t pm_at = __shfl_sync(FULL, pm_prefix, valid ? (int)((L - 2u) / 9u) : 0);
 			uint32_t cheapest = 0xffffffffu;
 			uint32_t live_lens = 0;  // bit (len-2): some candidate of that length is at or below the root
 			uint32_t first_live = 2; // shortest length with such a candidate (what a replay of a match longer than 33 starts at)
@@ -361,7 +393,7 @@ __device__ __noinline__ uint32_t warp_find(int lane, SmemU16 probs, SmemU32 pric
 				if (!full) {
 					cheapest = 0;
 					live_lens = 0xffffffffu;
-				} else if (bound <= root) {
+				} else if (bound <= root && (!MG_FINDER_PM || L < PM_MIN_LEN || rep_mask != 0 || pm_root != root || (int32_t)lo <= pm_at)) {
 					first_live = 0xffffffffu;
 					for (uint32_t len = 2; len <= L; len++) {
 						const uint32_t b = len == 2 ? base2 : len == 3 ? base3 : len == 4 ? base4 : base5;

@@ -16,6 +16,11 @@ constexpr int WARPS_PER_CTA = MG_WARPS_PER_CTA;
 constexpr int CTA_THREADS = WARPS_PER_CTA * 32;
 constexpr uint32_t RECIP_ENTRIES = 288;
 constexpr uint32_t PAIR_LANES = 0x3ffffu;  // lanes 0..17: the two literals of a pair step
+// Kernel experiments (tools/variants.sh): 0 = predicated idle lanes, no barrier between pairs (the product);
+// bit 0 = idle lanes parked on the spare slot instead, bit 1 = a warp barrier after every pair.
+#ifndef MG_PAIR_VARIANT
+#define MG_PAIR_VARIANT 0
+#endif
 
 struct ChainStats {
 	unsigned long long evals, attempts, accepted, new_best, packets, bits, slab_bytes, ck_bytes, finds, candidates,
@@ -276,17 +281,18 @@ __device__ __forceinline__ void window_events(const WalkEnv& e, Window& w)
 	const uint32_t second = (uint32_t)e.lane & 1u;
 	const uint32_t x = b ^ other;
 	const uint32_t out = e.ev_addr + 4u * (((uint32_t)e.lane >> 1) + EVENT_PAIR_COLUMNS * second);
+	const uint32_t idle = (MG_PAIR_VARIANT & 1) ? e.probs.a + 2 * S_DUMMY : 0u;
 	// same slot as the pair's other literal at tree depth d  <=>  the first d bits agree; the first literal's
 	// event is then 0 = "sit this pair out" (the second literal's lane steps the slot twice)
 	auto event = [&](uint32_t slot, uint32_t depth_bits, uint32_t bit_pos) -> uint32_t {
 		const bool same = (x >> (8 - depth_bits)) == 0;
 		const uint32_t own = (b >> bit_pos) & 1u, first = (other >> bit_pos) & 1u;
 		uint32_t ev = (e.probs.a + 2 * slot) | (own << 29);
-		if (same) ev = second ? (ev | 0x80000000u | (first << 30)) : 0u;
+		if (same) ev = second ? (ev | 0x80000000u | (first << 30)) : idle;
 		return ev;
 	};
 	// is_match[0]: both bits 0, always the same slot
-	sts_u32(out + 0 * 4 * EVENT_ROW_WORDS, second ? ((e.probs.a + 2 * S_ISMATCH) | 0x80000000u) : 0u);
+	sts_u32(out + 0 * 4 * EVENT_ROW_WORDS, second ? ((e.probs.a + 2 * S_ISMATCH) | 0x80000000u) : idle);
 	sts_u32(out + 1 * 4 * EVENT_ROW_WORDS, event(S_LIT01, 0, 7));
 	sts_u32(out + 2 * 4 * EVENT_ROW_WORDS, event(S_LIT01 + 4 + (b >> 7), 1, 6));
 	const uint32_t row = S_LIT + (b >> 6) * 64;
@@ -569,7 +575,7 @@ __device__ __forceinline__ uint32_t walk(const uint32_t MODE, const WalkEnv& e, 
 	// step: R2UR + BRA.DIV).  One per group of four keeps the lanes together.
 	// One predicate guards the step's three shared-memory accesses and its add (event 0 = the lane sits the pair
 	// out): written as one PTX block, because the compiler turns `if (ev != 0)` into a divergent branch per step.
-#define MG_PAIR_STEP(ev)                                                                               \
+#define MG_PAIR_STEP_PRED(ev)                                                                          \
 	asm volatile(                                                                                        \
 	    "{\n\t"                                                                                          \
 	    ".reg .pred p;\n\t"                                                                              \
@@ -594,6 +600,27 @@ __device__ __forceinline__ uint32_t walk(const uint32_t MODE, const WalkEnv& e, 
 	    : "+r"(k.t.acc)                                                                                  \
 	    : "r"(ev), "r"(e.trans_addr)                                                                     \
 	    : "memory")
+#if MG_PAIR_VARIANT & 1
+#define MG_PAIR_STEP_CORE(ev)                                                                          \
+	do {                                                                                                 \
+		const uint32_t ev_ = (ev);                                                                       \
+		const uint32_t pa_ = ev_ & 0x3ffffu;                                                             \
+		const uint32_t tr_ = lds_u32(e.trans_addr + ((ev_ >> 16) & 0xE000u) + (lds_u16(pa_) << 2));      \
+		sts_u16(pa_, tr_);                                                                               \
+		k.t.acc += tr_ >> 16;                                                                            \
+	} while (0)
+#else
+#define MG_PAIR_STEP_CORE(ev) MG_PAIR_STEP_PRED(ev)
+#endif
+#if MG_PAIR_VARIANT & 2
+#define MG_PAIR_STEP(ev)            \
+	do {                              \
+		MG_PAIR_STEP_CORE(ev);        \
+		__syncwarp(PAIR_LANES);       \
+	} while (0)
+#else
+#define MG_PAIR_STEP(ev) MG_PAIR_STEP_CORE(ev)
+#endif
 							while (ea != eend && (ea & 15u) != 0) {
 								MG_PAIR_STEP(lds_u32(ea));
 								ea += 4;
@@ -613,6 +640,8 @@ __device__ __forceinline__ uint32_t walk(const uint32_t MODE, const WalkEnv& e, 
 								ea += 4;
 							}
 #undef MG_PAIR_STEP
+#undef MG_PAIR_STEP_CORE
+#undef MG_PAIR_STEP_PRED
 						}
 						__syncwarp();
 						k.pos += 2u * pairs;

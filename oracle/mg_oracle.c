@@ -41,10 +41,19 @@ enum {
 };
 _Static_assert(S_TOTAL == MGO_NUM_PROBS, "slot map must cover the reference model");
 
+/* Literal context bits (lc).  The reference is fixed at lc = lp = pb = 0 (its todos: src/lzma_packet_encoder.c:17,
+ * 44,113); with lc > 0 the literal coder of LZMA picks one of 1 << lc tables by the top lc bits of the previous
+ * byte.  Table 0 keeps the reference's place, tables 1.. follow the reference's model.  Process-global, 0 by default;
+ * pinned, for want of a reference, by decoding the streams with liblzma (tests/test_oracle_golden.py). */
+#define MGO_MAX_LC 4
+static unsigned g_lc = 0;
+void mgo_set_lc(unsigned lc) { g_lc = lc > MGO_MAX_LC ? MGO_MAX_LC : lc; }
+unsigned mgo_get_lc(void) { return g_lc; }
+
 typedef struct {
 	const uint8_t* data;
 	size_t n;
-	uint16_t p[S_TOTAL];
+	uint16_t p[S_TOTAL + ((1 << MGO_MAX_LC) - 1) * 768];
 	uint8_t ctx;
 	uint32_t rep[4];
 	size_t pos;
@@ -180,10 +189,18 @@ static void model_init(Model* m, const uint8_t* data, size_t n)
 {
 	m->data = data;
 	m->n = n;
-	for (int i = 0; i < S_TOTAL; i++) m->p[i] = 1024; /* probability.h:7 */
+	for (size_t i = 0; i < sizeof(m->p) / sizeof(m->p[0]); i++) m->p[i] = 1024; /* probability.h:7 */
 	m->ctx = 0;
 	memset(m->rep, 0, sizeof(m->rep));
 	m->pos = 0;
+}
+
+/* first slot of the literal table the packet at m->pos uses: the top lc bits of the previous byte (0 before byte 0) */
+static unsigned literal_base(const Model* m)
+{
+	if (g_lc == 0 || m->pos == 0) return S_LIT;
+	unsigned t = m->data[m->pos - 1] >> (8 - g_lc);
+	return t == 0 ? S_LIT : S_TOTAL + (t - 1) * 768;
 }
 
 /* probability_model.c:5-15 */
@@ -296,7 +313,7 @@ static void code_packet(Model* m, Sink* s, MgoPacket pk)
 				slot += (1 + mbit) << 8;
 				matched = (mbit == bit);
 			}
-			code_bit(m, s, S_LIT + slot, bit);
+			code_bit(m, s, literal_base(m) + slot, bit);
 			node = (node << 1) | bit;
 		}
 		break;
@@ -366,7 +383,7 @@ void mgo_model_after_prefix(const uint8_t* data, size_t n, const MgoPacket* slab
 	model_init(&m, data, n);
 	sink_init(&s, SINK_COST);
 	while (m.pos < stop) code_packet(&m, &s, slab[m.pos]);
-	memcpy(out->probs, m.p, sizeof(m.p));
+	memcpy(out->probs, m.p, sizeof(out->probs)); /* the reference-layout part (lc = 0 tables) */
 	out->ctx_state = m.ctx;
 	memcpy(out->dists, m.rep, sizeof(m.rep));
 	out->position = m.pos;
@@ -394,7 +411,7 @@ size_t mgo_encode_slab(const uint8_t* data, size_t n, const MgoPacket* slab, uin
 	sink_init(&s, SINK_RC);
 	s.out = out;
 	s.out_cap = cap;
-	rc_put(&s, 0); /* props: (pb*5+lp)*9+lc with lc=lp=pb=0 */
+	rc_put(&s, (uint8_t)g_lc); /* props: (pb*5+lp)*9+lc with lp=pb=0 */
 	uint32_t dict = 0x400000;
 	for (int i = 0; i < 4; i++) rc_put(&s, (uint8_t)(dict >> (8 * i)));
 	/* the reference writes htole32(size) widened to 8 bytes: high word is always zero */
@@ -648,7 +665,7 @@ static uint32_t literal_price(const Model* m)
 			slot += (1 + mbit) << 8;
 			matched = (mbit == bit);
 		}
-		c += bit_price(m, S_LIT + slot, bit);
+		c += bit_price(m, literal_base(m) + slot, bit);
 		node = (node << 1) | bit;
 	}
 	return c;

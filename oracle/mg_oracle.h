@@ -105,6 +105,10 @@ int mgo_slab_valid(const uint8_t* data, size_t n, const MgoPacket* slab);
  * the bigram (0 = all).  Process-global, off by default; checks mg_ctx_set_finder_limits. */
 void mgo_set_finder_limits(size_t window, uint32_t max_occ);
 
+/* Literal context bits, 0..4 (0 = the reference).  Process-global. */
+void mgo_set_lc(unsigned lc);
+unsigned mgo_get_lc(void);
+
 #ifdef __cplusplus
 }
 #endif

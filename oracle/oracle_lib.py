@@ -159,6 +159,12 @@ class Port(_Lib):
         L.mgo_slab_valid.argtypes = [vp, sz, vp]
         L.mgo_set_finder_limits.restype = None
         L.mgo_set_finder_limits.argtypes = [sz, C.c_uint32]
+        L.mgo_set_lc.restype = None
+        L.mgo_set_lc.argtypes = [C.c_uint]
+
+    def set_lc(self, lc: int = 0) -> None:
+        """Literal context bits (process-global; 0 = the reference)."""
+        self.lib.mgo_set_lc(lc)
 
     def set_finder_limits(self, window: int = 0, max_occ: int = 0) -> None:
         """Process-global: 0, 0 restores the reference's semantics."""
