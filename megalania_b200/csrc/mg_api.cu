@@ -135,8 +135,8 @@ struct mg_ctx {
 	uint32_t* d_occ_start = nullptr;  // 65537
 	uint32_t* d_occ = nullptr;        // n
 	uint32_t* d_trans = nullptr;
-	uint32_t* d_trans2 = nullptr;
 	uint32_t* d_recip = nullptr;
+	uint4* d_litq = nullptr;          // literal queues, one per whole 32-byte window (litq_build_kernel)
 	Tables tables{};
 	int sm_count = 0;
 	double index_ms = 0;
@@ -269,31 +269,42 @@ extern "C" MG_API int mg_ctx_create(const uint8_t* data, size_t n, LZMAPropertie
 		std::vector<uint32_t> price(2048);
 		price[0] = 0;
 		for (int i = 1; i < 2048; i++) price[i] = (uint32_t)(-(long)(std::log2((double)i / 2048.0) * 2048.0));
-		std::vector<uint32_t> trans(4096);
-		for (uint32_t p = 0; p < 2048; p++) {
-			trans[p] = (p + ((2048u - p) >> 5)) | (price[p] << 16);                        // bit 0
-			trans[2048 + p] = (p - (p >> 5)) | (price[(2048u - p) & 2047u] << 16);        // bit 1
-		}
-		trans[0] = 0;  // probability 0 never occurs in a model: (0, bit 0) is a zero-price fixed point (the spare slot's value)
-		// two steps on one slot (pair steps of the literal walk): bits (a, b) in that order
-		std::vector<uint32_t> trans2(8192, 0);
-		for (uint32_t ab = 0; ab < 4; ab++)
-			for (uint32_t p = 1; p < 2048; p++) {
-				const uint32_t s1 = trans[((ab >> 1) << 11) | p], p1 = s1 & 0xffffu;
-				const uint32_t s2 = trans[((ab & 1) << 11) | p1];
-				trans2[(ab << 11) | p] = (s2 & 0xffffu) | (((s1 >> 16) + (s2 >> 16)) << 16);
+		// sections of 2048 entries indexed by p; entry = stored probability after (p << PROB_SHIFT) | price << 16
+		auto step = [&](uint32_t p, uint32_t bit, uint32_t& cost) {
+			cost += bit ? price[(2048u - p) & 2047u] : price[p];
+			return bit ? p - (p >> 5) : p + ((2048u - p) >> 5);
+		};
+		std::vector<uint32_t> trans(TRANS_WORDS, 0);
+		for (uint32_t p = 1; p < 2048; p++) {
+			for (uint32_t bit = 0; bit < 2; bit++) {
+				uint32_t cost = 0;
+				const uint32_t p1 = step(p, bit, cost);
+				trans[bit * 2048 + p] = (p1 << PROB_SHIFT) | (cost << 16);
 			}
+			// two steps on one slot (literal queues): bits (a, b) in that order
+			for (uint32_t ab = 0; ab < 4; ab++) {
+				uint32_t cost = 0;
+				const uint32_t p2 = step(step(p, ab >> 1, cost), ab & 1, cost);
+				trans[(2 + ab) * 2048 + p] = (p2 << PROB_SHIFT) | (cost << 16);
+			}
+		}
+		// probability 0 never occurs in a model: entry 0 of every section is a zero-price fixed point (the spare
+		// slots' value, see the slot map in mg_device.cuh)
 		std::vector<uint32_t> recip(RECIP_ENTRIES, 0);
 		for (uint32_t i = 1; i < RECIP_ENTRIES; i++) recip[i] = 0xffffffffu / i + 1u;
-		CUB(pool_malloc(&ctx->d_trans, 4096 * sizeof(uint32_t)));
-		CUB(pool_malloc(&ctx->d_trans2, 8192 * sizeof(uint32_t)));
+		CUB(pool_malloc(&ctx->d_trans, TRANS_WORDS * sizeof(uint32_t)));
 		CUB(pool_malloc(&ctx->d_recip, RECIP_ENTRIES * sizeof(uint32_t)));
-		CUB(cudaMemcpyAsync(ctx->d_trans, trans.data(), 4096 * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
-		CUB(cudaMemcpyAsync(ctx->d_trans2, trans2.data(), 8192 * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+		CUB(cudaMemcpyAsync(ctx->d_trans, trans.data(), TRANS_WORDS * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
 		CUB(cudaMemcpyAsync(ctx->d_recip, recip.data(), RECIP_ENTRIES * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+		const uint32_t nwin = (uint32_t)(n / 32);
+		if (nwin != 0 && !getenv("MEGALANIA_NO_LITQ")) {
+			CUB(pool_malloc(&ctx->d_litq, (size_t)nwin * 64 * sizeof(uint4)));
+			litq_build_kernel<<<(nwin + 7) / 8, 256, 0, ctx->stream>>>(ctx->d_data, (uint32_t)n, nwin, ctx->d_litq);
+			CUB(cudaGetLastError());
+		}
 		CUB(cudaStreamSynchronize(ctx->stream));
 		ctx->tables.trans = ctx->d_trans;
-		ctx->tables.trans2 = ctx->d_trans2;
+		ctx->tables.litq = ctx->d_litq;
 		ctx->tables.recip = ctx->d_recip;
 		rc = build_index(ctx);
 #undef CUB
@@ -318,8 +329,8 @@ extern "C" MG_API void mg_ctx_destroy(mg_ctx* ctx)
 	pool_free(ctx->d_occ_start);
 	pool_free(ctx->d_occ);
 	pool_free(ctx->d_trans);
-	pool_free(ctx->d_trans2);
 	pool_free(ctx->d_recip);
+	pool_free(ctx->d_litq);
 	if (ctx->stream) cudaStreamDestroy(ctx->stream);
 	delete ctx;
 }
@@ -467,7 +478,7 @@ extern "C" MG_API int mg_score_slabs(mg_ctx* ctx, const LZMAPacket* slabs, size_
 static void export_model(const Record& r, mg_model_dump* out)
 {
 	for (int i = 0; i < 2615; i++) out->probs[i] = 1024;
-	auto put = [&](uint32_t ref_index, uint32_t slot) { out->probs[ref_index] = r.probs[slot]; };
+	auto put = [&](uint32_t ref_index, uint32_t slot) { out->probs[ref_index] = (uint16_t)(r.probs[slot] >> PROB_SHIFT); };
 	for (uint32_t node = 0; node < 768; node++)
 		if (node & 0xff) put(node, lit_slot(node));  // node 0 of each tree is never coded
 	const uint32_t ref_len[2] = {768, 768 + 514};

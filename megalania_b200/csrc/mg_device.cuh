@@ -22,47 +22,70 @@ constexpr uint32_t T_INVALID = 0, T_LITERAL = 1, T_MATCH = 2, T_SHORT_REP = 3, T
 
 // ---- slot map at lc = lp = pb = 0 (only the reachable slots of src/lzma_state.h:15-55) ----
 //
-// Literal trees (plain, matched with match bit 0, matched with match bit 1; src/lzma_state.h:47-50):
-// a literal is priced by nine lanes at once (is_match + one lane per tree depth), so the layout is
-// chosen for shared-memory banks, not for the reference's node order.  Each tree is cut by the top
-// two bits of the byte into four 64-node sub-trees, one per 128-byte row, stored in heap order:
-// depth d (2..7) of every row then lives in words [2^(d-3), 2^(d-2)) of the row - the six depth
-// lanes always hit six different banks.  Depths 0 and 1 (9 slots) sit in a small block placed
-// over the deepest level's banks (that lane covers 16 banks, so a clash is a 1-in-16 event).
-// The natural layout measured 1.84 wavefronts per probability access on the 1 MiB corpus.
+// Probabilities are stored PRE-SHIFTED (p << 2, the byte offset of p's entry in a transition-table section):
+// a table address is then one three-input add, section + stored probability + table base.
+//
+// Plain literal tree (variant 0 of src/lzma_state.h:47-50) - the "ownership" block, 8 rows of 128 bytes:
+// every slot a run of plain literals touches sits in a fixed shared-memory BANK, and in the literal fast
+// path (walk_window in mg_kernels.cuh) lane L is the only lane that touches bank L.  The lanes then share
+// nothing: no bank conflicts on probabilities, no ordering between lanes, and all updates of one slot
+// come from one lane in input order.
+//   bank 0        is_match[0]                       (row 1; touched by every literal)
+//   bank 1        tree depth 0 (the root)           (row 0, one slot per word)
+//   banks 2-3     depth 1, banks 4-7 depth 2, banks 8-15 depth 3
+//   banks 16-31   depth 4 (row 0), depth 5 (row 1), depth 6 (rows 2-3), depth 7 (rows 4-7); the bank is
+//                 16 + four prefix bits XOR a per-depth constant, so that the nodes one byte value touches at
+//                 depths 4..7 fall into different banks for the byte values that come in runs
+//   row 0, odd slots: one spare slot per bank, always 0 - what a lane with nothing to do in a round
+//                 "updates" (transition-table entry 0 maps probability 0 to itself at price 0)
+//   rows 1-7, banks 0-15: the small per-state arrays (never touched by the fast path)
+// Matched-literal trees (variants 1, 2) are in plain heap order.
 constexpr uint32_t LEN_LOW = 2, LEN_MID = 10, LEN_HIGH = 18, LEN_SLOTS = 274;
-constexpr uint32_t S_LIT = 0;                       // [3 trees][4 rows][64]: slot 0 of each row unused
-constexpr uint32_t S_LIT01 = 768 + 40;              // depth 0: [3], depth 1 (+4): [3][2]; banks 20..25 of the deepest level
-constexpr uint32_t S_ISMATCH = S_LIT01 + 22;        // [12]; is_match[0] is touched by every literal of a run: bank 31.
-                                                    // (these two offsets minimise the clashes simulated over the 1 MiB corpus:
-                                                    // 1.05 wavefronts per access instead of 1.30)
-constexpr uint32_t S_ISREP = S_ISMATCH + 12;
+constexpr uint32_t PROB_SHIFT = 2;
+constexpr uint32_t PROB_INIT = 1024u << PROB_SHIFT;
+constexpr uint32_t S_LIT0 = 0;                      // 512 slot spaces, see lit0_slot()
+constexpr uint32_t S_ISMATCH = 64;                  // [12]; is_match[0] in bank 0
+constexpr uint32_t S_ISREP = 128;
 constexpr uint32_t S_ISREPG0 = S_ISREP + 12;
-constexpr uint32_t S_ISREPG1 = S_ISREPG0 + 12;
+constexpr uint32_t S_ISREPG1 = 192;
 constexpr uint32_t S_ISREPG2 = S_ISREPG1 + 12;
-constexpr uint32_t S_ISREP0LONG = S_ISREPG2 + 12;
-constexpr uint32_t S_LEN = S_ISREP0LONG + 12;       // choice1, choice2, low[8], mid[8], high[256]
+constexpr uint32_t S_ISREP0LONG = 256;
+constexpr uint32_t S_LITV = 512;                    // [2 variants][256] heap order, node 0 unused
+constexpr uint32_t S_LEN = S_LITV + 512;            // choice1, choice2, low[8], mid[8], high[256]
 constexpr uint32_t S_REPLEN = S_LEN + LEN_SLOTS;
 constexpr uint32_t S_POSSLOT = S_REPLEN + LEN_SLOTS;  // [4][64]
 constexpr uint32_t S_ALIGN = S_POSSLOT + 256;       // [16]
 constexpr uint32_t S_POSCODER = S_ALIGN + 16;       // [115]
 constexpr uint32_t S_TOTAL = S_POSCODER + 115;
-constexpr uint32_t S_DUMMY = S_TOTAL;               // spare slot: the address lanes without a slot class point at (never coded)
-constexpr uint32_t S_COUNT = ((S_TOTAL + 1 + 7) / 8) * 8;  // probabilities stored per record (16-byte multiple)
-// is_match[0] is touched by every literal of a run: keep it off the banks of the shallow tree levels
-static_assert(((S_ISMATCH / 2) % 32) >= 16, "is_match[0] must only share a bank with the deepest literal tree level");
+constexpr uint32_t S_COUNT = ((S_TOTAL + 7) / 8) * 8;  // probabilities stored per record (16-byte multiple)
+constexpr uint32_t S_DUMMY = 1;                     // bank 0's spare slot: the address lanes without a slot class point at (never coded)
+// per-depth XOR constants of the deep levels (bits of the prefix that select the bank), chosen by simulating
+// the lanes' queue lengths over the 1 MiB mixed corpus: runs of 0x00, 0xff, ' ', '0', '-', '=', 0x90, 0xcc ...
+// keep their four deep nodes in four different banks
+constexpr uint32_t LITX4 = 0, LITX5 = 13u << 1, LITX6 = 2u << 1, LITX7 = 11u << 1;
+static_assert(S_ISMATCH % 64 == 0 && S_ISREP % 64 == 0 && S_ISREPG1 % 64 == 0 && S_ISREP0LONG % 64 == 0, "small arrays sit in banks 0-15");
+
+// Slot of node (1 << depth | prefix) of the plain literal tree.
+__host__ __device__ inline uint32_t lit0_slot(uint32_t depth, uint32_t prefix)
+{
+	if (depth <= 3) return 2u * ((1u << depth) | prefix);
+	if (depth == 4) return 2u * (16u + (prefix ^ LITX4));
+	const uint32_t u = prefix ^ (depth == 5 ? LITX5 : depth == 6 ? LITX6 : LITX7);
+	if (depth == 5) return 64u + 32u + u;
+	if (depth == 6) return 128u + 32u + u + (u & 32u);
+	return 256u + 32u + u + (u & 0x60u);
+}
 
 // Slot of literal-tree node `node` = variant << 8 | (1 << depth | prefix), the reference's index
 // into its 0x300 literal probabilities (src/lzma_packet_encoder.c:106-136).
 __host__ __device__ inline uint32_t lit_slot(uint32_t node)
 {
 	const uint32_t v = node >> 8, i = node & 0xff;
-	if (i < 2) return S_LIT01 + v;
-	if (i < 4) return S_LIT01 + 4 + 2 * v + (i & 1);
-	uint32_t d = 2;
+	if (v != 0) return S_LITV + (v - 1) * 256 + i;
+	if (i == 0) return S_DUMMY;
+	uint32_t d = 0;
 	while ((i >> (d + 1)) != 0) d++;
-	const uint32_t top2 = (i >> (d - 2)) & 3, sub = (1u << (d - 2)) | (i & ((1u << (d - 2)) - 1));
-	return S_LIT + v * 256 + top2 * 64 + sub;
+	return S_LIT0 + lit0_slot(d, i - (1u << d));
 }
 
 // Working set of one warp == checkpoint record in HBM.
@@ -201,20 +224,24 @@ struct SmemU32 {
 	__device__ __forceinline__ void set(uint32_t i, uint32_t v) const { sts_u32(a + 4 * i, v); }
 };
 
-// Transition table, 4096 x u32, indexed by (bit << 11) | p:
-//   low 16 bits  = the adapted probability  (src/probability_model.c:5-15)
-//   high 16 bits = the price of coding `bit` at probability p (src/perplexity_encoder.c:6-10)
+// Transition tables, six sections of 2048 x u32 (8 KB each), indexed by the stored probability (p << 2 = the
+// entry's byte offset inside a section):
+//   section 0, 1      one step, bit 0 / 1
+//   section 2 + ab    two steps on one slot, bits (a, b) in that order
+//   low 16 bits  = the probability after the step(s), stored form   (src/probability_model.c:5-15)
+//   high 16 bits = the price of the step(s) (src/perplexity_encoder.c:6-10; two steps: at most 45 056)
 // One shared-memory load replaces the price lookup plus the shift/add/select update.
-__device__ __forceinline__ void code_bit(SmemU16 probs, SmemU32 trans, uint32_t slot, uint32_t bit11, uint32_t& acc)
+constexpr uint32_t TRANS_SECTION_SHIFT = 13, TRANS_SECTIONS = 6, TRANS_WORDS = TRANS_SECTIONS * 2048;
+__device__ __forceinline__ void code_bit(SmemU16 probs, SmemU32 trans, uint32_t slot, uint32_t bit, uint32_t& acc)
 {
-	const uint32_t t = trans.get(probs.get(slot) | bit11);
+	const uint32_t t = lds_u32(trans.a + (bit << TRANS_SECTION_SHIFT) + probs.get(slot));
 	acc += t >> 16;
 	probs.set(slot, t);
 }
 
 __device__ __forceinline__ uint32_t bit_price(SmemU16 probs, SmemU32 trans, uint32_t slot, uint32_t bit)
 {
-	return trans.get(probs.get(slot) | (bit << 11)) >> 16;
+	return lds_u32(trans.a + (bit << TRANS_SECTION_SHIFT) + probs.get(slot)) >> 16;
 }
 
 // ---- lane -> (slot, bit) maps ----------------------------------------------------------------
@@ -300,12 +327,7 @@ __device__ __forceinline__ void lit_event(uint32_t depth, uint32_t byte, bool ma
 	bit = (byte >> (7 - depth)) & 1;
 	uint32_t v = 0;
 	if (matched_mode && (mbyte >> (8 - depth)) == top) v = 1u + ((mbyte >> (7 - depth)) & 1);
-	if (depth == 0)
-		slot = S_LIT01 + v;
-	else if (depth == 1)
-		slot = S_LIT01 + 4 + 2 * v + top;
-	else
-		slot = S_LIT + v * 256 + (byte >> 6) * 64 + ((1u << (depth - 2)) | (top & ((1u << (depth - 2)) - 1)));
+	slot = v == 0 ? S_LIT0 + lit0_slot(depth, top) : S_LITV + (v - 1) * 256 + ((1u << depth) | top);
 }
 
 // The length coder's three trees (src/lzma_packet_encoder.c:42-63) as one: nb bits of value w
@@ -513,15 +535,17 @@ __device__ __forceinline__ uint32_t apply_packet(int lane, SmemU16 probs, SmemU3
 	// update and the model bookkeeping into every divergent lane group (measured: that tail ran
 	// with ~3 active lanes, about ten times per packet).
 	__syncwarp();
-	if (active) code_bit(probs, trans, slot, bit << 11, acc);
+	if (active) code_bit(probs, trans, slot, bit, acc);
 	if (lane == 0) acc += dp.direct << 11;  // src/perplexity_encoder.c:12-17
 	model_advance(m, type, len, dist);
 	return __popc(__ballot_sync(FULL, active));
 }
 
-__device__ __forceinline__ void model_init(int lane, SmemU16 probs, Model& m)
+// `half` = the stored form of probability 1/2 (PROB_INIT in the scoring kernels, 1024 in the range coder);
+// the spare slots of row 0 stay 0
+__device__ __forceinline__ void model_init(int lane, SmemU16 probs, Model& m, uint32_t half = PROB_INIT)
 {
-	for (uint32_t i = (uint32_t)lane; i < S_COUNT; i += 32) probs.set(i, 1024);
+	for (uint32_t i = (uint32_t)lane; i < S_COUNT; i += 32) probs.set(i, (i < 64 && (i & 1)) ? 0u : half);
 	m.pos = m.pidx = m.ctx = 0;
 	m.rep0 = m.rep1 = m.rep2 = m.rep3 = 0;
 	__syncwarp();
@@ -541,8 +565,8 @@ struct Window {
 	uint32_t base;        // multiple of 32; WINDOW_NONE = nothing loaded
 	uint32_t pf_base;     // window being copied into the warp's staging area by cp.async (WINDOW_NONE = none)
 	uint32_t litmask;     // bit i: slot base+i is a canonical LITERAL
-	uint32_t pairs;       // != 0: enough literals in the window for pair steps to repay the event mirror
-	uint32_t ev_base;     // window base | 1 literal events mirrored | 2 MATCH descriptors mirrored (see window_events / window_matches)
+	uint32_t md_base;     // window whose MATCH descriptors are mirrored in shared memory (see window_matches)
+	uint32_t q_base;      // window whose literal queue is staged, or on its way, in shared memory (see walk_window)
 };
 constexpr uint32_t WINDOW_NONE = 0x7fffffe0u;  // never within 32 of a real position (inputs < 2 GiB... see mg_ctx_create)
 
@@ -600,7 +624,6 @@ __device__ __forceinline__ void window_seek(int lane, Window& w, const uint64_t*
 	window_prefetch(lane, slab, data, n, want + 32, stage);
 	w.pf_base = want + 32;
 	w.litmask = __ballot_sync(FULL, (w.meta & 0xffffu) == META_LITERAL);
-	w.pairs = __popc(w.litmask) >= 16 ? 1u : 0u;
 }
 
 __device__ __forceinline__ uint32_t window_meta(const Window& w, uint32_t pos)

@@ -31,7 +31,7 @@ struct FindScratch {
 	uint64_t ent_pk[MAX_K];
 	uint32_t ent_price[MAX_K];
 	// [0] match lengths, [1] rep lengths; index len-2.  Only live during a find: between finds the
-	// walk keeps its literal-event mirror here (EVENT_* below, mg_kernels.cuh window_events()).
+	// walk keeps its window staging here (see below).
 	uint32_t len_price[2][MAX_MATCH - 1];
 	uint32_t hkey[MAX_K];                  // heap order -> price << 5 | entry index
 	uint8_t pop_order[MAX_K];              // entry indices, worst first
@@ -41,14 +41,13 @@ struct FindScratch {
 	uint32_t chunks;      // 32-occurrence steps the last find took (its cost in the step budget)
 };
 
-// Literal-event mirror: for each of the nine literal slot classes a row of 32 events (one per slot of the
-// current slab window; even window positions in columns 0..15, odd ones in columns 16..31, see
-// window_events() in mg_kernels.cuh) + 4 words of padding, so that a lane fetches the events of four pairs
-// with one 16-byte load and the rows start on different banks.
-constexpr uint32_t EVENT_ROW_WORDS = 36, EVENT_LANES = 9, EVENT_PAIR_COLUMNS = 16;
-// ... followed by one 16-byte MATCH descriptor per slot of the window (window_matches()).
-constexpr uint32_t MATCH_DESC_OFFSET = EVENT_LANES * EVENT_ROW_WORDS * 4;
-// ... followed by the staging area of the NEXT window: 32 slab slots (8 B) + 32 data bytes, filled by cp.async.
+// Between finds the length-price tables double as the walk's staging area (mg_kernels.cuh):
+//   [0, 1024)     the literal queue of the current window: two blocks of 32 lanes x 16 bytes (eight u16 entries
+//                 each), copied from the context's queue table by cp.async (walk_window())
+//   [1024, 1536)  one 16-byte MATCH descriptor per slot of the window (window_matches())
+//   [1536, 1824)  the NEXT window's 32 slab slots (8 B) + 32 data bytes, filled by cp.async (window_prefetch())
+constexpr uint32_t QUEUE_ROUNDS = 16, QUEUE_BYTES = 32 * QUEUE_ROUNDS * 2;
+constexpr uint32_t MATCH_DESC_OFFSET = QUEUE_BYTES;
 constexpr uint32_t STAGE_OFFSET = MATCH_DESC_OFFSET + 32 * 16;
 constexpr uint32_t STAGE_BYTES = 32 * 8 + 32;
 static_assert(STAGE_OFFSET % 16 == 0 && STAGE_OFFSET + STAGE_BYTES <= sizeof(uint32_t) * 2 * (MAX_MATCH - 1), "window mirrors must fit in len_price");

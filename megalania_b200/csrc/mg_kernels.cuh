@@ -5,21 +5,19 @@
 
 namespace mg {
 
-// One CTA of 27 warps per SM: 27 models + the transition tables (16 KB single-step, 32 KB two-step, see
-// CtaShared) fill the 227 KB of shared memory; 864 threads leave 72 registers per thread.  The walk is bound by
-// shared-memory wavefronts; literal runs are priced two literals per warp instruction, which doubles the work a
-// warp has in flight and pays for the five warps the two-step table displaces.
+// One CTA of 26 warps per SM: 26 models + the transition tables (48 KB, see mg_device.cuh) fill the 227 KB of
+// shared memory.  The walk is bound by shared-memory wavefronts; whole windows of plain literals are priced from
+// per-lane queues built once per input (walk_window()).
 #ifndef MG_WARPS_PER_CTA
-#define MG_WARPS_PER_CTA 27
+#define MG_WARPS_PER_CTA 26
 #endif
 constexpr int WARPS_PER_CTA = MG_WARPS_PER_CTA;
 constexpr int CTA_THREADS = WARPS_PER_CTA * 32;
 constexpr uint32_t RECIP_ENTRIES = 288;
-constexpr uint32_t PAIR_LANES = 0x3ffffu;  // lanes 0..17: the two literals of a pair step
-// Kernel experiments (tools/variants.sh): 0 = predicated idle lanes, no barrier between pairs (the product);
-// bit 0 = idle lanes parked on the spare slot instead, bit 1 = a warp barrier after every pair.
-#ifndef MG_PAIR_VARIANT
-#define MG_PAIR_VARIANT 0
+// Kernel experiments (tools/variants.sh): 0 = the product; bit 0 = literal queues off (every literal takes the
+// single-step path).
+#ifndef MG_WALK_VARIANT
+#define MG_WALK_VARIANT 0
 #endif
 
 struct ChainStats {
@@ -64,49 +62,45 @@ struct EditLog {
 	bool overflow;
 };
 
-// Dynamic shared memory of one CTA.
-struct WarpShared {
+// Dynamic shared memory of one CTA.  A warp's block starts on a 128-byte boundary with its record, so that the
+// record's rows are bank rows (slot map in mg_device.cuh).
+struct alignas(128) WarpShared {
 	Record rec;
 	FindScratch fs;
 	uint64_t bar;
 	ChainStats stats;    // counters of the running launch (kept out of the register file; lane 0 only)
 };
-// The transition tables span eight 8 KB sections so that an event's top three bits ARE its section
-// (table byte offset = (event >> 16) & 0xE000, see window_events()):
-//   section 0, 1   single step, bit 0 / 1            trans[bit << 11 | p]            (code_bit())
-//   section 2, 3   not table: reciprocals, lane constants and the first two warps' blocks live there
-//   section 4..7   two steps on one slot, bits (a, b)  trans2[a << 12 | b << 11 | p]:  low 16 bits the
-//                  probability after both steps, high 16 bits the sum of both prices (at most 45 056)
-constexpr int HOLE_WARPS = WARPS_PER_CTA < 2 ? WARPS_PER_CTA : 2;
-struct CtaShared {
-	uint32_t trans[4096];
+struct alignas(128) CtaShared {
+	uint32_t trans[TRANS_WORDS];
 	uint32_t recip[RECIP_ENTRIES];
 	uint4 lane_tab[32];    // match_lane_const() per lane
-	WarpShared hole_warp[HOLE_WARPS];
-	unsigned char hole_pad[16384 - sizeof(uint32_t) * RECIP_ENTRIES - sizeof(uint4) * 32 - sizeof(WarpShared) * HOLE_WARPS];
-	uint32_t trans2[8192];
-	WarpShared rest_warp[WARPS_PER_CTA > 2 ? WARPS_PER_CTA - 2 : 1];
+	WarpShared warp[WARPS_PER_CTA];
 };
-static_assert(sizeof(WarpShared) % 16 == 0, "per-warp shared block must keep the record 16-byte aligned");
-static_assert(offsetof(CtaShared, hole_warp) % 16 == 0 && offsetof(CtaShared, rest_warp) % 16 == 0, "record alignment");
-static_assert(offsetof(CtaShared, trans) == 0 && offsetof(CtaShared, trans2) == 32768, "table sections");
+static_assert(offsetof(WarpShared, rec) == 0 && sizeof(Record) % 128 == 0, "record rows must be bank rows");
+static_assert(offsetof(CtaShared, warp) % 128 == 0, "record alignment");
 static_assert(sizeof(CtaShared) <= 232448, "one CTA must fit the 227 KB of shared memory");
 
-__device__ __forceinline__ WarpShared* warp_block(CtaShared* sh, int warp)
-{
-	return warp < HOLE_WARPS ? &sh->hole_warp[warp] : &sh->rest_warp[warp - HOLE_WARPS];
-}
+__device__ __forceinline__ WarpShared* warp_block(CtaShared* sh, int warp) { return &sh->warp[warp]; }
+
+// One literal queue per 32-byte window of the input, built once per context (litq_build_kernel): for each lane the
+// up to QUEUE_ROUNDS table steps it owes the window when all 32 slots hold plain literals and the automaton is in
+// state 0.  Layout [window][2 blocks][32 lanes] x 16 bytes; entry = u16:
+//   bits 0-11   byte offset of the probability in the record (lane L only ever names slots in bank L)
+//   bit  12     lane 0, entry 0 only: reserved
+//   bits 13-15  transition-table section (one step: bit; two steps on the slot: 2 + first bit << 1 + second bit)
+// Entries a lane does not need name its spare slot (value 0) in section 0: table entry 0 is a zero-price fixed point.
+// A window some lane would need more rounds for has 0xffff in lane 0's first entry: it takes the single-step path.
+constexpr uint32_t QUEUE_UNUSABLE = 0xffffu;
 
 struct Tables {
-	const uint32_t* trans;   // [4096] adapted probability | price << 16 (price: reference generate_table.py:7-9)
-	const uint32_t* trans2;  // [8192] two steps on one slot
+	const uint32_t* trans;   // [TRANS_WORDS] stored probability after | price << 16 (price: reference generate_table.py:7-9)
 	const uint32_t* recip;   // [RECIP_ENTRIES]
+	const uint4* litq;       // [windows][64] literal queues, or null
 };
 
 __device__ __forceinline__ void cta_tables_load(CtaShared* sh, const Tables& t)
 {
-	for (int i = threadIdx.x; i < 4096; i += blockDim.x) sh->trans[i] = t.trans[i];
-	for (int i = threadIdx.x; i < 8192; i += blockDim.x) sh->trans2[i] = t.trans2[i];
+	for (int i = threadIdx.x; i < (int)TRANS_WORDS; i += blockDim.x) sh->trans[i] = t.trans[i];
 	for (int i = threadIdx.x; i < (int)RECIP_ENTRIES; i += blockDim.x) sh->recip[i] = t.recip[i];
 	if (threadIdx.x < 32) {
 		const LaneConst c = match_lane_const((int)threadIdx.x);
@@ -178,8 +172,8 @@ __device__ __forceinline__ void log_put(int lane, EditLog& lg, uint32_t pos, uin
 }
 
 // ---- the walk ----------------------------------------------------------------------------------------
-// Everything a walking warp needs besides its registers.  Lane roles in the literal fast path:
-// lane 0 owns is_match[ctx], lanes 1..8 own literal-tree depth 0..7, lanes 9..31 sit literal runs out.
+// Everything a walking warp needs besides its registers.  Lane roles in the single-literal path:
+// lane 0 owns is_match[ctx], lanes 1..8 own literal-tree depth 0..7, lanes 9..31 sit it out.
 struct WalkEnv {
 	int lane;
 	SmemU16 probs;        // the model's probabilities
@@ -191,26 +185,25 @@ struct WalkEnv {
 	const uint64_t* __restrict__ slab;
 	const uint8_t* __restrict__ data;
 	const uint32_t* __restrict__ abs_dist;  // region merges: the distance a LONG_REP slot stood for in its owner chain, or null
+	const uint4* __restrict__ litq;         // the context's literal queues, or null
 	uint32_t n;
 	uint32_t trans_addr;  // shared address of trans[]
 	uint32_t lane_tab_addr;  // shared address of this lane's match_lane_const() entry
-	uint32_t ev_addr;        // shared address of the warp's literal-event mirror
-	uint32_t ev_pair_addr;   // ... of this lane's half row in it (pair steps: lanes 0..8 first, 9..17 second literal)
+	uint32_t ev_addr;        // shared address of the warp's staging area (literal queue, MATCH descriptors, next window)
 	uint32_t stage_addr;     // shared address of the next window's staging area
-	// literal fast path (see the slot map in mg_device.cuh): the lane's slot for data byte b is
-	//   lit_addr + 2 * (((b >> lit_sh) & lowmask) | (b & topmask))  (+ 2 * ctx on lane 0)
-	uint32_t lit_addr;    // shared address of this lane's first slot
-	uint32_t lit_sh;      // b >> lit_sh = tree prefix at this lane's depth
-	uint32_t bit_shl;     // b << bit_shl puts the lane's data bit at bit 11 (the table's bit position)
-	uint32_t lowmask;     // prefix bits that index inside the row
-	uint32_t topmask;     // 0xC0 on depths 2..7: the top two bits of b select the row
-	uint32_t bitmask;     // 0x800 on tree lanes
+	// single-literal path (slot map in mg_device.cuh): with u = ((b >> lit_sh) & lit_mask) ^ lit_x the lane's
+	// probability for data byte b lives at lit_addr + u + (u & lit_hm)  (+ 2 * ctx on lane 0); in matched mode a
+	// tree lane whose prefix agrees with the match byte uses litv_addr + 2 * (b >> lit_psh) + 512 * match bit
+	uint32_t lit_addr, lit_sh, lit_mask, lit_x, lit_hm;
+	uint32_t litv_addr, lit_psh;
+	uint32_t bit_shl;     // b << bit_shl puts the lane's data bit at bit 13 (the table's section bit)
+	uint32_t bitmask;     // 0x2000 on tree lanes
 	uint32_t ctxmask;     // ~0 on lane 0
 	bool lit_active;      // lanes 0..8
 };
 
 __device__ __forceinline__ WalkEnv make_env(int lane, WarpShared* ws, const CtaShared* sh, const uint64_t* slab,
-                                            const uint8_t* data, uint32_t n)
+                                            const uint8_t* data, uint32_t n, const uint4* litq)
 {
 	WalkEnv e;
 	e.lane = lane;
@@ -228,81 +221,39 @@ __device__ __forceinline__ WalkEnv make_env(int lane, WarpShared* ws, const CtaS
 	e.slab = slab;
 	e.data = data;
 	e.abs_dist = nullptr;
+	e.litq = (MG_WALK_VARIANT & 1) ? nullptr : litq;
 	e.n = n;
 	e.trans_addr = e.trans.a;
 	e.lane_tab_addr = cta_base + (uint32_t)offsetof(CtaShared, lane_tab) + 16u * (uint32_t)lane;
 	e.ev_addr = warp_base + (uint32_t)offsetof(WarpShared, fs) + (uint32_t)offsetof(FindScratch, len_price);
-	{
-		const uint32_t pl = lane < 2 * (int)EVENT_LANES ? (uint32_t)lane : 0u;
-		e.ev_pair_addr = e.ev_addr + 4u * EVENT_ROW_WORDS * (pl % EVENT_LANES) + 4u * EVENT_PAIR_COLUMNS * (pl / EVENT_LANES);
-	}
 	e.stage_addr = e.ev_addr + STAGE_OFFSET;
 	const bool tree = lane >= 1 && lane <= 8;
-	const uint32_t depth = tree ? (uint32_t)lane - 1 : 0;
-	uint32_t first = S_DUMMY;
+	const uint32_t d = tree ? (uint32_t)lane - 1 : 0;
+	// byte offsets, see lit0_slot(): depth <= 3 one slot per word (4 * node), depth 4 the same with the XOR,
+	// depth 5..7 u + (u & hm) with u = 2 * (prefix ^ x)
+	uint32_t first = S_DUMMY, sh_ = 8, mask = 0, x = 0, hm = 0;
 	if (lane == 0) first = S_ISMATCH;
-	else if (lane == 1) first = S_LIT01;
-	else if (lane == 2) first = S_LIT01 + 4;
-	else if (tree) first = S_LIT + (1u << (depth - 2));
+	else if (tree && d <= 3) { first = S_LIT0 + 2u * (1u << d); sh_ = 6 - d; mask = ((1u << d) - 1u) << 2; }
+	else if (tree && d == 4) { first = S_LIT0 + 32; sh_ = 2; mask = 0x3c; x = LITX4 << 2; }
+	else if (tree && d == 5) { first = S_LIT0 + 96; sh_ = 2; mask = 0x3e; x = LITX5 << 1; }
+	else if (tree && d == 6) { first = S_LIT0 + 160; sh_ = 1; mask = 0x7e; x = LITX6 << 1; hm = 64; }
+	else if (tree && d == 7) { first = S_LIT0 + 288; sh_ = 0; mask = 0xfe; x = LITX7 << 1; hm = 0xc0; }
 	e.lit_addr = e.probs.a + 2 * first;
-	e.lit_sh = tree ? 8u - depth : 8u;
-	e.lowmask = !tree || depth == 0 ? 0u : depth == 1 ? 1u : (1u << (depth - 2)) - 1u;
-	e.topmask = tree && depth >= 2 ? 0xC0u : 0u;
-	e.bitmask = tree ? 0x800u : 0u;
+	e.lit_sh = sh_;
+	e.lit_mask = mask;
+	e.lit_x = x;
+	e.lit_hm = hm;
+	e.litv_addr = e.probs.a + 2 * (S_LITV + (1u << d));
+	e.lit_psh = tree ? 8u - d : 8u;
+	e.bitmask = tree ? 0x2000u : 0u;
 	e.ctxmask = lane == 0 ? 0xffffffffu : 0u;
-	e.bit_shl = 12u - e.lit_sh;
+	e.bit_shl = 6u + d;
 	e.lit_active = lane <= 8;
-	// Opaque to the compiler on purpose: it otherwise re-derives these seven constants from
-	// threadIdx inside the literal loop (14 instructions per four literals) instead of keeping
-	// them in registers.
-	asm volatile("" : "+r"(e.lit_addr), "+r"(e.lit_sh), "+r"(e.bit_shl), "+r"(e.lowmask), "+r"(e.topmask), "+r"(e.bitmask),
-	             "+r"(e.ctxmask), "+r"(e.ev_pair_addr));
+	// Opaque to the compiler on purpose: it otherwise re-derives these constants from threadIdx inside the
+	// literal loop instead of keeping them in registers.
+	asm volatile("" : "+r"(e.lit_addr), "+r"(e.lit_sh), "+r"(e.lit_mask), "+r"(e.lit_x), "+r"(e.lit_hm), "+r"(e.bit_shl),
+	             "+r"(e.bitmask), "+r"(e.ctxmask));
 	return e;
-}
-
-// Literal events of the current window, for PAIR steps: two consecutive plain literals (window positions 2g and
-// 2g+1) priced by one warp instruction each, the first on lanes 0..8, the second on lanes 9..17 (slot classes as
-// in a single step: is_match, then one lane per tree depth).  Lane i prices nothing here: it turns ITS data
-// byte into the nine events the literal at window position i needs and stores them transposed - row = slot
-// class, first-literal events in columns 0..15, second-literal events in columns 16..31 - so that the run loop
-// costs each lane one 16-byte load per four pairs.
-//   event = shared address of the probability | table section << 29   (sections: CtaShared)
-// When both literals of a pair touch the SAME slot (always for is_match and the tree root, whenever their bit
-// prefixes agree deeper down) the second literal's lane applies both steps with one load from the two-step
-// table (section 4 | first bit << 1 | second bit), and the first literal's lane sits the pair out (event 0: its
-// loads and store are predicated off - several lanes parked on one spare slot measured as a two-way bank conflict
-// on every 16-bit access): per-slot order is the reference's, nothing is touched twice in a step.
-// Plain literals only (automaton state 0; src/lzma_packet_encoder.c:106-121).
-__device__ __forceinline__ void window_events(const WalkEnv& e, Window& w)
-{
-	__syncwarp();
-	const uint32_t b = (w.meta >> 16) & 0xffu;
-	const uint32_t other = __shfl_xor_sync(FULL, b, 1);  // the pair's other literal
-	const uint32_t second = (uint32_t)e.lane & 1u;
-	const uint32_t x = b ^ other;
-	const uint32_t out = e.ev_addr + 4u * (((uint32_t)e.lane >> 1) + EVENT_PAIR_COLUMNS * second);
-	const uint32_t idle = (MG_PAIR_VARIANT & 1) ? e.probs.a + 2 * S_DUMMY : 0u;
-	// same slot as the pair's other literal at tree depth d  <=>  the first d bits agree; the first literal's
-	// event is then 0 = "sit this pair out" (the second literal's lane steps the slot twice)
-	auto event = [&](uint32_t slot, uint32_t depth_bits, uint32_t bit_pos) -> uint32_t {
-		const bool same = (x >> (8 - depth_bits)) == 0;
-		const uint32_t own = (b >> bit_pos) & 1u, first = (other >> bit_pos) & 1u;
-		uint32_t ev = (e.probs.a + 2 * slot) | (own << 29);
-		if (same) ev = second ? (ev | 0x80000000u | (first << 30)) : idle;
-		return ev;
-	};
-	// is_match[0]: both bits 0, always the same slot
-	sts_u32(out + 0 * 4 * EVENT_ROW_WORDS, second ? ((e.probs.a + 2 * S_ISMATCH) | 0x80000000u) : idle);
-	sts_u32(out + 1 * 4 * EVENT_ROW_WORDS, event(S_LIT01, 0, 7));
-	sts_u32(out + 2 * 4 * EVENT_ROW_WORDS, event(S_LIT01 + 4 + (b >> 7), 1, 6));
-	const uint32_t row = S_LIT + (b >> 6) * 64;
-#pragma unroll
-	for (uint32_t d = 2; d < 8; d++) {
-		const uint32_t slot = row + ((1u << (d - 2)) | ((b >> (8 - d)) & ((1u << (d - 2)) - 1u)));
-		sts_u32(out + (d + 1) * 4 * EVENT_ROW_WORDS, event(slot, d, 7 - d));
-	}
-	w.ev_base = (w.ev_base & ~31u) == w.base ? (w.ev_base | 1u) : (w.base | 1u);
-	__syncwarp();
 }
 
 // MATCH descriptors of the current window: lane i turns ITS slot, if it holds a MATCH that is valid
@@ -319,7 +270,7 @@ __device__ __forceinline__ void window_matches(const WalkEnv& e, Window& w)
 		if (ok) d = match_desc(0, len, dist);
 		sts_v4(e.ev_addr + MATCH_DESC_OFFSET + 16u * (uint32_t)e.lane, d.F, d.G, d.amask | (d.direct << 26), dist);
 	}
-	w.ev_base = (w.ev_base & ~31u) == w.base ? (w.ev_base | 2u) : (w.base | 2u);
+	w.md_base = w.base;
 	__syncwarp();
 }
 
@@ -393,13 +344,13 @@ __device__ __forceinline__ void walker_init(const WalkEnv& e, Walker& k)
 	Model m;
 	model_init(e.lane, e.probs, m);
 	if (e.lane < 4) e.reps.set(e.lane, 0);
-	if (e.lane == 0) e.probs.set(S_DUMMY, 0);
 	__syncwarp();
 	k.pos = k.delta = k.ctx = k.mb = 0;
 	k.t = {0, 0, 0};
 	k.w.base = WINDOW_NONE;
 	k.w.pf_base = WINDOW_NONE;
-	k.w.ev_base = WINDOW_NONE;
+	k.w.md_base = WINDOW_NONE;
+	k.w.q_base = WINDOW_NONE;
 }
 
 __device__ __forceinline__ void walker_load(const WalkEnv& e, Walker& k, const Record* src, uint64_t* bar, uint32_t& parity)
@@ -413,7 +364,8 @@ __device__ __forceinline__ void walker_load(const WalkEnv& e, Walker& k, const R
 	k.t = {cost, 0, 0};
 	k.w.base = WINDOW_NONE;
 	k.w.pf_base = WINDOW_NONE;
-	k.w.ev_base = WINDOW_NONE;
+	k.w.md_base = WINDOW_NONE;
+	k.w.q_base = WINDOW_NONE;
 	k.mb = MB_UNKNOWN;
 }
 
@@ -512,6 +464,88 @@ __device__ __forceinline__ void ck_absolute(int lane, const CkMeta* meta, const 
 	cost = c;
 }
 
+// ---- a window of 32 plain literals -------------------------------------------------------------------
+// The queue of window w travels global -> shared memory by cp.async, one window ahead of the walk.
+__device__ __forceinline__ void queue_fetch(const WalkEnv& e, uint32_t w)
+{
+	const uint4* src = e.litq + (size_t)w * 64 + (uint32_t)e.lane;
+	const uint32_t dst = e.ev_addr + 16u * (uint32_t)e.lane;
+	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 512u), "l"(src + 32) : "memory");
+	asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+// One queue entry: the lane's probability at the entry's offset takes the one or two steps its section names.
+__device__ __forceinline__ void queue_round(uint32_t ev, uint32_t probs_a, uint32_t trans_a, uint32_t& acc)
+{
+	asm volatile(
+	    "{\n\t"
+	    ".reg .b32 pa, ta, pv, tr;\n\t"
+	    ".reg .b16 h;\n\t"
+	    "and.b32 pa, %1, 0x0FFE;\n\t"
+	    "add.u32 pa, pa, %2;\n\t"
+	    "ld.shared.u16 h, [pa];\n\t"
+	    "cvt.u32.u16 pv, h;\n\t"
+	    "and.b32 ta, %1, 0xE000;\n\t"
+	    "add.u32 ta, ta, %3;\n\t"
+	    "add.u32 ta, ta, pv;\n\t"
+	    "ld.shared.u32 tr, [ta];\n\t"
+	    "cvt.u16.u32 h, tr;\n\t"
+	    "st.shared.u16 [pa], h;\n\t"
+	    "shr.u32 tr, tr, 16;\n\t"
+	    "add.u32 %0, %0, tr;\n\t"
+	    "}"
+	    : "+r"(acc)
+	    : "r"(ev), "r"(probs_a), "r"(trans_a)
+	    : "memory");
+}
+
+// Prices the 32 plain literals of the current window (automaton state 0 before and after): lane L performs the
+// table steps of its own queue, all on slots of bank L (slot map in mg_device.cuh), so the lanes neither share
+// a bank nor an address and need no ordering among themselves; per slot the steps are in input order.
+// Returns false when the window has no usable queue (the caller then takes the literals one by one).
+__device__ __forceinline__ bool walk_window(const WalkEnv& e, Walker& k)
+{
+	const uint32_t w = k.w.base >> 5;
+	if (k.w.q_base != k.w.base) {
+		// nothing staged for this window (the first of a run): fetch it now.  A copy still in flight must have
+		// landed before another one is aimed at the same bytes.
+		asm volatile("cp.async.wait_group 0;" ::: "memory");
+		__syncwarp();
+		queue_fetch(e, w);
+		asm volatile("cp.async.wait_group 0;" ::: "memory");
+	}
+	__syncwarp();
+	const uint4 a = lds_v4(e.ev_addr + 16u * (uint32_t)e.lane);
+	const uint4 b = lds_v4(e.ev_addr + 512u + 16u * (uint32_t)e.lane);
+	const uint32_t head = __shfl_sync(FULL, a.x, 0) & 0xffffu;
+	__syncwarp();  // every lane holds its entries: the staging area may be overwritten
+	if (k.w.base + 64u <= e.n) {
+		queue_fetch(e, w + 1);
+		k.w.q_base = k.w.base + 32u;
+	} else {
+		k.w.q_base = WINDOW_NONE;
+	}
+	if (head == QUEUE_UNUSABLE) return false;
+	uint32_t acc = k.t.acc;
+	const uint32_t pa = e.probs.a, ta = e.trans_addr;
+#define MG_QUEUE_WORD(v)               \
+	queue_round((v), pa, ta, acc); \
+	queue_round((v) >> 16, pa, ta, acc)
+	MG_QUEUE_WORD(a.x);
+	MG_QUEUE_WORD(a.y);
+	MG_QUEUE_WORD(a.z);
+	MG_QUEUE_WORD(a.w);
+	MG_QUEUE_WORD(b.x);
+	MG_QUEUE_WORD(b.y);
+	MG_QUEUE_WORD(b.z);
+	MG_QUEUE_WORD(b.w);
+#undef MG_QUEUE_WORD
+	k.t.acc = acc;
+	__syncwarp();  // other paths reach these slots from other lanes
+	return true;
+}
+
 enum WalkMode { WALK_PLAIN = 0, WALK_REPAIR_HEAD = 1, WALK_REPAIR = 2 };
 enum WalkResult { WALK_DONE = 0, WALK_NEED_FIND = 1, WALK_ERROR = 2, WALK_REJOINED = 3, WALK_SUSPENDED = 4 };
 
@@ -540,7 +574,8 @@ __device__ __forceinline__ uint32_t walk(const uint32_t MODE, const WalkEnv& e, 
 				return WALK_SUSPENDED;
 		}
 		if (k.pos - k.w.base >= 32u) {
-			tally_flush(k.t);
+			// the per-lane sums are 32 bits wide: a lane adds at most ~10^5 per packet, so once per KiB of input is plenty
+			if (((k.pos ^ k.w.base) >> 10) != 0) tally_flush(k.t);
 			window_seek(e.lane, k.w, e.slab, e.data, e.n, k.pos, e.stage_addr);
 		}
 		uint32_t limit = k.w.base + 32 < stop_pos ? k.w.base + 32 : stop_pos;
@@ -554,119 +589,30 @@ __device__ __forceinline__ uint32_t walk(const uint32_t MODE, const WalkEnv& e, 
 			const uint32_t meta = window_meta(k.w, k.pos);
 			if (MODE != WALK_REPAIR_HEAD && (meta & 0xffffu) == META_LITERAL) {
 				const uint32_t ctx = k.ctx;
-				const uint32_t idx = k.pos - k.w.base;
-				if (ctx == 0 && (idx & 1u) == 0 && k.w.pairs) {
-					// ---- run of plain literals, two per step: lanes 0..8 price the literal at the even window
-					// position, lanes 9..17 the one after it, each lane on its slot class (is_match, one tree
-					// depth each); a slot both literals touch is stepped twice by the second literal's lane
-					// through the two-step table (see window_events) -----------------------------------------
-					uint32_t run = (uint32_t)__ffs((int)~(k.w.litmask >> idx)) - 1u;
-					run = run < limit - k.pos ? run : limit - k.pos;
-					const uint32_t pairs = run >> 1;
-					if (pairs != 0) {
-						if ((k.w.ev_base | 2u) != (k.w.base | 3u)) window_events(e, k.w);
-						// Lanes 18..31 have no slot class: they sit the run out (one divergence per run).
-						if (e.lane < 2 * (int)EVENT_LANES) {
-							uint32_t ea = e.ev_pair_addr + 2u * idx;
-							const uint32_t eend = ea + 4u * pairs;
-	// No barrier between pairs: the 18 lanes run this loop converged (uniform trip counts, no lane-dependent branch,
-	// only predication), and a warp's shared-memory instructions are performed in issue order, so the store of one
-	// pair is visible to the load of the next whichever lane reaches the slot (a __syncwarp per pair cost 30 % of the
-	// step: R2UR + BRA.DIV).  One per group of four keeps the lanes together.
-	// One predicate guards the step's three shared-memory accesses and its add (event 0 = the lane sits the pair
-	// out): written as one PTX block, because the compiler turns `if (ev != 0)` into a divergent branch per step.
-#define MG_PAIR_STEP_PRED(ev)                                                                          \
-	asm volatile(                                                                                        \
-	    "{\n\t"                                                                                          \
-	    ".reg .pred p;\n\t"                                                                              \
-	    ".reg .b32 pa, ta, pv, tr;\n\t"                                                                  \
-	    ".reg .b16 h;\n\t"                                                                               \
-	    "setp.ne.u32 p, %1, 0;\n\t"                                                                      \
-	    "and.b32 pa, %1, 0x3ffff;\n\t"                                                                   \
-	    "shr.u32 ta, %1, 16;\n\t"                                                                        \
-	    "and.b32 ta, ta, 0xE000;\n\t"                                                                    \
-	    "add.u32 ta, ta, %2;\n\t"                                                                        \
-	    "mov.b16 h, 0;\n\t"                                                                              \
-	    "@p ld.shared.u16 h, [pa];\n\t"                                                                  \
-	    "cvt.u32.u16 pv, h;\n\t"                                                                         \
-	    "mad.lo.u32 ta, pv, 4, ta;\n\t"                                                                  \
-	    "mov.b32 tr, 0;\n\t"                                                                             \
-	    "@p ld.shared.u32 tr, [ta];\n\t"                                                                 \
-	    "cvt.u16.u32 h, tr;\n\t"                                                                         \
-	    "@p st.shared.u16 [pa], h;\n\t"                                                                  \
-	    "shr.u32 tr, tr, 16;\n\t"                                                                        \
-	    "add.u32 %0, %0, tr;\n\t"                                                                        \
-	    "}"                                                                                              \
-	    : "+r"(k.t.acc)                                                                                  \
-	    : "r"(ev), "r"(e.trans_addr)                                                                     \
-	    : "memory")
-#if MG_PAIR_VARIANT & 1
-#define MG_PAIR_STEP_CORE(ev)                                                                          \
-	do {                                                                                                 \
-		const uint32_t ev_ = (ev);                                                                       \
-		const uint32_t pa_ = ev_ & 0x3ffffu;                                                             \
-		const uint32_t tr_ = lds_u32(e.trans_addr + ((ev_ >> 16) & 0xE000u) + (lds_u16(pa_) << 2));      \
-		sts_u16(pa_, tr_);                                                                               \
-		k.t.acc += tr_ >> 16;                                                                            \
-	} while (0)
-#else
-#define MG_PAIR_STEP_CORE(ev) MG_PAIR_STEP_PRED(ev)
-#endif
-#if MG_PAIR_VARIANT & 2
-#define MG_PAIR_STEP(ev)            \
-	do {                              \
-		MG_PAIR_STEP_CORE(ev);        \
-		__syncwarp(PAIR_LANES);       \
-	} while (0)
-#else
-#define MG_PAIR_STEP(ev) MG_PAIR_STEP_CORE(ev)
-#endif
-							while (ea != eend && (ea & 15u) != 0) {
-								MG_PAIR_STEP(lds_u32(ea));
-								ea += 4;
-							}
-							// body: the events of four pairs per shared-memory load
-							for (uint32_t groups = (eend - ea) >> 4; groups != 0; groups--) {
-								const uint4 v = lds_v4(ea);
-								MG_PAIR_STEP(v.x);
-								MG_PAIR_STEP(v.y);
-								MG_PAIR_STEP(v.z);
-								MG_PAIR_STEP(v.w);
-								ea += 16;
-								__syncwarp(PAIR_LANES);
-							}
-							while (ea != eend) {
-								MG_PAIR_STEP(lds_u32(ea));
-								ea += 4;
-							}
-#undef MG_PAIR_STEP
-#undef MG_PAIR_STEP_CORE
-#undef MG_PAIR_STEP_PRED
-						}
-						__syncwarp();
-						k.pos += 2u * pairs;
-						continue;
-					}
+				// ---- a whole window of plain literals: every lane works off its own queue (walk_window) ----
+				if (ctx == 0 && k.pos == k.w.base && k.w.litmask == FULL && limit - k.pos == 32u && e.litq != nullptr &&
+				    walk_window(e, k)) {
+					k.pos += 32u;
+					continue;
 				}
 				// ---- one literal: plain (slot classes on lanes 0..8, the lane's slot computed from the data
 				// byte) or matched (lzma_packet_encoder.c:123-130: the tree follows the match byte for as long
 				// as the prefixes agree) -----------------------------------------------------------------
 				const uint32_t byte = (meta >> 16) & 0xff;
-				uint32_t off = (((byte >> e.lit_sh) & e.lowmask) | (byte & e.topmask)) + (ctx & e.ctxmask);
+				const uint32_t u = ((byte >> e.lit_sh) & e.lit_mask) ^ e.lit_x;
+				uint32_t addr = e.lit_addr + u + (u & e.lit_hm) + 2u * (ctx & e.ctxmask);
 				if (ctx >= 7) {
 					const uint32_t mb = walker_mb(e, k);
-					// variant stride of this lane's slot class: depth 0 -> 1, depth 1 -> 2, deeper -> 256
-					const uint32_t vstride = e.lane == 1 ? 1u : e.lane == 2 ? 2u : e.topmask ? 256u : 0u;
-					if ((mb >> e.lit_sh) == (byte >> e.lit_sh)) off += (1u + ((mb >> (e.lit_sh - 1)) & 1u)) * vstride;
+					if (e.bitmask != 0 && (mb >> e.lit_psh) == (byte >> e.lit_psh))
+						addr = e.litv_addr + 2u * (byte >> e.lit_psh) + 512u * ((mb >> (e.lit_psh - 1)) & 1u);
 				}
 				k.ctx = ctx < 4 ? 0u : ctx < 10 ? ctx - 3 : ctx - 6;
-				const uint32_t addr = e.lit_addr + 2 * off;
 				if (e.lit_active) {
-					const uint32_t tr = lds_u32(e.trans_addr + ((lds_u16(addr) | ((byte << e.bit_shl) & e.bitmask)) << 2));
+					const uint32_t tr = lds_u32(e.trans_addr + ((byte << e.bit_shl) & e.bitmask) + lds_u16(addr));
 					sts_u16(addr, tr);
 					k.t.acc += tr >> 16;
 				}
-				__syncwarp();  // pair steps reach the same slots from other lanes
+				__syncwarp();  // the window path reaches the same slots from other lanes
 				k.pos++;
 				continue;
 			}
@@ -674,7 +620,7 @@ __device__ __forceinline__ uint32_t walk(const uint32_t MODE, const WalkEnv& e, 
 			// is priced straight from the slab.  One warp step: F/G/amask are the same on every lane,
 			// the lane's four constants turn them into its slot and bit ----------------------------
 			if (MODE != WALK_REPAIR_HEAD && meta_type(meta) == T_MATCH) {
-				if ((k.w.ev_base | 1u) != (k.w.base | 3u)) window_matches(e, k.w);
+				if (k.w.md_base != k.w.base) window_matches(e, k.w);
 				const uint4 d = lds_v4(e.ev_addr + MATCH_DESC_OFFSET + 16u * (k.pos - k.w.base));
 				if (d.x != 0) {
 					const uint32_t len = meta_len(meta), dist = d.w, amask = d.z & 0x3ffffffu;
@@ -684,7 +630,7 @@ __device__ __forceinline__ uint32_t walk(const uint32_t MODE, const WalkEnv& e, 
 					             : "r"(e.lane_tab_addr));
 					const uint32_t nwb = (d.x >> shb) & mask2;
 					const uint32_t slot = base + __byte_perm(d.y | k.ctx, 0, sel) + (nwb >> 1);
-					if ((amask >> e.lane) & 1u) code_bit(e.probs, e.trans, slot, (nwb & 1u) << 11, k.t.acc);
+					if ((amask >> e.lane) & 1u) code_bit(e.probs, e.trans, slot, nwb & 1u, k.t.acc);
 					if (e.lane == 0) k.t.acc += (d.z >> 26) << 11;  // src/perplexity_encoder.c:12-17
 					k.t.bits += (uint32_t)__popc(amask) - 9u;
 					// src/lzma_state.c:59-65, 29-57
@@ -788,14 +734,14 @@ struct ScoreArgs {
 
 __global__ void __launch_bounds__(CTA_THREADS) score_kernel(ScoreArgs a)
 {
-	extern __shared__ __align__(16) unsigned char smem_raw[];
+	extern __shared__ __align__(128) unsigned char smem_raw[];
 	CtaShared* sh = reinterpret_cast<CtaShared*>(smem_raw);
 	cta_tables_load(sh, a.tables);
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const uint32_t s = blockIdx.x * WARPS_PER_CTA + warp;
 	if (s >= a.nslabs) return;
 	WarpShared* ws = warp_block(sh, warp);
-	const WalkEnv e = make_env(lane, ws, sh, a.slabs + (size_t)s * a.n, a.data, a.n);
+	const WalkEnv e = make_env(lane, ws, sh, a.slabs + (size_t)s * a.n, a.data, a.n, a.tables.litq);
 	Walker k;
 	walker_init(e, k);
 	const size_t ckoff = (size_t)s * a.ck_chain_stride;
@@ -853,12 +799,12 @@ struct TopkArgs {
 
 __global__ void __launch_bounds__(CTA_THREADS) topk_kernel(TopkArgs a)
 {
-	extern __shared__ __align__(16) unsigned char smem_raw[];
+	extern __shared__ __align__(128) unsigned char smem_raw[];
 	CtaShared* sh = reinterpret_cast<CtaShared*>(smem_raw);
 	cta_tables_load(sh, a.tables);
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	WarpShared* ws = warp_block(sh, warp);
-	const WalkEnv e = make_env(lane, ws, sh, a.slab, a.data, a.n);
+	const WalkEnv e = make_env(lane, ws, sh, a.slab, a.data, a.n, a.tables.litq);
 	uint32_t parity = 0;
 	unsigned long long cand = 0;
 	for (uint32_t q = blockIdx.x * WARPS_PER_CTA + warp; q < a.npos; q += gridDim.x * WARPS_PER_CTA) {
@@ -956,7 +902,7 @@ struct AnnealArgs {
 #endif
 __global__ void __launch_bounds__(CTA_THREADS, MG_ANNEAL_MIN_CTAS) anneal_kernel(AnnealArgs a)
 {
-	extern __shared__ __align__(16) unsigned char smem_raw[];
+	extern __shared__ __align__(128) unsigned char smem_raw[];
 	CtaShared* sh = reinterpret_cast<CtaShared*>(smem_raw);
 	cta_tables_load(sh, a.tables);
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -968,7 +914,7 @@ __global__ void __launch_bounds__(CTA_THREADS, MG_ANNEAL_MIN_CTAS) anneal_kernel
 	const uint32_t n = a.n, nck = a.nslots - 1;
 	const uint32_t reg_lo = a.regions ? a.regions[2 * c] : 0u, reg_hi = a.regions ? a.regions[2 * c + 1] : 0u;
 	uint64_t* slab = a.slabs + (size_t)c * n;
-	WalkEnv e_init = make_env(lane, ws, sh, slab, a.data, n);
+	WalkEnv e_init = make_env(lane, ws, sh, slab, a.data, n, a.tables.litq);
 	e_init.abs_dist = a.abs_dist;
 	const WalkEnv e = e_init;
 	Record* ck_base = a.ck + (size_t)c * 2 * nck;
@@ -1200,7 +1146,8 @@ __global__ void __launch_bounds__(CTA_THREADS, MG_ANNEAL_MIN_CTAS) anneal_kernel
 				const uint32_t count = warp_find(lane, e.probs, e.trans, e.recip, &ws->fs, a.data, n, a.occ_start, a.occ,
 				                                 walker_model(e, k), excluded, a.k,
 				                                 (a.suspend && attempts > 1) ? deadline : 0, a.limits);
-				k.w.ev_base = WINDOW_NONE;  // the finder's length tables share the window mirrors' memory
+				k.w.md_base = WINDOW_NONE;  // the finder's length tables share the window mirrors' memory
+				k.w.q_base = WINDOW_NONE;   // ... the literal queue's
 				k.w.pf_base = WINDOW_NONE;  // ... and the staging area of the next window
 				if (count == FIND_GAVE_UP) {
 					gave_up = true;
@@ -1547,21 +1494,16 @@ __device__ __forceinline__ void encode_produce(EncodeShared* sh, const EncodeArg
 {
 	Model m;
 	const SmemU16 probs{smem_u32(sh->rec.probs)};
-	model_init(lane, probs, m);
+	model_init(lane, probs, m, 1024);  // the range coder keeps plain probabilities
 	Window w;
 	w.base = WINDOW_NONE;
 	w.pf_base = WINDOW_NONE;
 	uint32_t head = 0, published = 0, tail_seen = 0, err = 0;
 	const uint32_t ring = smem_u32(sh->ring);
 	const uint32_t stage = smem_u32(sh->stage);
-	// literal lanes: lane 0 is_match, lanes 1..8 tree depth 0..7; the lane's slot for byte b is
-	//   first + (((b >> sh) & lowmask) | (b & topmask))   (slot map in mg_device.cuh)
+	// literal lanes: lane 0 is_match, lanes 1..8 tree depth 0..7 (slot map in mg_device.cuh)
 	const bool tree = lane >= 1 && lane <= 8;
 	const uint32_t depth = tree ? (uint32_t)lane - 1 : 0;
-	const uint32_t lit_first = lane == 0 ? S_ISMATCH : lane == 1 ? S_LIT01 : lane == 2 ? S_LIT01 + 4 : tree ? S_LIT + (1u << (depth - 2)) : S_DUMMY;
-	const uint32_t lit_sh = tree ? 8u - depth : 8u;
-	const uint32_t lowmask = !tree || depth == 0 ? 0u : depth == 1 ? 1u : (1u << (depth - 2)) - 1u;
-	const uint32_t topmask = tree && depth >= 2 ? 0xC0u : 0u;
 	while (m.pos < a.n) {
 		// room for a whole window of literals (32 x 9 events; the largest other packet appends 28)?
 		while (head + 288 - tail_seen > ENC_RING) {
@@ -1587,7 +1529,7 @@ __device__ __forceinline__ void encode_produce(EncodeShared* sh, const EncodeArg
 			for (uint32_t i = 0; i < run; i++) {
 				const uint32_t b = (__shfl_sync(FULL, w.meta, (int)(idx + i)) >> 16) & 0xffu;
 				if (lane <= 8) {
-					const uint32_t slot = lit_first + (((b >> lit_sh) & lowmask) | (b & topmask)) + (lane == 0 ? cj : 0u);
+					const uint32_t slot = lane == 0 ? S_ISMATCH + cj : S_LIT0 + lit0_slot(depth, b >> (8 - depth));
 					const uint32_t bit = tree ? (b >> (7 - depth)) & 1u : 0u;
 					const uint32_t p = probs.get(slot);
 					sts_u32(ring + 4u * (at & (ENC_RING - 1)), enc_event(p, bit));
@@ -1863,6 +1805,77 @@ __global__ void validate_kernel(const uint64_t* __restrict__ packed, uint32_t n,
 		else ok = false;
 		if (!ok) atomicAdd(bad, 1u);
 	}
+}
+
+// ---- literal queues (walk_window) --------------------------------------------------------------------
+// One warp per 32-byte window of the input.  Lane L collects, slot by slot, the bits the window's 32 plain
+// literals send to the slots of bank L (is_match[0] on lane 0: 32 zero bits), pairs them up (two steps on one
+// slot = one two-step table section) and writes its entries; lanes with nothing left to do name their spare
+// slot.  Steps on different slots commute, steps on one slot keep the input order: the model after the queue
+// is the model after the 32 literals (src/lzma_packet_encoder.c:106-121, src/probability_model.c:5-15).
+__global__ void __launch_bounds__(256) litq_build_kernel(const uint8_t* __restrict__ data, uint32_t n, uint32_t nwin, uint4* __restrict__ out)
+{
+	const int lane = threadIdx.x & 31;
+	const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	if (w >= nwin) return;
+	const uint32_t base = w * 32u;
+	const uint32_t b = data[base + (uint32_t)lane];  // windows are whole: base + 32 <= n
+	const uint32_t spare = 2u * (2u * (uint32_t)lane + 1u);  // row 0, odd slot of this bank
+	uint32_t ent[QUEUE_ROUNDS];
+	uint32_t count = 0;
+#pragma unroll
+	for (uint32_t i = 0; i < QUEUE_ROUNDS; i++) ent[i] = spare;
+	auto put = [&](uint32_t off, uint32_t section) {
+#pragma unroll
+		for (uint32_t i = 0; i < QUEUE_ROUNDS; i++)
+			if (i == count) ent[i] = off | (section << 13);
+		count++;
+	};
+	// the bits the window sends to one slot (mask of window positions, bit i of `bits` = the data bit of
+	// position i), in input order, two at a time
+	auto emit = [&](uint32_t off, uint32_t members, uint32_t bits) {
+		while (members) {
+			const uint32_t i0 = (uint32_t)__ffs((int)members) - 1u;
+			members &= members - 1;
+			const uint32_t b0 = (bits >> i0) & 1u;
+			if (members) {
+				const uint32_t i1 = (uint32_t)__ffs((int)members) - 1u;
+				members &= members - 1;
+				put(off, 2u + (b0 << 1) + ((bits >> i1) & 1u));
+			} else {
+				put(off, b0);
+			}
+		}
+	};
+	if (lane == 0) emit(2u * S_ISMATCH, FULL, 0);
+	for (uint32_t d = 0; d < 8; d++) {
+		const uint32_t prefix = b >> (8 - d);
+		const uint32_t slot = S_LIT0 + lit0_slot(d, prefix);
+		const uint32_t bits = __ballot_sync(FULL, (b >> (7 - d)) & 1u);
+		// every distinct slot of this depth, handled by the lane that owns its bank
+		uint32_t todo = FULL;
+		while (todo) {
+			const int leader = __ffs((int)todo) - 1;
+			const uint32_t s = __shfl_sync(FULL, slot, leader);
+			const uint32_t members = __ballot_sync(FULL, slot == s);
+			todo &= ~members;
+			if ((int)((s >> 1) & 31u) == lane) emit(2u * s, members, bits);
+		}
+	}
+	const uint32_t most = __reduce_max_sync(FULL, count);
+	if (most > QUEUE_ROUNDS && lane == 0) ent[0] = QUEUE_UNUSABLE;
+	uint4 lo, hi;
+	lo.x = ent[0] | ent[1] << 16;
+	lo.y = ent[2] | ent[3] << 16;
+	lo.z = ent[4] | ent[5] << 16;
+	lo.w = ent[6] | ent[7] << 16;
+	hi.x = ent[8] | ent[9] << 16;
+	hi.y = ent[10] | ent[11] << 16;
+	hi.z = ent[12] | ent[13] << 16;
+	hi.w = ent[14] | ent[15] << 16;
+	out[(size_t)w * 64 + (uint32_t)lane] = lo;
+	out[(size_t)w * 64 + 32 + (uint32_t)lane] = hi;
+	(void)n;
 }
 
 // ---- K1: bigram index (src/substring_enumerator.c:26-47) ---------------------------------------------
