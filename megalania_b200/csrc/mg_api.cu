@@ -298,7 +298,7 @@ extern "C" MG_API int mg_ctx_create(const uint8_t* data, size_t n, LZMAPropertie
 		CUB(cudaMemcpyAsync(ctx->d_recip, recip.data(), RECIP_ENTRIES * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
 		const uint32_t nwin = (uint32_t)(n / 32);
 		if (nwin != 0 && !getenv("MEGALANIA_NO_LITQ")) {
-			CUB(pool_malloc(&ctx->d_litq, (size_t)nwin * 64 * sizeof(uint4)));
+			CUB(pool_malloc(&ctx->d_litq, (size_t)nwin * QUEUE_BLOCKS * 32 * sizeof(uint4)));
 			litq_build_kernel<<<(nwin + 7) / 8, 256, 0, ctx->stream>>>(ctx->d_data, (uint32_t)n, nwin, ctx->d_litq);
 			CUB(cudaGetLastError());
 		}

@@ -84,13 +84,14 @@ __device__ __forceinline__ WarpShared* warp_block(CtaShared* sh, int warp) { ret
 
 // One literal queue per 32-byte window of the input, built once per context (litq_build_kernel): for each lane the
 // up to QUEUE_ROUNDS table steps it owes the window when all 32 slots hold plain literals and the automaton is in
-// state 0.  Layout [window][2 blocks][32 lanes] x 16 bytes; entry = u16:
+// state 0.  Layout [window][3 blocks][32 lanes] x 16 bytes (eight entries per lane and block; the third block is
+// only read for the few windows in which some lane owes more than 16 steps); entry = u16:
 //   bits 0-11   byte offset of the probability in the record (lane L only ever names slots in bank L)
-//   bit  12     lane 0, entry 0 only: reserved
+//   bit  12     lane 0, entry 0 only: the third block is in use
 //   bits 13-15  transition-table section (one step: bit; two steps on the slot: 2 + first bit << 1 + second bit)
 // Entries a lane does not need name its spare slot (value 0) in section 0: table entry 0 is a zero-price fixed point.
 // A window some lane would need more rounds for has 0xffff in lane 0's first entry: it takes the single-step path.
-constexpr uint32_t QUEUE_UNUSABLE = 0xffffu;
+constexpr uint32_t QUEUE_UNUSABLE = 0xffffu, QUEUE_MORE = 0x1000u, QUEUE_BLOCKS = 3, QUEUE_MAX_ROUNDS = 8 * QUEUE_BLOCKS;
 
 struct Tables {
 	const uint32_t* trans;   // [TRANS_WORDS] stored probability after | price << 16 (price: reference generate_table.py:7-9)
@@ -263,8 +264,12 @@ __device__ __forceinline__ WalkEnv make_env(int lane, WarpShared* ws, const CtaS
 __device__ __forceinline__ void window_matches(const WalkEnv& e, Window& w)
 {
 	__syncwarp();
-	const uint32_t len = meta_len(w.meta), dist = w.dist, pos = w.base + (uint32_t)e.lane;
-	const bool ok = meta_type(w.meta) == T_MATCH && len - 2 <= MAX_MATCH - 2 && pos < e.n && len <= e.n - pos && dist < pos;
+	// opaque on purpose: the compiler otherwise computes match_desc() speculatively for EVERY window right after
+	// the window is decoded (36 instructions per window of plain literals, 8 % of all instructions of the bench)
+	uint32_t meta = w.meta;
+	asm volatile("" : "+r"(meta));
+	const uint32_t len = meta_len(meta), dist = w.dist, pos = w.base + (uint32_t)e.lane;
+	const bool ok = meta_type(meta) == T_MATCH && len - 2 <= MAX_MATCH - 2 && pos < e.n && len <= e.n - pos && dist < pos;
 	if (__any_sync(FULL, ok)) {
 		MatchDesc d = {0, 0, 0, 0};
 		if (ok) d = match_desc(0, len, dist);
@@ -468,7 +473,7 @@ __device__ __forceinline__ void ck_absolute(int lane, const CkMeta* meta, const 
 // The queue of window w travels global -> shared memory by cp.async, one window ahead of the walk.
 __device__ __forceinline__ void queue_fetch(const WalkEnv& e, uint32_t w)
 {
-	const uint4* src = e.litq + (size_t)w * 64 + (uint32_t)e.lane;
+	const uint4* src = e.litq + (size_t)w * QUEUE_BLOCKS * 32 + (uint32_t)e.lane;
 	const uint32_t dst = e.ev_addr + 16u * (uint32_t)e.lane;
 	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 512u), "l"(src + 32) : "memory");
@@ -500,50 +505,74 @@ __device__ __forceinline__ void queue_round(uint32_t ev, uint32_t probs_a, uint3
 	    : "memory");
 }
 
-// Prices the 32 plain literals of the current window (automaton state 0 before and after): lane L performs the
-// table steps of its own queue, all on slots of bank L (slot map in mg_device.cuh), so the lanes neither share
-// a bank nor an address and need no ordering among themselves; per slot the steps are in input order.
-// Returns false when the window has no usable queue (the caller then takes the literals one by one).
-__device__ __forceinline__ bool walk_window(const WalkEnv& e, Walker& k)
+// Prices whole windows of 32 plain literals (automaton state 0 before and after), starting with the current
+// window and carrying on, window after window, for as long as the next one is all plain literals too and ends
+// at or before `wend`: lane L performs the table steps of its own queue, all on slots of bank L (slot map in
+// mg_device.cuh), so the lanes neither share a bank nor an address and need no ordering among themselves; per
+// slot the steps are in input order.  The window state in k.w is kept as window_seek() leaves it.
+// Returns false when the current window has no usable queue (the caller then takes its literals one by one).
+__device__ __forceinline__ bool walk_windows(const WalkEnv& e, Walker& k, uint32_t wend)
 {
-	const uint32_t w = k.w.base >> 5;
-	if (k.w.q_base != k.w.base) {
-		// nothing staged for this window (the first of a run): fetch it now.  A copy still in flight must have
-		// landed before another one is aimed at the same bytes.
-		asm volatile("cp.async.wait_group 0;" ::: "memory");
-		__syncwarp();
-		queue_fetch(e, w);
-		asm volatile("cp.async.wait_group 0;" ::: "memory");
-	}
-	__syncwarp();
-	const uint4 a = lds_v4(e.ev_addr + 16u * (uint32_t)e.lane);
-	const uint4 b = lds_v4(e.ev_addr + 512u + 16u * (uint32_t)e.lane);
-	const uint32_t head = __shfl_sync(FULL, a.x, 0) & 0xffffu;
-	__syncwarp();  // every lane holds its entries: the staging area may be overwritten
-	if (k.w.base + 64u <= e.n) {
-		queue_fetch(e, w + 1);
-		k.w.q_base = k.w.base + 32u;
-	} else {
-		k.w.q_base = WINDOW_NONE;
-	}
-	if (head == QUEUE_UNUSABLE) return false;
+	bool any = false;
 	uint32_t acc = k.t.acc;
 	const uint32_t pa = e.probs.a, ta = e.trans_addr;
+	for (;;) {
+		const uint32_t w = k.w.base >> 5;
+		if (k.w.q_base != k.w.base) {
+			// nothing staged for this window (the first of a run): fetch it now.  A copy still in flight must have
+			// landed before another one is aimed at the same bytes.
+			asm volatile("cp.async.wait_group 0;" ::: "memory");
+			__syncwarp();
+			queue_fetch(e, w);
+			asm volatile("cp.async.wait_group 0;" ::: "memory");
+		}
+		__syncwarp();
+		const uint4 a = lds_v4(e.ev_addr + 16u * (uint32_t)e.lane);
+		const uint4 b = lds_v4(e.ev_addr + 512u + 16u * (uint32_t)e.lane);
+		const uint32_t head = __shfl_sync(FULL, a.x, 0) & 0xffffu;
+		__syncwarp();  // every lane holds its entries: the staging area may be overwritten
+		if (k.w.base + 64u <= e.n) {
+			queue_fetch(e, w + 1);
+			k.w.q_base = k.w.base + 32u;
+		} else {
+			k.w.q_base = WINDOW_NONE;
+		}
+		if (head == QUEUE_UNUSABLE) break;
 #define MG_QUEUE_WORD(v)               \
 	queue_round((v), pa, ta, acc); \
 	queue_round((v) >> 16, pa, ta, acc)
-	MG_QUEUE_WORD(a.x);
-	MG_QUEUE_WORD(a.y);
-	MG_QUEUE_WORD(a.z);
-	MG_QUEUE_WORD(a.w);
-	MG_QUEUE_WORD(b.x);
-	MG_QUEUE_WORD(b.y);
-	MG_QUEUE_WORD(b.z);
-	MG_QUEUE_WORD(b.w);
+		MG_QUEUE_WORD(a.x);
+		MG_QUEUE_WORD(a.y);
+		MG_QUEUE_WORD(a.z);
+		MG_QUEUE_WORD(a.w);
+		MG_QUEUE_WORD(b.x);
+		MG_QUEUE_WORD(b.y);
+		MG_QUEUE_WORD(b.z);
+		MG_QUEUE_WORD(b.w);
+		if (head & QUEUE_MORE) {
+			// the rare window in which some lane owes more than 16 steps: eight more from the third block
+			const uint4 c = __ldg(e.litq + (size_t)w * QUEUE_BLOCKS * 32 + 64 + (uint32_t)e.lane);
+			MG_QUEUE_WORD(c.x);
+			MG_QUEUE_WORD(c.y);
+			MG_QUEUE_WORD(c.z);
+			MG_QUEUE_WORD(c.w);
+		}
 #undef MG_QUEUE_WORD
+		any = true;
+		k.pos += 32u;
+		if (k.pos + 32u > wend) break;
+		// the per-lane sums are 32 bits wide: a window adds at most 24 x 45 056 to one
+		if ((k.pos & 1023u) == 0) {
+			k.t.acc = acc;
+			tally_flush(k.t);
+			acc = 0;
+		}
+		window_seek(e.lane, k.w, e.slab, e.data, e.n, k.pos, e.stage_addr);
+		if (k.w.litmask != FULL) break;
+	}
 	k.t.acc = acc;
 	__syncwarp();  // other paths reach these slots from other lanes
-	return true;
+	return any;
 }
 
 enum WalkMode { WALK_PLAIN = 0, WALK_REPAIR_HEAD = 1, WALK_REPAIR = 2 };
@@ -590,10 +619,11 @@ __device__ __forceinline__ uint32_t walk(const uint32_t MODE, const WalkEnv& e, 
 			if (MODE != WALK_REPAIR_HEAD && (meta & 0xffffu) == META_LITERAL) {
 				const uint32_t ctx = k.ctx;
 				// ---- a whole window of plain literals: every lane works off its own queue (walk_window) ----
-				if (ctx == 0 && k.pos == k.w.base && k.w.litmask == FULL && limit - k.pos == 32u && e.litq != nullptr &&
-				    walk_window(e, k)) {
-					k.pos += 32u;
-					continue;
+				if (ctx == 0 && k.pos == k.w.base && k.w.litmask == FULL && limit - k.pos == 32u && e.litq != nullptr) {
+					// whole windows may go on up to the nearest of: the stop position, the next checkpoint, the stop packet
+					uint32_t wend = stop_pos < ck.next ? stop_pos : ck.next;
+					if (stop_pidx != 0xffffffffu) wend = stop_pidx + k.delta < wend ? stop_pidx + k.delta : wend;
+					if (walk_windows(e, k, wend)) break;  // the window moved on: recompute the limits
 				}
 				// ---- one literal: plain (slot classes on lanes 0..8, the lane's slot computed from the data
 				// byte) or matched (lzma_packet_encoder.c:123-130: the tree follows the match byte for as long
@@ -1821,13 +1851,13 @@ __global__ void __launch_bounds__(256) litq_build_kernel(const uint8_t* __restri
 	const uint32_t base = w * 32u;
 	const uint32_t b = data[base + (uint32_t)lane];  // windows are whole: base + 32 <= n
 	const uint32_t spare = 2u * (2u * (uint32_t)lane + 1u);  // row 0, odd slot of this bank
-	uint32_t ent[QUEUE_ROUNDS];
+	uint32_t ent[QUEUE_MAX_ROUNDS];
 	uint32_t count = 0;
 #pragma unroll
-	for (uint32_t i = 0; i < QUEUE_ROUNDS; i++) ent[i] = spare;
+	for (uint32_t i = 0; i < QUEUE_MAX_ROUNDS; i++) ent[i] = spare;
 	auto put = [&](uint32_t off, uint32_t section) {
 #pragma unroll
-		for (uint32_t i = 0; i < QUEUE_ROUNDS; i++)
+		for (uint32_t i = 0; i < QUEUE_MAX_ROUNDS; i++)
 			if (i == count) ent[i] = off | (section << 13);
 		count++;
 	};
@@ -1863,8 +1893,11 @@ __global__ void __launch_bounds__(256) litq_build_kernel(const uint8_t* __restri
 		}
 	}
 	const uint32_t most = __reduce_max_sync(FULL, count);
-	if (most > QUEUE_ROUNDS && lane == 0) ent[0] = QUEUE_UNUSABLE;
-	uint4 lo, hi;
+	if (lane == 0) {
+		if (most > QUEUE_MAX_ROUNDS) ent[0] = QUEUE_UNUSABLE;
+		else if (most > QUEUE_ROUNDS) ent[0] |= QUEUE_MORE;
+	}
+	uint4 lo, hi, ex;
 	lo.x = ent[0] | ent[1] << 16;
 	lo.y = ent[2] | ent[3] << 16;
 	lo.z = ent[4] | ent[5] << 16;
@@ -1873,8 +1906,13 @@ __global__ void __launch_bounds__(256) litq_build_kernel(const uint8_t* __restri
 	hi.y = ent[10] | ent[11] << 16;
 	hi.z = ent[12] | ent[13] << 16;
 	hi.w = ent[14] | ent[15] << 16;
-	out[(size_t)w * 64 + (uint32_t)lane] = lo;
-	out[(size_t)w * 64 + 32 + (uint32_t)lane] = hi;
+	ex.x = ent[16] | ent[17] << 16;
+	ex.y = ent[18] | ent[19] << 16;
+	ex.z = ent[20] | ent[21] << 16;
+	ex.w = ent[22] | ent[23] << 16;
+	out[(size_t)w * QUEUE_BLOCKS * 32 + (uint32_t)lane] = lo;
+	out[(size_t)w * QUEUE_BLOCKS * 32 + 32 + (uint32_t)lane] = hi;
+	out[(size_t)w * QUEUE_BLOCKS * 32 + 64 + (uint32_t)lane] = ex;
 	(void)n;
 }
 

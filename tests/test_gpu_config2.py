@@ -302,3 +302,36 @@ def test_finder_limits_match_the_restricted_oracle(mg, port, corpora, window, ma
             assert not ((counts0 == counts).all() and (prices0 == prices).all())
     finally:
         port.set_finder_limits(0, 0)
+
+
+def test_literal_queue_edge_windows(mg, port):
+    """The per-lane literal queues (walk_windows): runs of every byte value (some put two hot slots of the
+    tree into one bank: more than 16, some more than 24 rounds -> third block / single-step fallback),
+    alternating bytes, random bytes, windows interrupted by matches - cost and the whole model after
+    several prefixes must equal the oracle's."""
+    rng = np.random.default_rng(99)
+    parts = []
+    for v in range(256):
+        parts.append(bytes([v]) * 40)
+    for a, b in ((0x00, 0xff), (0x65, 0x30), (0x41, 0xc1), (0x18, 0x98)):
+        parts.append(bytes([a, b]) * 48)
+    parts.append(rng.integers(0, 256, 4096, dtype=np.uint8).tobytes())
+    parts.append(rng.integers(0x60, 0x68, 2048, dtype=np.uint8).tobytes())
+    data = b"".join(parts)
+    data = data[: len(data) // 32 * 32 + 7]  # a ragged tail window
+    n = len(data)
+    lit = mg.literal_slab(n)
+    greedy = port.greedy_slab(data)
+    mixed = lit.copy()
+    for p in range(300, n - 64, 517):  # sparse matches: most windows stay whole, some are cut
+        if greedy[p]["type"] == mg.MATCH:  # a MATCH is valid wherever its bytes match, whatever came before
+            mixed[p] = greedy[p]
+    with mg.Context(data) as ctx:
+        costs = ctx.score_slabs(np.concatenate([lit, greedy]))
+        assert int(costs[0]) == port.slab_cost(data, lit)
+        assert int(costs[1]) == port.slab_cost(data, greedy)
+        for stop in (0, 32, 40 * 7, 40 * 0x65 + 32, 40 * 256, n // 2 // 32 * 32, n):
+            got = ctx.model_after_prefix(lit, stop)
+            want = port.model_after_prefix(data, lit, stop)
+            assert got.tobytes() == want.tobytes(), stop
+        assert ctx.score_slab(mixed) == port.slab_cost(data, mixed)
