@@ -25,7 +25,6 @@ constexpr uint32_t MAX_MATCH = 273;  // src/packet_enumerator.c:6-7
 #ifndef MG_FINDER_PM
 #define MG_FINDER_PM 1  // 0 switches the running-maximum filter off (kernel experiments)
 #endif
-constexpr uint32_t PM_MIN_LEN = 16;  // matches at least this long go through the running-maximum filter of warp_find
 
 struct FindScratch {
 	uint64_t ent_pk[MAX_K];
@@ -247,7 +246,8 @@ __device__ __noinline__ uint32_t warp_find(int lane, SmemU16 probs, SmemU32 pric
 		uint32_t have_len[2] = {1, 1};  // len_price filled for lengths 2..have_len
 		uint32_t min_lp[2] = {0xffffffffu, 0xffffffffu};  // cheapest length price filled so far
 		uint32_t slot_cached = 0xffffffffu, slot_price2 = 0, slot_price3 = 0, slot_price4 = 0, slot_price5 = 0;
-		int32_t pm_prefix = INT32_MAX;  // see the running-maximum filter below
+		int32_t pm_prefix = INT32_MAX, pm_short = INT32_MAX;  // see the running-maximum filters below
+		int32_t pm_t2 = INT32_MAX, pm_t3 = INT32_MAX, pm_t4 = INT32_MAX;
 		uint32_t pm_root = 0xffffffffu, pm_have = 0;
 		// align tree prices (src/lzma_packet_encoder.c:97-102): value i on lane i
 		DistParts ap;
@@ -258,9 +258,19 @@ __device__ __noinline__ uint32_t warp_find(int lane, SmemU16 probs, SmemU32 pric
 		ap.rbits = 4;
 		ap.direct = 0;
 		const uint32_t align_tab = dist_tail_price(probs, price, ap);
+		// One step ahead of the walk through the bucket: the next step's occurrence and the four bytes behind
+		// its bigram are loaded while this step is priced (a step is one warp's serial work: nothing else hides
+		// the two dependent L2 round trips, occurrence list -> input bytes).
+		const uint32_t q2 = load_u32_unaligned(data + pos + 2);
+		uint32_t o_next = begin + (uint32_t)lane < end ? occ[begin + (uint32_t)lane] : 0xffffffffu;
+		uint32_t r2_next = o_next < pos ? load_u32_unaligned(data + o_next + 2) : 0u;
 		for (uint32_t chunk = begin; chunk < end; chunk += 32) {
-			const uint32_t idx = chunk + (uint32_t)lane;
-			const uint32_t o = idx < end ? occ[idx] : 0xffffffffu;
+			const uint32_t o = o_next, r2 = r2_next;
+			{
+				const uint32_t idxn = chunk + 32u + (uint32_t)lane;
+				o_next = idxn < end ? occ[idxn] : 0xffffffffu;
+				r2_next = o_next < pos ? load_u32_unaligned(data + o_next + 2) : 0u;
+			}
 			const bool valid = o < pos;  // ascending bucket: stop at the first occurrence >= pos
 			const uint32_t valid_mask = __ballot_sync(FULL, valid);
 			if (valid_mask == 0) break;
@@ -273,16 +283,21 @@ __device__ __noinline__ uint32_t warp_find(int lane, SmemU16 probs, SmemU32 pric
 			}
 			uint32_t L = 0;
 			if (valid) {
-				L = 2;
-				const uint8_t* q = data + pos;
-				const uint8_t* r = data + o;
-				while (L < max_len) {
-					const uint32_t x = load_u32_unaligned(q + L) ^ load_u32_unaligned(r + L);
-					if (x) {
-						L += ((uint32_t)__ffs((int)x) - 1u) >> 3;
-						break;
+				const uint32_t x2 = q2 ^ r2;
+				if (x2) {
+					L = 2 + (((uint32_t)__ffs((int)x2) - 1u) >> 3);
+				} else {
+					L = 6;
+					const uint8_t* q = data + pos;
+					const uint8_t* r = data + o;
+					while (L < max_len) {
+						const uint32_t x = load_u32_unaligned(q + L) ^ load_u32_unaligned(r + L);
+						if (x) {
+							L += ((uint32_t)__ffs((int)x) - 1u) >> 3;
+							break;
+						}
+						L += 4;
 					}
-					L += 4;
 				}
 				L = L < max_len ? L : max_len;
 			}
@@ -350,26 +365,42 @@ __device__ __noinline__ uint32_t warp_find(int lane, SmemU16 probs, SmemU32 pric
 			// the heap" with one comparison.  It is kept in registers, nine lengths per lane (lane j: lengths up to
 			// 10 + 9 j), looked up by shuffle; the bucket's upper end only makes it pass more, never less:
 			// occurrences that pass are priced length by length as before.
-			const bool any_long = MG_FINDER_PM && __any_sync(FULL, valid && L >= PM_MIN_LEN && rep_mask == 0);
-			if (full && any_long && (root != pm_root || have_len[0] != pm_have)) {
-				int32_t q = INT32_MIN;
+			// For lengths up to 31 a second running maximum has one length per lane (lane j: lengths 5..j, where the
+			// pos-slot context no longer depends on the length): with the thresholds of lengths 2, 3 and 4 it answers
+			// the question EXACTLY, so only occurrences that do hold a candidate at or below the root are priced
+			// length by length.
+			if (MG_FINDER_PM && full && (root != pm_root || have_len[0] != pm_have)) {
+				int32_t q = INT32_MIN, s5 = INT32_MIN;
+				pm_t2 = pm_t3 = pm_t4 = INT32_MAX;
 				if (root < 0x400000u) {
 					for (uint32_t j = 0; j < 9; j++) {
 						const uint32_t len = 2u + 9u * (uint32_t)lane + j;
 						if (len <= have_len[0]) q = max(q, (int32_t)((root + 1u) * len - 1u) - (int32_t)fs->len_price[0][len - 2]);
 					}
+					if (lane >= 5 && (uint32_t)lane <= have_len[0])
+						s5 = (int32_t)((root + 1u) * (uint32_t)lane - 1u) - (int32_t)fs->len_price[0][lane - 2];
+					if (have_len[0] >= 2) pm_t2 = (int32_t)((root + 1u) * 2u - 1u) - (int32_t)fs->len_price[0][0];
+					if (have_len[0] >= 3) pm_t3 = (int32_t)((root + 1u) * 3u - 1u) - (int32_t)fs->len_price[0][1];
+					if (have_len[0] >= 4) pm_t4 = (int32_t)((root + 1u) * 4u - 1u) - (int32_t)fs->len_price[0][2];
 				} else {
 					q = INT32_MAX;
+					s5 = lane >= 5 ? INT32_MAX : INT32_MIN;
 				}
 				for (int o = 1; o < 32; o <<= 1) {
 					const int32_t t = __shfl_up_sync(FULL, q, o);
-					if (lane >= o) q = max(q, t);
+					const int32_t t5 = __shfl_up_sync(FULL, s5, o);
+					if (lane >= o) {
+						q = max(q, t);
+						s5 = max(s5, t5);
+					}
 				}
 				pm_prefix = q;
+				pm_short = s5;
 				pm_root = root;
 				pm_have = have_len[0];
 			}
 			const int32_t pm_at = __shfl_sync(FULL, pm_prefix, valid ? (int)((L - 2u) / 9u) : 0);
+			const int32_t pm_sh = __shfl_sync(FULL, pm_short, valid && L < 31u ? (int)L : 31);
 			uint32_t cheapest = 0xffffffffu;
 			uint32_t live_lens = 0;  // bit (len-2): some candidate of that length is at or below the root
 			uint32_t first_live = 2; // shortest length with such a candidate (what a replay of a match longer than 33 starts at)
@@ -392,7 +423,11 @@ __device__ __noinline__ uint32_t warp_find(int lane, SmemU16 probs, SmemU32 pric
 				if (!full) {
 					cheapest = 0;
 					live_lens = 0xffffffffu;
-				} else if (bound <= root && (!MG_FINDER_PM || L < PM_MIN_LEN || rep_mask != 0 || pm_root != root || (int32_t)lo <= pm_at)) {
+				} else if (bound <= root &&
+				           (!MG_FINDER_PM || rep_mask != 0 || pm_root != root ||
+				            (L > 31u ? (int32_t)lo <= pm_at
+				                     : ((int32_t)base2 <= pm_t2 || (L >= 3u && (int32_t)base3 <= pm_t3) || (L >= 4u && (int32_t)base4 <= pm_t4) ||
+				                        (L >= 5u && (int32_t)base5 <= pm_sh))))) {
 					first_live = 0xffffffffu;
 					for (uint32_t len = 2; len <= L; len++) {
 						const uint32_t b = len == 2 ? base2 : len == 3 ? base3 : len == 4 ? base4 : base5;

@@ -480,28 +480,77 @@ __device__ __forceinline__ void queue_fetch(const WalkEnv& e, uint32_t w)
 	asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
-// One queue entry: the lane's probability at the entry's offset takes the one or two steps its section names.
-__device__ __forceinline__ void queue_round(uint32_t ev, uint32_t probs_a, uint32_t trans_a, uint32_t& acc)
+// Four queue entries of one lane (two words): the probability at each entry's offset takes the one or two steps the
+// entry's section names.  The four probability loads go out together and the table loads follow as their inputs
+// arrive: a lane's entries on one slot are adjacent in its queue (litq_build_kernel emits slot by slot), so the only
+// hazard inside the group is "same slot as the entry before", which takes the probability the entry before produced
+// instead of the one loaded.  The stores follow in order, so the last entry of a slot wins.
+__device__ __forceinline__ void queue_rounds4(uint32_t v0, uint32_t v1, uint32_t probs_a, uint32_t trans_a, uint32_t& acc)
 {
 	asm volatile(
 	    "{\n\t"
-	    ".reg .b32 pa, ta, pv, tr;\n\t"
-	    ".reg .b16 h;\n\t"
-	    "and.b32 pa, %1, 0x0FFE;\n\t"
-	    "add.u32 pa, pa, %2;\n\t"
-	    "ld.shared.u16 h, [pa];\n\t"
-	    "cvt.u32.u16 pv, h;\n\t"
-	    "and.b32 ta, %1, 0xE000;\n\t"
-	    "add.u32 ta, ta, %3;\n\t"
-	    "add.u32 ta, ta, pv;\n\t"
-	    "ld.shared.u32 tr, [ta];\n\t"
-	    "cvt.u16.u32 h, tr;\n\t"
-	    "st.shared.u16 [pa], h;\n\t"
-	    "shr.u32 tr, tr, 16;\n\t"
-	    "add.u32 %0, %0, tr;\n\t"
+	    ".reg .b32 h0, h1, a0, a1, a2, a3, s0, s1, s2, s3, p0, p1, p2, p3, t0, t1, t2, t3, x;\n\t"
+	    ".reg .b16 q0, q1, q2, q3;\n\t"
+	    ".reg .pred e1, e2, e3;\n\t"
+	    "shr.u32 h0, %1, 16;\n\t"
+	    "shr.u32 h1, %2, 16;\n\t"
+	    "and.b32 a0, %1, 0x0FFE;\n\t"
+	    "and.b32 a1, h0, 0x0FFE;\n\t"
+	    "and.b32 a2, %2, 0x0FFE;\n\t"
+	    "and.b32 a3, h1, 0x0FFE;\n\t"
+	    "add.u32 a0, a0, %3;\n\t"
+	    "add.u32 a1, a1, %3;\n\t"
+	    "add.u32 a2, a2, %3;\n\t"
+	    "add.u32 a3, a3, %3;\n\t"
+	    "ld.shared.u16 q0, [a0];\n\t"
+	    "ld.shared.u16 q1, [a1];\n\t"
+	    "ld.shared.u16 q2, [a2];\n\t"
+	    "ld.shared.u16 q3, [a3];\n\t"
+	    "and.b32 s0, %1, 0xE000;\n\t"
+	    "and.b32 s1, h0, 0xE000;\n\t"
+	    "and.b32 s2, %2, 0xE000;\n\t"
+	    "and.b32 s3, h1, 0xE000;\n\t"
+	    "add.u32 s0, s0, %4;\n\t"
+	    "add.u32 s1, s1, %4;\n\t"
+	    "add.u32 s2, s2, %4;\n\t"
+	    "add.u32 s3, s3, %4;\n\t"
+	    "setp.eq.u32 e1, a1, a0;\n\t"
+	    "setp.eq.u32 e2, a2, a1;\n\t"
+	    "setp.eq.u32 e3, a3, a2;\n\t"
+	    "cvt.u32.u16 p0, q0;\n\t"
+	    "cvt.u32.u16 p1, q1;\n\t"
+	    "cvt.u32.u16 p2, q2;\n\t"
+	    "cvt.u32.u16 p3, q3;\n\t"
+	    "add.u32 s0, s0, p0;\n\t"
+	    "ld.shared.u32 t0, [s0];\n\t"
+	    "@e1 and.b32 p1, t0, 0xFFFF;\n\t"
+	    "add.u32 s1, s1, p1;\n\t"
+	    "ld.shared.u32 t1, [s1];\n\t"
+	    "@e2 and.b32 p2, t1, 0xFFFF;\n\t"
+	    "add.u32 s2, s2, p2;\n\t"
+	    "ld.shared.u32 t2, [s2];\n\t"
+	    "@e3 and.b32 p3, t2, 0xFFFF;\n\t"
+	    "add.u32 s3, s3, p3;\n\t"
+	    "ld.shared.u32 t3, [s3];\n\t"
+	    "cvt.u16.u32 q0, t0;\n\t"
+	    "cvt.u16.u32 q1, t1;\n\t"
+	    "cvt.u16.u32 q2, t2;\n\t"
+	    "cvt.u16.u32 q3, t3;\n\t"
+	    "st.shared.u16 [a0], q0;\n\t"
+	    "st.shared.u16 [a1], q1;\n\t"
+	    "st.shared.u16 [a2], q2;\n\t"
+	    "st.shared.u16 [a3], q3;\n\t"
+	    "shr.u32 t0, t0, 16;\n\t"
+	    "shr.u32 t1, t1, 16;\n\t"
+	    "shr.u32 t2, t2, 16;\n\t"
+	    "shr.u32 t3, t3, 16;\n\t"
+	    "add.u32 t0, t0, t1;\n\t"
+	    "add.u32 t2, t2, t3;\n\t"
+	    "add.u32 %0, %0, t0;\n\t"
+	    "add.u32 %0, %0, t2;\n\t"
 	    "}"
 	    : "+r"(acc)
-	    : "r"(ev), "r"(probs_a), "r"(trans_a)
+	    : "r"(v0), "r"(v1), "r"(probs_a), "r"(trans_a)
 	    : "memory");
 }
 
@@ -538,26 +587,16 @@ __device__ __forceinline__ bool walk_windows(const WalkEnv& e, Walker& k, uint32
 			k.w.q_base = WINDOW_NONE;
 		}
 		if (head == QUEUE_UNUSABLE) break;
-#define MG_QUEUE_WORD(v)               \
-	queue_round((v), pa, ta, acc); \
-	queue_round((v) >> 16, pa, ta, acc)
-		MG_QUEUE_WORD(a.x);
-		MG_QUEUE_WORD(a.y);
-		MG_QUEUE_WORD(a.z);
-		MG_QUEUE_WORD(a.w);
-		MG_QUEUE_WORD(b.x);
-		MG_QUEUE_WORD(b.y);
-		MG_QUEUE_WORD(b.z);
-		MG_QUEUE_WORD(b.w);
+		queue_rounds4(a.x, a.y, pa, ta, acc);
+		queue_rounds4(a.z, a.w, pa, ta, acc);
+		queue_rounds4(b.x, b.y, pa, ta, acc);
+		queue_rounds4(b.z, b.w, pa, ta, acc);
 		if (head & QUEUE_MORE) {
 			// the rare window in which some lane owes more than 16 steps: eight more from the third block
 			const uint4 c = __ldg(e.litq + (size_t)w * QUEUE_BLOCKS * 32 + 64 + (uint32_t)e.lane);
-			MG_QUEUE_WORD(c.x);
-			MG_QUEUE_WORD(c.y);
-			MG_QUEUE_WORD(c.z);
-			MG_QUEUE_WORD(c.w);
+			queue_rounds4(c.x, c.y, pa, ta, acc);
+			queue_rounds4(c.z, c.w, pa, ta, acc);
 		}
-#undef MG_QUEUE_WORD
 		any = true;
 		k.pos += 32u;
 		if (k.pos + 32u > wend) break;
