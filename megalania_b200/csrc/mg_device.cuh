@@ -27,7 +27,7 @@ constexpr uint32_t T_INVALID = 0, T_LITERAL = 1, T_MATCH = 2, T_SHORT_REP = 3, T
 //
 // Plain literal tree (variant 0 of src/lzma_state.h:47-50) - the "ownership" block, 8 rows of 128 bytes:
 // every slot a run of plain literals touches sits in a fixed shared-memory BANK, and in the literal fast
-// path (walk_window in mg_kernels.cuh) lane L is the only lane that touches bank L.  The lanes then share
+// path (walk_windows in mg_kernels.cuh) lane L is the only lane that touches bank L.  The lanes then share
 // nothing: no bank conflicts on probabilities, no ordering between lanes, and all updates of one slot
 // come from one lane in input order.
 //   bank 0        is_match[0]                       (row 1; touched by every literal)
@@ -566,7 +566,6 @@ struct Window {
 	uint32_t pf_base;     // window being copied into the warp's staging area by cp.async (WINDOW_NONE = none)
 	uint32_t litmask;     // bit i: slot base+i is a canonical LITERAL
 	uint32_t md_base;     // window whose MATCH descriptors are mirrored in shared memory (see window_matches)
-	uint32_t q_base;      // window whose literal queue is staged, or on its way, in shared memory (see walk_window)
 };
 constexpr uint32_t WINDOW_NONE = 0x7fffffe0u;  // never within 32 of a real position (inputs < 2 GiB... see mg_ctx_create)
 

@@ -41,12 +41,10 @@ struct FindScratch {
 };
 
 // Between finds the length-price tables double as the walk's staging area (mg_kernels.cuh):
-//   [0, 1024)     the literal queue of the current window: two blocks of 32 lanes x 16 bytes (eight u16 entries
-//                 each), copied from the context's queue table by cp.async (walk_window())
-//   [1024, 1536)  one 16-byte MATCH descriptor per slot of the window (window_matches())
-//   [1536, 1824)  the NEXT window's 32 slab slots (8 B) + 32 data bytes, filled by cp.async (window_prefetch())
-constexpr uint32_t QUEUE_ROUNDS = 16, QUEUE_BYTES = 32 * QUEUE_ROUNDS * 2;
-constexpr uint32_t MATCH_DESC_OFFSET = QUEUE_BYTES;
+//   [0, 512)     one 16-byte MATCH descriptor per slot of the window (window_matches())
+//   [512, 800)   the NEXT window's 32 slab slots (8 B) + 32 data bytes, filled by cp.async (window_prefetch())
+constexpr uint32_t QUEUE_ROUNDS = 16;
+constexpr uint32_t MATCH_DESC_OFFSET = 0;
 constexpr uint32_t STAGE_OFFSET = MATCH_DESC_OFFSET + 32 * 16;
 constexpr uint32_t STAGE_BYTES = 32 * 8 + 32;
 static_assert(STAGE_OFFSET % 16 == 0 && STAGE_OFFSET + STAGE_BYTES <= sizeof(uint32_t) * 2 * (MAX_MATCH - 1), "window mirrors must fit in len_price");

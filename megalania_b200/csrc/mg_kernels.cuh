@@ -7,7 +7,7 @@ namespace mg {
 
 // One CTA of 26 warps per SM: 26 models + the transition tables (48 KB, see mg_device.cuh) fill the 227 KB of
 // shared memory.  The walk is bound by shared-memory wavefronts; whole windows of plain literals are priced from
-// per-lane queues built once per input (walk_window()).
+// per-lane queues built once per input (walk_windows()).
 #ifndef MG_WARPS_PER_CTA
 #define MG_WARPS_PER_CTA 26
 #endif
@@ -355,7 +355,6 @@ __device__ __forceinline__ void walker_init(const WalkEnv& e, Walker& k)
 	k.w.base = WINDOW_NONE;
 	k.w.pf_base = WINDOW_NONE;
 	k.w.md_base = WINDOW_NONE;
-	k.w.q_base = WINDOW_NONE;
 }
 
 __device__ __forceinline__ void walker_load(const WalkEnv& e, Walker& k, const Record* src, uint64_t* bar, uint32_t& parity)
@@ -370,7 +369,6 @@ __device__ __forceinline__ void walker_load(const WalkEnv& e, Walker& k, const R
 	k.w.base = WINDOW_NONE;
 	k.w.pf_base = WINDOW_NONE;
 	k.w.md_base = WINDOW_NONE;
-	k.w.q_base = WINDOW_NONE;
 	k.mb = MB_UNKNOWN;
 }
 
@@ -469,17 +467,7 @@ __device__ __forceinline__ void ck_absolute(int lane, const CkMeta* meta, const 
 	cost = c;
 }
 
-// ---- a window of 32 plain literals -------------------------------------------------------------------
-// The queue of window w travels global -> shared memory by cp.async, one window ahead of the walk.
-__device__ __forceinline__ void queue_fetch(const WalkEnv& e, uint32_t w)
-{
-	const uint4* src = e.litq + (size_t)w * QUEUE_BLOCKS * 32 + (uint32_t)e.lane;
-	const uint32_t dst = e.ev_addr + 16u * (uint32_t)e.lane;
-	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 512u), "l"(src + 32) : "memory");
-	asm volatile("cp.async.commit_group;" ::: "memory");
-}
-
+// ---- windows of 32 plain literals -----------------------------------------------------------------
 // Four queue entries of one lane (two words): the probability at each entry's offset takes the one or two steps the
 // entry's section names.  The four probability loads go out together and the table loads follow as their inputs
 // arrive: a lane's entries on one slot are adjacent in its queue (litq_build_kernel emits slot by slot), so the only
@@ -558,59 +546,58 @@ __device__ __forceinline__ void queue_rounds4(uint32_t v0, uint32_t v1, uint32_t
 // window and carrying on, window after window, for as long as the next one is all plain literals too and ends
 // at or before `wend`: lane L performs the table steps of its own queue, all on slots of bank L (slot map in
 // mg_device.cuh), so the lanes neither share a bank nor an address and need no ordering among themselves; per
-// slot the steps are in input order.  The window state in k.w is kept as window_seek() leaves it.
+// slot the steps are in input order.  The kernel is bound by instruction issue, so the loop is kept bare: a lane's
+// queue entries come straight from global memory into its registers, one window ahead of their use, and all it
+// looks at of the next window is the type/length word of its slab slots.  The generic window state (k.w) is
+// dropped on the way out: window_seek() reloads it.
 // Returns false when the current window has no usable queue (the caller then takes its literals one by one).
 __device__ __forceinline__ bool walk_windows(const WalkEnv& e, Walker& k, uint32_t wend)
 {
 	bool any = false;
 	uint32_t acc = k.t.acc;
 	const uint32_t pa = e.probs.a, ta = e.trans_addr;
+	uint32_t base = k.w.base;
+	const uint4* q = e.litq + (size_t)(base >> 5) * (QUEUE_BLOCKS * 32) + (uint32_t)e.lane;
+	const uint32_t* slab_hi = reinterpret_cast<const uint32_t*>(e.slab) + 1;  // type << 16 | len of slot i at [2 * i]
+	uint4 a = __ldcg(q), b = __ldcg(q + 32);
 	for (;;) {
-		const uint32_t w = k.w.base >> 5;
-		if (k.w.q_base != k.w.base) {
-			// nothing staged for this window (the first of a run): fetch it now.  A copy still in flight must have
-			// landed before another one is aimed at the same bytes.
-			asm volatile("cp.async.wait_group 0;" ::: "memory");
-			__syncwarp();
-			queue_fetch(e, w);
-			asm volatile("cp.async.wait_group 0;" ::: "memory");
-		}
-		__syncwarp();
-		const uint4 a = lds_v4(e.ev_addr + 16u * (uint32_t)e.lane);
-		const uint4 b = lds_v4(e.ev_addr + 512u + 16u * (uint32_t)e.lane);
 		const uint32_t head = __shfl_sync(FULL, a.x, 0) & 0xffffu;
-		__syncwarp();  // every lane holds its entries: the staging area may be overwritten
-		if (k.w.base + 64u <= e.n) {
-			queue_fetch(e, w + 1);
-			k.w.q_base = k.w.base + 32u;
-		} else {
-			k.w.q_base = WINDOW_NONE;
-		}
 		if (head == QUEUE_UNUSABLE) break;
+		const bool more = base + 64u <= wend;  // another whole window may follow
+		uint32_t next_hi = 0;
+		if (more) next_hi = __ldcg(slab_hi + 2 * (size_t)(base + 32u + (uint32_t)e.lane));
 		queue_rounds4(a.x, a.y, pa, ta, acc);
 		queue_rounds4(a.z, a.w, pa, ta, acc);
+		if (more) a = __ldcg(q + QUEUE_BLOCKS * 32);
 		queue_rounds4(b.x, b.y, pa, ta, acc);
 		queue_rounds4(b.z, b.w, pa, ta, acc);
+		if (more) b = __ldcg(q + QUEUE_BLOCKS * 32 + 32);
 		if (head & QUEUE_MORE) {
 			// the rare window in which some lane owes more than 16 steps: eight more from the third block
-			const uint4 c = __ldg(e.litq + (size_t)w * QUEUE_BLOCKS * 32 + 64 + (uint32_t)e.lane);
+			const uint4 c = __ldcg(q + 64);
 			queue_rounds4(c.x, c.y, pa, ta, acc);
 			queue_rounds4(c.z, c.w, pa, ta, acc);
 		}
 		any = true;
-		k.pos += 32u;
-		if (k.pos + 32u > wend) break;
+		base += 32u;
+		if (!more) break;
 		// the per-lane sums are 32 bits wide: a window adds at most 24 x 45 056 to one
-		if ((k.pos & 1023u) == 0) {
+		if ((base & 1023u) == 0) {
 			k.t.acc = acc;
 			tally_flush(k.t);
 			acc = 0;
 		}
-		window_seek(e.lane, k.w, e.slab, e.data, e.n, k.pos, e.stage_addr);
-		if (k.w.litmask != FULL) break;
+		if (!__all_sync(FULL, next_hi == ((T_LITERAL << 16) | 1u))) break;
+		q += QUEUE_BLOCKS * 32;
 	}
-	k.t.acc = acc;
-	__syncwarp();  // other paths reach these slots from other lanes
+	if (any) {
+		k.pos = base;
+		k.t.acc = acc;
+		k.w.base = WINDOW_NONE;
+		k.w.pf_base = WINDOW_NONE;
+		k.w.md_base = WINDOW_NONE;
+		__syncwarp();  // other paths reach these slots from other lanes
+	}
 	return any;
 }
 
@@ -657,7 +644,7 @@ __device__ __forceinline__ uint32_t walk(const uint32_t MODE, const WalkEnv& e, 
 			const uint32_t meta = window_meta(k.w, k.pos);
 			if (MODE != WALK_REPAIR_HEAD && (meta & 0xffffu) == META_LITERAL) {
 				const uint32_t ctx = k.ctx;
-				// ---- a whole window of plain literals: every lane works off its own queue (walk_window) ----
+				// ---- a whole window of plain literals: every lane works off its own queue (walk_windows) ----
 				if (ctx == 0 && k.pos == k.w.base && k.w.litmask == FULL && limit - k.pos == 32u && e.litq != nullptr) {
 					// whole windows may go on up to the nearest of: the stop position, the next checkpoint, the stop packet
 					uint32_t wend = stop_pos < ck.next ? stop_pos : ck.next;
@@ -1216,7 +1203,6 @@ __global__ void __launch_bounds__(CTA_THREADS, MG_ANNEAL_MIN_CTAS) anneal_kernel
 				                                 walker_model(e, k), excluded, a.k,
 				                                 (a.suspend && attempts > 1) ? deadline : 0, a.limits);
 				k.w.md_base = WINDOW_NONE;  // the finder's length tables share the window mirrors' memory
-				k.w.q_base = WINDOW_NONE;   // ... the literal queue's
 				k.w.pf_base = WINDOW_NONE;  // ... and the staging area of the next window
 				if (count == FIND_GAVE_UP) {
 					gave_up = true;
@@ -1876,7 +1862,7 @@ __global__ void validate_kernel(const uint64_t* __restrict__ packed, uint32_t n,
 	}
 }
 
-// ---- literal queues (walk_window) --------------------------------------------------------------------
+// ---- literal queues (walk_windows) --------------------------------------------------------------------
 // One warp per 32-byte window of the input.  Lane L collects, slot by slot, the bits the window's 32 plain
 // literals send to the slots of bank L (is_match[0] on lane 0: 32 zero bits), pairs them up (two steps on one
 // slot = one two-step table section) and writes its entries; lanes with nothing left to do name their spare
