@@ -174,6 +174,7 @@ static int set_smem_attrs()
 	CU(cudaFuncSetAttribute(score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CtaShared)));
 	CU(cudaFuncSetAttribute(topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CtaShared)));
 	CU(cudaFuncSetAttribute(anneal_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CtaShared)));
+	CU(cudaFuncSetAttribute(encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EncodeShared)));
 	// the model lives in shared memory: ask for the largest carve-out so that occupancy is set by registers
 	CU(cudaFuncSetAttribute(score_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
 	CU(cudaFuncSetAttribute(topk_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -649,7 +650,7 @@ static int encode_to_host(mg_ctx* ctx, const LZMAPacket* slab, std::vector<uint8
 	DevBuf packed, out, len, err;
 	if (int rc = dev_alloc(packed, (size_t)n * 8)) return rc;
 	if (int rc = dev_alloc(out, cap)) return rc;
-	if (int rc = dev_alloc(len, 8)) return rc;
+	if (int rc = dev_alloc(len, 32)) return rc;
 	if (int rc = dev_alloc(err, 4)) return rc;
 	if (int rc = upload_packed(ctx, slab, n, packed.as<uint64_t>())) return rc;
 	EncodeArgs a;
@@ -661,16 +662,18 @@ static int encode_to_host(mg_ctx* ctx, const LZMAPacket* slab, std::vector<uint8
 	a.out_len = len.as<uint32_t>();
 	a.out_err = err.as<uint32_t>();
 	a.out_events = len.as<uint32_t>() + 1;
+	const bool debug_wait = getenv("MEGALANIA_ENCODE_DEBUG") != nullptr;
+	a.out_wait = debug_wait ? reinterpret_cast<unsigned long long*>(len.as<uint32_t>() + 2) : nullptr;
 	a.tables = ctx->tables;
 	cudaEvent_t t0, t1;
 	CU(cudaEventCreate(&t0));
 	CU(cudaEventCreate(&t1));
 	CU(cudaEventRecord(t0, ctx->stream));
-	encode_kernel<<<1, 64, 0, ctx->stream>>>(a);
+	encode_kernel<<<1, 96, sizeof(EncodeShared), ctx->stream>>>(a);
 	CU(cudaEventRecord(t1, ctx->stream));
 	CU(cudaGetLastError());
-	uint32_t hlen2[2] = {0, 0}, herr = 0;
-	CU(cudaMemcpyAsync(hlen2, len.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+	uint32_t hlen2[8] = {0, 0, 0, 0, 0, 0, 0, 0}, herr = 0;
+	CU(cudaMemcpyAsync(hlen2, len.p, 32, cudaMemcpyDeviceToHost, ctx->stream));
 	CU(cudaMemcpyAsync(&herr, err.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
 	CU(cudaStreamSynchronize(ctx->stream));
 	{
@@ -678,6 +681,11 @@ static int encode_to_host(mg_ctx* ctx, const LZMAPacket* slab, std::vector<uint8
 		cudaEventElapsedTime(&ms, t0, t1);
 		ctx->last_encode_ms = ms;
 		ctx->last_encode_events = hlen2[1];
+		if (debug_wait) {
+			unsigned long long w[3];
+			memcpy(w, hlen2 + 2, sizeof(w));
+			fprintf(stderr, "mg_encode_slab: %.2f ms, %u events; clocks waiting: producer %llu, range %llu, low %llu\n", ms, hlen2[1], w[0], w[1], w[2]);
+		}
 		cudaEventDestroy(t0);
 		cudaEventDestroy(t1);
 	}

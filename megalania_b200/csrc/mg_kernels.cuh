@@ -1439,6 +1439,7 @@ struct EncodeArgs {
 	uint32_t* out_len;
 	uint32_t* out_err;
 	uint32_t* out_events;  // events coded (modelled bits + direct-bit groups)
+	unsigned long long* out_wait;  // [3] clocks each strand spent waiting for its neighbour (producer, range, low), or null
 	Tables tables;
 };
 
@@ -1503,28 +1504,34 @@ __device__ __forceinline__ void rc_direct(RangeCoder& rc, uint32_t bits, uint32_
 	}
 }
 
-// One CTA of two warps joined by a ring of events in shared memory:
+// One CTA of three warps joined by two rings in shared memory - a pipeline of the coder's three strands:
 //   warp 0 (producer) walks the slab with the model exactly as the scorer does and appends each packet's
-//          (bit, probability) events - in the reference's coding order, direct bits included - to the ring;
+//          (bit, probability) events - in the reference's coding order, direct bits included - to ring A;
 //          plain literals (nine events from nine lanes, no cross-lane traffic) take a short path;
-//   warp 1 (consumer), lane 0, runs the range coder's carry / shift-low recurrence (src/range_encoder.c:18-64)
-//          over the ring.  That recurrence is the one strictly sequential part of the whole path: its critical
-//          chain per event is range -> range >> 11 -> multiply-add -> normalise, everything else (low, cache,
-//          output bytes) hangs off it.  Events are pre-digested by the producer for it: q = the probability of
-//          the coded bit (p or 2048 - p), so that the new range is (range >> 11) * q + (bit ? range & 2047 : 0)
-//          for either bit value - one multiply-add, no select.
-// The two warps sit on different schedulers of the SM, so the model walk (50-100 cycles per packet) hides
-// behind the recurrence (round 1 ran them back to back on one warp: 1.2 s per MiB).
-constexpr uint32_t ENC_RING = 8192;  // events; a packet appends at most 28
+//   warp 1, lane 0 (range) runs the one strictly sequential recurrence of the whole path, the range
+//          (src/range_encoder.c:47-81): per event range -> range >> 11 -> multiply-add -> normalise, and nothing
+//          else.  Events come pre-digested: q = the probability of the coded bit (p or 2048 - p), so that the new
+//          range is (range >> 11) * q + (bit ? range & 2047 : 0) for either bit value - one multiply-add, no
+//          select.  What the event adds to `low` and whether it shifts go to ring B;
+//   warp 2, lane 0 (low) adds up `low`, propagates carries and writes the bytes (src/range_encoder.c:18-45).
+//          `low` never feeds back into the range, so this strand only has to keep pace.
+// The three warps sit on different schedulers of the SM.  Round 1 ran everything back to back on one warp (1.2 s per
+// MiB), the first split (model walk | coder) took 0.39 s; the range chain alone is ~15 dependent cycles per event.
+constexpr uint32_t ENC_RING = 8192;   // ring A, events; a packet appends at most 28
+constexpr uint32_t ENC_RING_B = 4096; // ring B, (add, shifts) pairs
 constexpr uint32_t ENC_DIRECT = 0x80000000u;
 
 struct EncodeShared {
 	Record rec;
 	uint32_t ring[ENC_RING];
+	uint2 ring_b[ENC_RING_B];
 	unsigned char stage[STAGE_BYTES];
-	uint32_t head;  // events produced so far (producer writes, consumer reads)
-	uint32_t tail;  // events consumed so far
-	uint32_t done;  // 1 = producer finished, 2 = producer stopped on an error
+	uint32_t head;    // events produced so far (producer writes, range reads)
+	uint32_t tail;    // events consumed so far
+	uint32_t head_b;  // ring B entries produced (range writes, low reads)
+	uint32_t tail_b;
+	uint32_t done;    // 1 = producer finished, 2 = producer stopped on an error
+	uint32_t done_b;  // range strand finished
 	uint32_t err;
 };
 
@@ -1554,21 +1561,35 @@ __device__ __forceinline__ void encode_produce(EncodeShared* sh, const EncodeArg
 	w.base = WINDOW_NONE;
 	w.pf_base = WINDOW_NONE;
 	uint32_t head = 0, published = 0, tail_seen = 0, err = 0;
+	unsigned long long waited = 0;
 	const uint32_t ring = smem_u32(sh->ring);
 	const uint32_t stage = smem_u32(sh->stage);
-	// literal lanes: lane 0 is_match, lanes 1..8 tree depth 0..7 (slot map in mg_device.cuh)
+	// literal lanes: lane 0 is_match, lanes 1..8 tree depth 0..7 (slot map in mg_device.cuh); per-lane constants of
+	// the plain tree as in make_env(): slot byte offset = first + u + (u & hm), u = ((b >> sh) & mask) ^ x
 	const bool tree = lane >= 1 && lane <= 8;
 	const uint32_t depth = tree ? (uint32_t)lane - 1 : 0;
+	uint32_t lit_first = 2u * S_DUMMY, lit_sh = 8, lit_mask = 0, lit_x = 0, lit_hm = 0;
+	if (lane == 0) lit_first = 2u * S_ISMATCH;
+	else if (tree && depth <= 3) { lit_first = 2u * (S_LIT0 + 2u * (1u << depth)); lit_sh = 6 - depth; lit_mask = ((1u << depth) - 1u) << 2; }
+	else if (tree && depth == 4) { lit_first = 2u * (S_LIT0 + 32); lit_sh = 2; lit_mask = 0x3c; lit_x = LITX4 << 2; }
+	else if (tree && depth == 5) { lit_first = 2u * (S_LIT0 + 96); lit_sh = 2; lit_mask = 0x3e; lit_x = LITX5 << 1; }
+	else if (tree && depth == 6) { lit_first = 2u * (S_LIT0 + 160); lit_sh = 1; lit_mask = 0x7e; lit_x = LITX6 << 1; lit_hm = 64; }
+	else if (tree && depth == 7) { lit_first = 2u * (S_LIT0 + 288); lit_sh = 0; lit_mask = 0xfe; lit_x = LITX7 << 1; lit_hm = 0xc0; }
+	const uint32_t lit_addr = probs.a + lit_first;
 	while (m.pos < a.n) {
 		// room for a whole window of literals (32 x 9 events; the largest other packet appends 28)?
-		while (head + 288 - tail_seen > ENC_RING) {
-			if (published != head) {
-				__syncwarp();
-				if (lane == 0) st_release_u32(&sh->head, head);
-				published = head;
+		if (head + 288 - tail_seen > ENC_RING) {
+			const long long t0 = clock64();
+			while (head + 288 - tail_seen > ENC_RING) {
+				if (published != head) {
+					__syncwarp();
+					if (lane == 0) st_release_u32(&sh->head, head);
+					published = head;
+				}
+				tail_seen = ld_acquire_u32(&sh->tail);
+				if (head + 288 - tail_seen > ENC_RING) __nanosleep(64);
 			}
-			tail_seen = ld_acquire_u32(&sh->tail);
-			if (head + 288 - tail_seen > ENC_RING) __nanosleep(64);
+			waited += (unsigned long long)(clock64() - t0);
 		}
 		window_seek(lane, w, a.slab, a.data, a.n, m.pos, stage);
 		const uint32_t meta = window_meta(w, m.pos);
@@ -1584,11 +1605,12 @@ __device__ __forceinline__ void encode_produce(EncodeShared* sh, const EncodeArg
 			for (uint32_t i = 0; i < run; i++) {
 				const uint32_t b = (__shfl_sync(FULL, w.meta, (int)(idx + i)) >> 16) & 0xffu;
 				if (lane <= 8) {
-					const uint32_t slot = lane == 0 ? S_ISMATCH + cj : S_LIT0 + lit0_slot(depth, b >> (8 - depth));
+					const uint32_t u = ((b >> lit_sh) & lit_mask) ^ lit_x;
+					const uint32_t addr = lit_addr + u + (u & lit_hm) + (lane == 0 ? 2u * cj : 0u);
 					const uint32_t bit = tree ? (b >> (7 - depth)) & 1u : 0u;
-					const uint32_t p = probs.get(slot);
+					const uint32_t p = lds_u16(addr);
 					sts_u32(ring + 4u * (at & (ENC_RING - 1)), enc_event(p, bit));
-					probs.set(slot, bit ? p - (p >> 5) : p + ((2048u - p) >> 5));
+					sts_u16(addr, bit ? p - (p >> 5) : p + ((2048u - p) >> 5));
 				}
 				at += 9;
 				cj = cj < 4 ? 0u : cj - 3;
@@ -1637,12 +1659,14 @@ __device__ __forceinline__ void encode_produce(EncodeShared* sh, const EncodeArg
 	__syncwarp();
 	if (lane == 0) {
 		sh->err = err;
+		if (a.out_wait) a.out_wait[0] = waited;
 		st_release_u32(&sh->head, head);
 		st_release_u32(&sh->done, err ? 2u : 1u);
 	}
 }
 
-// One modelled bit (src/range_encoder.c:47-64) in the form the consumer's chain wants.  With bound = (range >> 11) * p:
+// ---- the range strand ----
+// One modelled bit (src/range_encoder.c:47-64).  With bound = (range >> 11) * p:
 //   bit 0: range' = bound,         low unchanged      = (range >> 11) * q                     (q = p)
 //   bit 1: range' = range - bound, low += bound       = (range >> 11) * q + (range & 2047)    (q = 2048 - p)
 // The state is kept as hi = range >> 11 and the kept low bits of the NEXT event, both selected from the two
@@ -1651,58 +1675,106 @@ __device__ __forceinline__ void encode_produce(EncodeShared* sh, const EncodeArg
 struct RangeChain {
 	uint32_t range;  // the reference's range (normalised)
 	uint32_t hi;     // range >> 11
-	uint32_t lk;     // range & (the coming event codes a 1 ? 2047 : 0); only valid between rc_event calls that pass keep_next
+	uint32_t lk;     // range & (the coming event codes a 1 ? 2047 : 0); only valid between range_event calls that pass keep_next
 };
 
 __device__ __forceinline__ uint32_t enc_keep(uint32_t e) { return (e >> 15) ? 2047u : 0u; }
 
-// keep_next = enc_keep(the event after e) when it is known (then ch.lk stays valid), anything otherwise
-__device__ __forceinline__ void rc_event(RangeCoder& rc, RangeChain& ch, uint32_t e, uint32_t keep_next)
+// keep_next = enc_keep(the event after e) when it is known (then ch.lk stays valid), anything otherwise.
+// Returns what the event means for `low`: x = the amount added, y = 1 when the coder shifts after it.
+__device__ __forceinline__ uint2 range_event(RangeChain& ch, uint32_t e, uint32_t keep_next)
 {
 	const uint32_t q = e & 0x7fffu;
 	const uint32_t next = ch.hi * q + ch.lk;
-	if (e >> 15) rc.low += ch.range - next;
+	uint2 out;
+	out.x = (e >> 15) ? ch.range - next : 0u;
 	const bool shift = (next & 0xFF000000u) == 0;
+	out.y = shift ? 1u : 0u;
 	ch.hi = shift ? next >> 3 : next >> 11;
 	ch.lk = shift ? ((next & 7u) << 8) & keep_next : next & keep_next;
 	ch.range = shift ? next << 8 : next;
-	if (shift) rc_shift_low(rc);
+	return out;
 }
 
-// any event, nothing known about its neighbours
-__device__ __forceinline__ void rc_any(RangeCoder& rc, RangeChain& ch, uint32_t e)
+struct RingBWriter {
+	uint32_t ring;  // shared address of ring_b
+	uint32_t head, published, tail_seen;
+	EncodeShared* sh;
+	unsigned long long waited;
+};
+
+__device__ __forceinline__ void ring_b_room(RingBWriter& wb, uint32_t want)
+{
+	if (wb.head + want - wb.tail_seen <= ENC_RING_B) return;
+	const long long t0 = clock64();
+	while (wb.head + want - wb.tail_seen > ENC_RING_B) {
+		if (wb.published != wb.head) {
+			st_release_u32(&wb.sh->head_b, wb.head);
+			wb.published = wb.head;
+		}
+		wb.tail_seen = ld_acquire_u32(&wb.sh->tail_b);
+	}
+	wb.waited += (unsigned long long)(clock64() - t0);
+}
+
+__device__ __forceinline__ void ring_b_put(RingBWriter& wb, uint2 v)
+{
+	asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(wb.ring + 8u * (wb.head & (ENC_RING_B - 1))), "r"(v.x), "r"(v.y) : "memory");
+	wb.head++;
+}
+
+// any event, nothing known about its neighbours (src/range_encoder.c:66-81 for the direct bits)
+__device__ __forceinline__ void range_any(RangeChain& ch, RingBWriter& wb, uint32_t e)
 {
 	if (e & ENC_DIRECT) {
-		rc.range = ch.range;
-		rc_direct(rc, e & 0x3ffffffu, (e >> 26) & 31u);
-		ch.range = rc.range;
-		ch.hi = rc.range >> 11;
+		uint32_t range = ch.range, nbits = (e >> 26) & 31u;
+		const uint32_t bits = e & 0x3ffffffu;
+		ring_b_room(wb, nbits);
+		while (nbits) {
+			nbits--;
+			range >>= 1;
+			uint2 out;
+			out.x = ((bits >> nbits) & 1u) ? range : 0u;
+			out.y = 0;
+			if ((range & 0xFF000000u) == 0) {
+				range <<= 8;
+				out.y = 1;
+			}
+			ring_b_put(wb, out);
+		}
+		ch.range = range;
+		ch.hi = range >> 11;
 	} else {
 		ch.lk = ch.range & enc_keep(e);
-		rc_event(rc, ch, e, 0);
+		ring_b_put(wb, range_event(ch, e, 0));
 	}
 }
 
-__device__ __forceinline__ void encode_consume(EncodeShared* sh, const EncodeArgs& a)
+__device__ __forceinline__ void encode_range(EncodeShared* sh, const EncodeArgs& a)
 {
-	RangeCoder rc = {0, 0xFFFFFFFFu, 0, 1, a.out, a.cap, 0};
 	RangeChain ch = {0xFFFFFFFFu, 0xFFFFFFFFu >> 11, 0};
+	RingBWriter wb = {smem_u32(sh->ring_b), 0, 0, 0, sh, 0};
 	uint32_t tail = 0;
+	unsigned long long starved = 0;
 	const uint32_t ring = smem_u32(sh->ring);
 	for (;;) {
 		uint32_t head = ld_acquire_u32(&sh->head);
 		if (head == tail) {
 			if (ld_acquire_u32(&sh->done) == 0) {
+				const long long t0 = clock64();
 				__nanosleep(32);
+				starved += (unsigned long long)(clock64() - t0);
 				continue;
 			}
 			head = ld_acquire_u32(&sh->head);  // published before `done`
 			if (head == tail) break;
 		}
-		// a bounded batch, so that the producer sees the ring drain while a long backlog is coded
-		if (head - tail > ENC_RING / 4) head = tail + ENC_RING / 4;
+		// a bounded batch, so that the producer sees ring A drain (and the low strand ring B fill) while a long
+		// backlog is coded
+		if (head - tail > ENC_RING / 8) head = tail + ENC_RING / 8;
 		while (tail != head && (tail & 3u) != 0) {
-			rc_any(rc, ch, lds_u32(ring + 4u * (tail & (ENC_RING - 1))));
+			ring_b_room(wb, 1);
+			range_any(ch, wb, lds_u32(ring + 4u * (tail & (ENC_RING - 1))));
 			tail++;
 		}
 		// groups of four events per 16-byte load, the next group in flight while this one is coded
@@ -1712,44 +1784,133 @@ __device__ __forceinline__ void encode_consume(EncodeShared* sh, const EncodeArg
 				const uint4 cur = v;
 				v = lds_v4(ring + 4u * ((tail + 4) & (ENC_RING - 1)));  // may run past head: never used then
 				tail += 4;
+				ring_b_room(wb, 4);
 				if ((cur.x | cur.y | cur.z | cur.w) & ENC_DIRECT) {
-					rc_any(rc, ch, cur.x);
-					rc_any(rc, ch, cur.y);
-					rc_any(rc, ch, cur.z);
-					rc_any(rc, ch, cur.w);
+					range_any(ch, wb, cur.x);
+					range_any(ch, wb, cur.y);
+					range_any(ch, wb, cur.z);
+					range_any(ch, wb, cur.w);
 				} else {
 					ch.lk = ch.range & enc_keep(cur.x);
-					rc_event(rc, ch, cur.x, enc_keep(cur.y));
-					rc_event(rc, ch, cur.y, enc_keep(cur.z));
-					rc_event(rc, ch, cur.z, enc_keep(cur.w));
-					rc_event(rc, ch, cur.w, 0);
+					const uint2 o0 = range_event(ch, cur.x, enc_keep(cur.y));
+					const uint2 o1 = range_event(ch, cur.y, enc_keep(cur.z));
+					const uint2 o2 = range_event(ch, cur.z, enc_keep(cur.w));
+					const uint2 o3 = range_event(ch, cur.w, 0);
+					// four entries = two 16-byte stores (ring B never wraps inside a group: its head stays a multiple
+					// of 2 only if no direct bits came before - so store entry by entry unless aligned)
+					if ((wb.head & 1u) == 0) {
+						const uint32_t at0 = wb.ring + 8u * (wb.head & (ENC_RING_B - 1));
+						const uint32_t at1 = wb.ring + 8u * ((wb.head + 2) & (ENC_RING_B - 1));
+						sts_v4(at0, o0.x, o0.y, o1.x, o1.y);
+						sts_v4(at1, o2.x, o2.y, o3.x, o3.y);
+						wb.head += 4;
+					} else {
+						ring_b_put(wb, o0);
+						ring_b_put(wb, o1);
+						ring_b_put(wb, o2);
+						ring_b_put(wb, o3);
+					}
 				}
 			}
 		}
 		while (tail != head) {
-			rc_any(rc, ch, lds_u32(ring + 4u * (tail & (ENC_RING - 1))));
+			ring_b_room(wb, 1);
+			range_any(ch, wb, lds_u32(ring + 4u * (tail & (ENC_RING - 1))));
 			tail++;
 		}
 		st_release_u32(&sh->tail, tail);
+		st_release_u32(&sh->head_b, wb.head);
+		wb.published = wb.head;
 	}
-	for (int i = 0; i < 5; i++) rc_shift_low(rc);  // src/range_encoder.c:40-45
-	const uint32_t err = sh->err;
-	*a.out_len = rc.len;
-	*a.out_err = err | (rc.len > rc.cap ? ERR_OUTPUT_FULL : 0);
-	*a.out_events = tail;
+	if (a.out_wait) a.out_wait[1] = starved + wb.waited;
+	st_release_u32(&sh->head_b, wb.head);
+	st_release_u32(&sh->done_b, 1u);
 }
 
-__global__ void __launch_bounds__(64) encode_kernel(EncodeArgs a)
+// ---- the low strand: low += what each event added, shift when it shifted (src/range_encoder.c:18-45) ----
+// A whole warp takes 32 ring-B entries per step, one per lane.  `low` only changes what is written at a SHIFT, so
+// the adds between two shifts are summed first - a segmented scan across the lanes (segments end at the lanes
+// that shift; the sum of a segment is below 2^32: the coder's range bounds everything added between two
+// normalisations) - and lane 0 then performs one `low += sum; shift` per shift of the step, about four per 32 entries.
+__device__ __forceinline__ void encode_low(EncodeShared* sh, const EncodeArgs& a, int lane)
 {
-	__shared__ __align__(16) EncodeShared sh;
+	RangeCoder rc = {0, 0xFFFFFFFFu, 0, 1, a.out, a.cap, 0};  // lane 0's copy is the coder
+	uint32_t tail = 0, pending = 0;  // pending: adds since the last shift (uniform)
+	unsigned long long starved = 0;
+	const uint32_t ring = smem_u32(sh->ring_b);
+	for (;;) {
+		uint32_t head = ld_acquire_u32(&sh->head_b);
+		if (head == tail) {
+			if (ld_acquire_u32(&sh->done_b) == 0) {
+				const long long t0 = clock64();
+				__nanosleep(32);
+				starved += (unsigned long long)(clock64() - t0);
+				continue;
+			}
+			head = ld_acquire_u32(&sh->head_b);
+			if (head == tail) break;
+		}
+		if (head - tail > ENC_RING_B / 4) head = tail + ENC_RING_B / 4;
+		while (tail != head) {
+			const uint32_t cnt = head - tail < 32u ? head - tail : 32u;
+			uint32_t add = 0, shifts = 0;
+			if ((uint32_t)lane < cnt)
+				asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(add), "=r"(shifts) : "r"(ring + 8u * ((tail + (uint32_t)lane) & (ENC_RING_B - 1))) : "memory");
+			tail += cnt;
+			const uint32_t m = __ballot_sync(FULL, shifts != 0);
+			const uint32_t seg = (uint32_t)__popc(m & ((1u << lane) - 1u));  // shifts before this entry
+			// inclusive segmented sum: a lane that shifts ends up with everything added since the shift before it
+			uint32_t x = add;
+#pragma unroll
+			for (int d = 1; d < 32; d <<= 1) {
+				const uint32_t y = __shfl_up_sync(FULL, x, d), sg = __shfl_up_sync(FULL, seg, d);
+				if (lane >= d && sg == seg) x += y;
+			}
+			// what follows the step's last shift carries over to the next step
+			const uint32_t nshift = (uint32_t)__popc(m);
+			const uint32_t trailing = __reduce_add_sync(FULL, seg == nshift ? add : 0u);
+			uint32_t todo = m;
+			bool first = true;
+			while (todo) {
+				const int who = __ffs((int)todo) - 1;
+				todo &= todo - 1;
+				const uint32_t sum = __shfl_sync(FULL, x, who);
+				if (lane == 0) {
+					rc.low += (uint64_t)sum + (first ? pending : 0u);
+					rc_shift_low(rc);
+				}
+				first = false;
+			}
+			pending = (nshift ? 0u : pending) + trailing;
+		}
+		if (lane == 0) st_release_u32(&sh->tail_b, tail);
+		__syncwarp();
+	}
+	if (lane == 0) {
+		rc.low += pending;
+		for (int i = 0; i < 5; i++) rc_shift_low(rc);  // src/range_encoder.c:40-45
+		const uint32_t err = sh->err;
+		*a.out_len = rc.len;
+		*a.out_err = err | (rc.len > rc.cap ? ERR_OUTPUT_FULL : 0);
+		*a.out_events = ld_acquire_u32(&sh->tail);
+		if (a.out_wait) a.out_wait[2] = starved;
+	}
+}
+
+__global__ void __launch_bounds__(96) encode_kernel(EncodeArgs a)
+{
+	extern __shared__ __align__(128) unsigned char smem_raw[];
+	EncodeShared& sh = *reinterpret_cast<EncodeShared*>(smem_raw);
 	if (threadIdx.x == 0) {
-		sh.head = sh.tail = sh.done = sh.err = 0;
+		sh.head = sh.tail = sh.head_b = sh.tail_b = sh.done = sh.done_b = sh.err = 0;
 	}
 	__syncthreads();
 	if (threadIdx.x < 32)
 		encode_produce(&sh, a, (int)threadIdx.x);
 	else if (threadIdx.x == 32)
-		encode_consume(&sh, a);
+		encode_range(&sh, a);
+	else if (threadIdx.x >= 64)
+		encode_low(&sh, a, (int)threadIdx.x - 64);
 }
 
 // ---- slab format conversion: host LZMAPacket (12 B) <-> packed u64 ----------------------------------
