@@ -428,12 +428,18 @@ def run_cuda(args) -> None:
 
     # ---- roofline of the dominant kernel (anneal_kernel), this rank ---------------------------
     pk, pk_src = peaks()
+    # 9 B per byte walked (slab slot + data byte) + 3968 B per checkpoint moved + 16 B per edit, counted by the kernel.
+    # The literal queues (32 B per literal priced from them) are read from L2, where the 48 B/byte table lives: they
+    # show up in ncu's DRAM bytes only as far as they miss (traffic / algorithmic, below)
     alg_bytes = agg["slab_bytes_read"] + agg["checkpoint_bytes"] + 16 * agg["edits"]
     achieved = alg_bytes / (agg["kernel_ms"] / 1e3) / 1e9
     # DRAM traffic: ncu (dram__bytes_read + write of one captured launch of this kernel on this workload,
-    # profiles/r01_final_traffic.json) as a ratio to the algorithmic bytes of that launch, applied to this run's
+    # profiles/r02_final_traffic.json) as a ratio to the algorithmic bytes of that launch, SCALED to this run's
+    # (not measured in this run: a number taken under a profiler is never a bench value)
     traffic, traffic_src = None, None
-    tpath = os.path.join(ROOT, "profiles", "r01_final_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r02_final_traffic.json")
+    if not os.path.exists(tpath):
+        tpath = os.path.join(ROOT, "profiles", "r01_final_traffic.json")
     if os.path.exists(tpath):
         with open(tpath) as f:
             tj = json.load(f)
@@ -450,8 +456,9 @@ def run_cuda(args) -> None:
                       "peak": ISSUE_CEILING_BITS_PER_S, "unit": "modelled bits/s", "frac": bits_per_s / ISSUE_CEILING_BITS_PER_S,
                       "bits_per_eval": agg["bits_scored"] / max(1, agg["attempts"]),
                       "note": "peak = 148 SMs x f_SM x 32 banks / 3 accesses per modelled bit (SURVEY 8d: every lane of every "
-                              "shared-memory instruction useful); the slot-class design issues ~4.9 shared-memory wavefronts per "
-                              "9-bit literal, i.e. its own ceiling is one wavefront per cycle per SM = ~5.3e11 bits/s (DESIGN.md 5)"}
+                              "shared-memory instruction useful); the per-lane literal queues issue ~2.1 shared-memory wavefronts per "
+                              "9-bit literal (16 rounds x 3 accesses + conflicts per 32 literals: the hottest slots take one two-step "
+                              "table lookup per two literals, the other lanes wait for them), LSU data pipe ~70 % busy (DESIGN.md 5)"}
 
     ctx_comm_stats = ctx.comm_stats() if dist is not None else None
     best_slab = None
@@ -516,7 +523,7 @@ def run_cuda(args) -> None:
 
     size = config3 = encode = None
     if rank == 0 and world == 1 and not args.no_size:
-        wave = props.multi_processor_count * 27
+        wave = props.multi_processor_count * 26
         try:
             c0 = mg.Context(b"wave probe wave probe", device=local)
             wave = c0.full_wave()

@@ -12,4 +12,5 @@ an.set_slab(None)
 budget = int(sys.argv[1]) if len(sys.argv) > 1 else 2_000_000
 for it in range(2):
     st = an.run(1000, first_eval=mg.CONTINUE_EVALS, suspend=True, packet_budget=budget)
-    print(it, round(st["kernel_ms"], 1), st["evals"], st["packets_scored"], "finder share %.3f" % (st["finder_cycles"] / max(1, st["chain_cycles"])))
+    print(it, round(st["kernel_ms"], 1), st["evals"], st["packets_scored"], "finder share %.3f" % (st["finder_cycles"] / max(1, st["chain_cycles"])),
+          "algorithmic_bytes", st["slab_bytes_read"] + st["checkpoint_bytes"] + 16 * st["edits"])
