@@ -242,13 +242,16 @@ def size_leg(mg, wave: int, budget_s: float, device: int) -> list:
         with tempfile.NamedTemporaryFile(suffix=".bin") as f:
             f.write(data)
             f.flush()
-            cmd = [cli, "--chains", str(chains), "--time", str(int(budget_s)), "--round-ms", "250", "--device", str(device), f.name]
+            cmd = [cli, "--chains", str(chains), "--time", str(int(budget_s)), "--round-ms", "250", "--device", str(device)]
+            if n >= (1 << 20):
+                cmd += ["--greedy", "1024"]  # a greedy parse of 1024 regions as the starting slab (mg_anneal_greedy_init)
+            cmd.append(f.name)
             t0 = time.perf_counter()
             r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
             wall = time.perf_counter() - t0
         rec = {"config": name, "input_bytes": n, "chains": chains, "wall_s": wall,
-               "command": "megalania --chains %d --time %d --round-ms 250 <file>  (drop-in C CLI: cooperative regions, "
-                          "final range-coder pass on the device)" % (chains, int(budget_s))}
+               "command": " ".join(["megalania"] + cmd[1:-1] + ["<file>"]) + "  (drop-in C CLI: cooperative regions, final "
+                          "range-coder pass on the device)"}
         if r.returncode != 0:
             rec["error"] = r.stderr.decode(errors="replace")[-300:]
             out.append(rec)

@@ -240,6 +240,15 @@ MG_API size_t mg_anneal_chain_bytes(const mg_ctx* ctx, const mg_anneal_params* p
 MG_API int mg_anneal_set_slab(mg_anneal* an, uint32_t first, uint32_t count, const LZMAPacket* slab,
                        int adopt_cost, int reset_best);
 
+/* A starting slab better than the reference's all-literal one (src/packet_slab.c:30-32), built on the device: the
+ * input is cut into `nregions` equal byte regions, each parsed greedily from a fresh model - at every packet the
+ * cheapest candidate per byte of the exact top-k (src/top_k_packet_finder.c, under the context's finder limits) -
+ * and the stitched slab goes through the forced repair pass of the region merge (rep packets whose distances
+ * changed at a seam, see mg_anneal_merge_regions).  It becomes the current slab of chain `dst_chain`, priced exactly
+ * (*cost_out); mg_anneal_broadcast_chain hands it to the other chains.  nregions = 1 with no finder limits is the
+ * oracle's greedy parse packet for packet.  Search strategy on top of the hot path: off unless asked for. */
+MG_API int mg_anneal_greedy_init(mg_anneal* an, uint32_t nregions, uint32_t dst_chain, uint64_t* cost_out);
+
 /* Cooperative regions.  After region-confined chains (mg_anneal_run_params.regions) have run from a
  * common slab, builds the slab that takes region r = [bounds[r], bounds[r+1]) from chain owners[r]
  * (bounds[0] = 0, bounds[nregions] = n), stores it as the current slab of chain `dst_chain`, repairs the

@@ -86,7 +86,7 @@ EXPORTS = [
     "mg_anneal_merge_export", "mg_anneal_merge_import", "mg_debug_index", "mg_encode_stats", "mg_ctx_full_wave",
     "mg_comm_unique_id", "mg_comm_init", "mg_comm_destroy", "mg_comm_rank", "mg_comm_size", "mg_comm_exchange_best",
     "mg_comm_temper_exchange", "mg_temper_decide", "mg_comm_merge_regions", "mg_comm_stats", "mg_pool_trim",
-    "mg_comm_broadcast_chain", "mg_comm_allgather_u64", "mg_ctx_set_finder_limits",
+    "mg_comm_broadcast_chain", "mg_comm_allgather_u64", "mg_ctx_set_finder_limits", "mg_anneal_greedy_init",
 ]
 
 _lib = None
@@ -140,6 +140,7 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
     L.mg_anneal_refresh_chain.argtypes = [vp, u32, i32]
     L.mg_anneal_merge_regions.argtypes = [vp, u32, vp, vp, u32, C.POINTER(u64)]
     L.mg_anneal_broadcast_chain.argtypes = [vp, u32]
+    L.mg_anneal_greedy_init.argtypes = [vp, u32, u32, C.POINTER(u64)]
     L.mg_anneal_merge_export.argtypes = [vp, u32, vp, vp, vp, vp]
     L.mg_anneal_merge_import.argtypes = [vp, vp, vp, u32, C.POINTER(u64)]
     L.mg_anneal_export_slab.argtypes = [vp, u32, i32, vp]
@@ -477,6 +478,13 @@ class Annealer:
 
     def broadcast_chain(self, src_chain: int) -> None:
         _check(self._lib.mg_anneal_broadcast_chain(self._h, src_chain))
+
+    def greedy_init(self, nregions: int = 1, dst_chain: int = 0) -> int:
+        """mg_anneal_greedy_init: greedy parse of `nregions` byte regions side by side, stitched, repaired and priced
+        into chain dst_chain; returns its cost.  One region, no finder limits = the oracle's greedy slab."""
+        cost = C.c_uint64(0)
+        _check(self._lib.mg_anneal_greedy_init(self._h, nregions, dst_chain, C.byref(cost)))
+        return int(cost.value)
 
     def refresh_chain(self, chain: int, adopt_cost: bool = True) -> None:
         _check(self._lib.mg_anneal_refresh_chain(self._h, chain, int(adopt_cost)))

@@ -1368,6 +1368,51 @@ extern "C" MG_API int mg_anneal_merge_regions(mg_anneal* an, uint32_t nregions, 
 	return mg_anneal_merge_import(an, slab.p, abs.p, dst_chain, cost_out);
 }
 
+extern "C" MG_API int mg_anneal_greedy_init(mg_anneal* an, uint32_t nregions, uint32_t dst_chain, uint64_t* cost_out)
+{
+	if (!an || dst_chain >= an->p.chains) return fail(MG_EINVAL, "mg_anneal_greedy_init: bad argument");
+	mg_ctx* ctx = an->ctx;
+	const uint32_t n = ctx->n;
+	if (nregions == 0) nregions = 1;
+	if (nregions > n / 64 + 1) nregions = n / 64 + 1;  // a region is at least 64 bytes
+	CU(cudaSetDevice(ctx->device));
+	std::vector<uint32_t> bounds(nregions + 1);
+	for (uint32_t r = 0; r <= nregions; r++) bounds[r] = (uint32_t)((uint64_t)n * r / nregions);
+	DevBuf slab, abs, dbounds, derr;
+	if (int rc = dev_alloc(slab, (size_t)n * 8)) return rc;
+	if (int rc = dev_alloc(abs, (size_t)n * 4)) return rc;
+	if (int rc = dev_alloc(dbounds, sizeof(uint32_t) * (nregions + 1))) return rc;
+	if (int rc = dev_alloc(derr, 4)) return rc;
+	CU(cudaMemcpyAsync(dbounds.p, bounds.data(), sizeof(uint32_t) * (nregions + 1), cudaMemcpyHostToDevice, ctx->stream));
+	CU(cudaMemsetAsync(abs.p, 0, (size_t)n * 4, ctx->stream));
+	CU(cudaMemsetAsync(derr.p, 0, 4, ctx->stream));
+	fill_literal_kernel<<<grid_for(n, 256, ctx->sm_count * 8), 256, 0, ctx->stream>>>(slab.as<uint64_t>(), n);
+	CU(cudaGetLastError());
+	GreedyArgs g;
+	g.data = ctx->d_data;
+	g.n = n;
+	g.occ_start = ctx->d_occ_start;
+	g.occ = ctx->d_occ;
+	g.tables = ctx->tables;
+	g.limits = ctx->limits;
+	g.k = an->p.top_k;
+	g.bounds = dbounds.as<uint32_t>();
+	g.nregions = nregions;
+	g.slab = slab.as<uint64_t>();
+	g.abs_dist = abs.as<uint32_t>();
+	g.err = derr.as<uint32_t>();
+	int blocks = (int)((nregions + WARPS_PER_CTA - 1) / WARPS_PER_CTA);
+	if (blocks > ctx->sm_count) blocks = ctx->sm_count;
+	CU(cudaFuncSetAttribute(greedy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CtaShared)));
+	greedy_kernel<<<blocks, CTA_THREADS, sizeof(CtaShared), ctx->stream>>>(g);
+	CU(cudaGetLastError());
+	uint32_t herr = 0;
+	CU(cudaMemcpyAsync(&herr, derr.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+	CU(cudaStreamSynchronize(ctx->stream));
+	if (herr) return fail(MG_ESLAB, "mg_anneal_greedy_init: %s", walk_error(herr));
+	return mg_anneal_merge_import(an, slab.p, abs.p, dst_chain, cost_out);
+}
+
 extern "C" MG_API int mg_anneal_broadcast_chain(mg_anneal* an, uint32_t src_chain)
 {
 	if (!an || src_chain >= an->p.chains) return fail(MG_EINVAL, "mg_anneal_broadcast_chain: bad argument");

@@ -910,6 +910,72 @@ __global__ void __launch_bounds__(CTA_THREADS) topk_kernel(TopkArgs a)
 	if (lane == 0 && cand) atomicAdd(a.candidates, cand);
 }
 
+// ---- greedy parse (starting slabs) ---------------------------------------------------------------------
+// One warp per byte region: from a fresh model at the region's first byte it takes, packet after packet, the
+// cheapest candidate per byte of the exact top-k (the last one popped) and prices it, until the region is
+// covered; the last packet is cut to the region's end.  With one region and no finder limits this is the
+// oracle's greedy slab (mgo_greedy_slab) packet for packet.  Regions parsed side by side do not know each other's
+// rep distances: what every LONG_REP stood for is recorded (abs_dist, stored + 1) and the caller sends the stitched
+// slab through the forced repair pass of the region merge (mg_anneal_merge_import), which keeps such a packet as a
+// MATCH at that distance and re-decides SHORT_REP / LITERAL by the reference's rule.
+struct GreedyArgs {
+	const uint8_t* data;
+	uint32_t n;
+	const uint32_t* occ_start;
+	const uint32_t* occ;
+	Tables tables;
+	FindLimits limits;
+	uint32_t k;
+	const uint32_t* bounds;  // [nregions + 1]
+	uint32_t nregions;
+	uint64_t* slab;          // [n] packed, pre-filled with literals
+	uint32_t* abs_dist;      // [n] zeroed
+	uint32_t* err;
+};
+
+__global__ void __launch_bounds__(CTA_THREADS) greedy_kernel(GreedyArgs a)
+{
+	extern __shared__ __align__(128) unsigned char smem_raw[];
+	CtaShared* sh = reinterpret_cast<CtaShared*>(smem_raw);
+	cta_tables_load(sh, a.tables);
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	WarpShared* ws = warp_block(sh, warp);
+	const WalkEnv e = make_env(lane, ws, sh, a.slab, a.data, a.n, nullptr);
+	for (uint32_t r = (uint32_t)warp * gridDim.x + blockIdx.x; r < a.nregions; r += gridDim.x * WARPS_PER_CTA) {
+		const uint32_t lo = a.bounds[r], hi = a.bounds[r + 1];
+		Walker k;
+		walker_init(e, k);
+		k.pos = k.delta = lo;
+		while (k.pos < hi) {
+			Model m = walker_model(e, k);
+			const uint32_t count = warp_find(lane, e.probs, e.trans, e.recip, &ws->fs, a.data, a.n, a.occ_start, a.occ, m, 0, a.k, 0,
+			                                 a.limits);
+			uint64_t pk = count ? ws->fs.ent_pk[ws->fs.pop_order[count - 1]] : PK_LITERAL;
+			__syncwarp();
+			uint32_t type = pk_type(pk), len = pk_len(pk), dist = pk_dist(pk);
+			if (len > hi - k.pos) {
+				if ((type == T_MATCH || type == T_LONG_REP) && hi - k.pos >= 2) {
+					len = hi - k.pos;
+				} else {
+					type = T_LITERAL;
+					len = 1;
+					dist = 0;
+				}
+				pk = pk_pack(type, dist, len);
+			}
+			if (!packet_ok(m, a.n, type, len, dist)) {
+				if (lane == 0) atomicOr(a.err, ERR_BAD_PACKET);
+				break;
+			}
+			if (lane == 0) {
+				a.slab[k.pos] = pk;
+				if (type == T_LONG_REP) a.abs_dist[k.pos] = model_rep(m, dist) + 1u;
+			}
+			walker_apply(e, k, m, type, len, dist, a.data[k.pos]);
+		}
+	}
+}
+
 // ---- K3/K4: the annealing loop ---------------------------------------------------------------------
 
 

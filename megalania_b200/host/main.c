@@ -29,12 +29,12 @@ static void usage(const char* argv0)
 	fprintf(stderr,
 	        "usage: %s [--chains N] [--iters N] [--epochs N] [--steps N] [--seed N] [--device N] [--gpus N] [--top-k N]\n"
 	        "          [--rounds N | --time SECONDS] [--round-ms N] [--group N] [--temp T] [--sm-khz N]\n"
-	        "          [--window BYTES] [--max-occ N] filename\n",
+	        "          [--window BYTES] [--max-occ N] [--greedy REGIONS] filename\n",
 	        argv0);
 }
 
 typedef struct {
-	unsigned chains, iters, epochs, steps, device, top_k, rounds, round_ms, group, temp0, gpus, sm_khz, window, max_occ;
+	unsigned chains, iters, epochs, steps, device, top_k, rounds, round_ms, group, temp0, gpus, sm_khz, window, max_occ, greedy;
 	unsigned long long seed;
 	const uint8_t* data;
 	size_t size;
@@ -99,6 +99,13 @@ static int run_rounds(Worker* w, mg_anneal* an)
 		return -1;
 	}
 	if (mg_anneal_set_slab(an, 0, chains, NULL, 1, 1)) return die(w, "mg_anneal_set_slab");
+	if (c->greedy) {
+		/* --greedy N: start from a greedy parse of N regions instead of the all-literal slab; every rank builds
+		 * the same slab (the parse draws nothing) */
+		uint64_t cost = 0;
+		if (mg_anneal_greedy_init(an, c->greedy, 0, &cost)) return die(w, "mg_anneal_greedy_init");
+		if (mg_anneal_broadcast_chain(an, 0)) return die(w, "mg_anneal_broadcast_chain");
+	}
 	unsigned long long lcg = c->seed, evals = 0;
 	double device_ms = 0;
 	for (unsigned r = 0; r < c->rounds; r++) {
@@ -331,6 +338,7 @@ int main(int argc, char** argv)
 		else if (!strcmp(a, "--sm-khz")) target = &cfg.sm_khz;
 		else if (!strcmp(a, "--window")) target = &cfg.window;   /* match-finder limits for huge inputs; 0 = the */
 		else if (!strcmp(a, "--max-occ")) target = &cfg.max_occ; /* reference's unbounded enumeration */
+		else if (!strcmp(a, "--greedy")) target = &cfg.greedy;   /* start the rounds from a greedy parse of N regions */
 		if (target) {
 			if (++i >= argc) { usage(argv[0]); return -1; }
 			*target = (unsigned)strtoul(argv[i], NULL, 10);

@@ -335,3 +335,34 @@ def test_literal_queue_edge_windows(mg, port):
             want = port.model_after_prefix(data, lit, stop)
             assert got.tobytes() == want.tobytes(), stop
         assert ctx.score_slab(mixed) == port.slab_cost(data, mixed)
+
+
+@pytest.mark.parametrize("kind,n", [("text", 4096), ("binary", 4096)])
+def test_greedy_init_equals_oracle(mg, port, corpora, kind, n):
+    """mg_anneal_greedy_init with one region and no finder limits is the oracle's greedy parse packet for packet
+    (exact top-k at every packet, cheapest candidate per byte, adaptive model); with many regions the stitched,
+    repaired slab is valid, priced exactly and no worse than the all-literal slab."""
+    data = corpora(kind, n)
+    want = port.greedy_slab(data)
+    with mg.Context(data) as ctx:
+        an = mg.Annealer(ctx, 4, seed=3)
+        an.set_slab(None)
+        cost = an.greedy_init(1, 0)
+        got = an.get_slab(0)
+        b = 0
+        while b < n:  # compare the live chain: slots behind a packet are dead
+            assert (int(got[b]["type"]), int(got[b]["dist"]), int(got[b]["len"])) == \
+                   (int(want[b]["type"]), int(want[b]["dist"]), int(want[b]["len"])), b
+            b += int(want[b]["len"])
+        assert cost == port.slab_cost(data, want)
+        cost16 = an.greedy_init(16, 1)
+        slab16 = an.get_slab(1)
+        assert cost16 == port.slab_cost(data, slab16) == ctx.score_slab(slab16)
+        assert cost16 < port.slab_cost(data, mg.literal_slab(n))
+        stream = ctx.encode_slab(slab16)
+        import lzma
+        assert lzma.decompress(stream, format=lzma.FORMAT_ALONE) == data
+        an.broadcast_chain(1)
+        cur, _ = an.costs()
+        assert (cur == cost16).all()
+        an.close()
