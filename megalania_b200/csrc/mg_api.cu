@@ -116,7 +116,7 @@ extern "C" MG_API void mg_pool_trim(void)
 	cudaGetDevice(&device);
 	for (auto it = P.cached.begin(); it != P.cached.end();) {
 		cudaSetDevice(it->first.first);
-		pool_free(it->second);
+		cudaFree(it->second);  // not pool_free(): the lock is held, and a cached block is not live
 		it = P.cached.erase(it);
 	}
 	cudaSetDevice(device);
@@ -167,19 +167,20 @@ static int grid_for(size_t items, int threads, int cap)
 	return g ? (int)g : 1;
 }
 
+// Function attributes belong to a device's context: every context creation sets them for its own device (a host
+// with one thread per GPU creates eight).
 static int set_smem_attrs()
 {
-	static bool done = false;
-	if (done) return 0;
 	CU(cudaFuncSetAttribute(score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CtaShared)));
 	CU(cudaFuncSetAttribute(topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CtaShared)));
 	CU(cudaFuncSetAttribute(anneal_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CtaShared)));
+	CU(cudaFuncSetAttribute(greedy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CtaShared)));
 	CU(cudaFuncSetAttribute(encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EncodeShared)));
 	// the model lives in shared memory: ask for the largest carve-out so that occupancy is set by registers
 	CU(cudaFuncSetAttribute(score_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
 	CU(cudaFuncSetAttribute(topk_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
 	CU(cudaFuncSetAttribute(anneal_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-	done = true;
+	CU(cudaFuncSetAttribute(greedy_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
 	return 0;
 }
 
@@ -1403,7 +1404,6 @@ extern "C" MG_API int mg_anneal_greedy_init(mg_anneal* an, uint32_t nregions, ui
 	g.err = derr.as<uint32_t>();
 	int blocks = (int)((nregions + WARPS_PER_CTA - 1) / WARPS_PER_CTA);
 	if (blocks > ctx->sm_count) blocks = ctx->sm_count;
-	CU(cudaFuncSetAttribute(greedy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CtaShared)));
 	greedy_kernel<<<blocks, CTA_THREADS, sizeof(CtaShared), ctx->stream>>>(g);
 	CU(cudaGetLastError());
 	uint32_t herr = 0;

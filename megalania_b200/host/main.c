@@ -20,6 +20,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <unistd.h>
 
 #include "host_io.h"
 #include "megalania_cuda.h"
@@ -56,6 +57,12 @@ typedef struct {
 static int die(const Worker* w, const char* what)
 {
 	fprintf(stderr, "[gpu %u] %s: %s\n", w->cfg->device + (unsigned)w->rank, what, mg_last_error());
+	/* with several GPUs the other ranks are, or soon will be, inside a collective that this rank will never
+	 * join: leave as a whole instead of hanging them */
+	if (w->cfg->gpus > 1) {
+		fflush(stderr);
+		_exit(1);
+	}
 	return -1;
 }
 
@@ -362,6 +369,16 @@ int main(int argc, char** argv)
 		return -1;
 	}
 
+	/* stdout carries the .lzma stream and nothing else: libraries that print there (NCCL's version banner does) are
+	 * sent to stderr, the stream goes to a private copy of the original descriptor */
+	fflush(stdout);
+	const int stream_fd = dup(1);
+	FILE* stream_out = stream_fd >= 0 ? fdopen(stream_fd, "wb") : NULL;
+	if (!stream_out || dup2(2, 1) < 0) {
+		fprintf(stderr, "could not set the output stream up\n");
+		return -1;
+	}
+
 	InputFile input;
 	if (input_file_open(&input, filename) < 0) return -1;
 	cfg.data = input.data;
@@ -414,12 +431,12 @@ int main(int argc, char** argv)
 
 	OutputInterface output;
 	StreamSink sink;
-	stream_sink_init(&output, &sink, stdout);
+	stream_sink_init(&output, &sink, stream_out);
 	if (mg_encode_slab(win->ctx, win->packets_best, &output)) {
 		fprintf(stderr, "mg_encode_slab: %s\n", mg_last_error());
 		return -1;
 	}
-	if (fflush(stdout) != 0 || sink.failed) {
+	if (fflush(stream_out) != 0 || sink.failed) {
 		fprintf(stderr, "could not write the output stream\n");
 		return -1;
 	}

@@ -11,7 +11,7 @@ open('/tmp/c16.bin','wb').write(corpus.make('corpus16', 16 << 20))
 P
 CLI=megalania_b200/_build/megalania
 s=$(date +%s)
-$CLI --gpus $N --chains $CH --time $T --round-ms 1000 --greedy 4096 --max-occ 128 --window 16777216 /tmp/c16.bin > /tmp/c16.lzma 2> gpurun_out/config5_cli.err
+$CLI --gpus $N --chains $CH --time $T --round-ms 1000 --greedy 4096 --max-occ 512 --window 16777216 /tmp/c16.bin > /tmp/c16.lzma 2> gpurun_out/config5_cli.err
 rc=$?
 e=$(date +%s)
 tail -3 gpurun_out/config5_cli.err
@@ -22,7 +22,7 @@ n_gpus, budget, chains, wall, rc = (int(x) for x in sys.argv[1:6])
 data = open('/tmp/c16.bin', 'rb').read()
 out = open('/tmp/c16.lzma', 'rb').read()
 rec = {"config": "BASELINE configs[4]: 16 MiB synthetic corpus (tools/corpus.py corpus16, seed 99)", "n_gpus": n_gpus, "chains_per_gpu": chains,
-       "command": f"megalania --gpus {n_gpus} --chains {chains} --time {budget} --round-ms 1000 --greedy 4096 --max-occ 128 --window 16777216 <file>",
+       "command": f"megalania --gpus {n_gpus} --chains {chains} --time {budget} --round-ms 1000 --greedy 4096 --max-occ 512 --window 16777216 <file>",
        "exit_code": rc, "wall_s": wall, "bytes": len(out)}
 try:
     rec["round_trip"] = lzma.decompress(out, format=lzma.FORMAT_ALONE) == data
@@ -37,12 +37,14 @@ rec["xz_9e_s"] = round(time.time() - t0, 1)
 from oracle import oracle_lib as ol
 ol.build()
 import os
-lib = ol.Ref() if os.path.exists(ol.REF_SO) else ol.Port()
+is_ref = os.path.exists(ol.REF_SO)
+lib = ol.Ref() if is_ref else ol.Port()
+kw = {} if is_ref else {"rng_mode": 0}
 slab = ol.literal_slab(len(data)); best = slab.copy()
-t0 = time.time(); evals = 0; bc = cc = 0
+t0 = time.time(); evals = 0; bc = cc = 0; first = True
 while time.time() - t0 < wall:
-    r = lib.anneal_epoch(data, slab, best, bc, cc, seed=1673551, evals=2, **({} if isinstance(lib, ol.Ref) else {"rng_mode": 0}))
-    bc, cc = r[1], r[2]; evals += 2
+    r = lib.anneal_epoch(data, slab, best, bc, cc, reseed=1 if first else 0, seed=1673551, evals=1, **kw)
+    bc, cc = r[1], r[2]; evals += 1; first = False
 stream = lib.encode_slab(data, best if bc else slab)
 rec["reference_same_wall"] = {"bytes": len(stream), "evals": evals, "wall_s": round(time.time() - t0, 1), "cores": 1}
 rec["no_larger_than_reference"] = rec["bytes"] <= len(stream)
