@@ -15,7 +15,8 @@ constexpr int WARPS_PER_CTA = MG_WARPS_PER_CTA;
 constexpr int CTA_THREADS = WARPS_PER_CTA * 32;
 constexpr uint32_t RECIP_ENTRIES = 288;
 // Kernel experiments (tools/variants.sh): 0 = the product; bit 0 = literal queues off (every literal takes the
-// single-step path).
+// single-step path); bit 1 = walk_windows() keeps the next window's type/length word in a register (round-2 form up
+// to 27e4c2c) instead of staging it by cp.async.
 #ifndef MG_WALK_VARIANT
 #define MG_WALK_VARIANT 0
 #endif
@@ -559,19 +560,52 @@ __device__ __forceinline__ bool walk_windows(const WalkEnv& e, Walker& k, uint32
 	uint32_t base = k.w.base;
 	const uint4* q = e.litq + (size_t)(base >> 5) * (QUEUE_BLOCKS * 32) + (uint32_t)e.lane;
 	const uint32_t* slab_hi = reinterpret_cast<const uint32_t*>(e.slab) + 1;  // type << 16 | len of slot i at [2 * i]
+	// The next window's type/length words travel global -> shared memory by cp.async into the lane's own slot of
+	// the staging area (the place window_prefetch() puts them; a copy window_seek() left in flight there carries
+	// the same words).  Held in a register the load was sunk by ptxas to the end of the window - the kernel is
+	// compiled against a 72-register cap - and every window waited out one HBM round trip there (34 % of all warp
+	// samples, profiles/r02_final_anneal_kernel_ncu.txt, line of the __all_sync below).
+	const uint32_t hi_stage = e.stage_addr + 8u * (uint32_t)e.lane + 4u;
 	uint4 a = __ldcg(q), b = __ldcg(q + 32);
 	for (;;) {
 		const uint32_t head = __shfl_sync(FULL, a.x, 0) & 0xffffu;
 		if (head == QUEUE_UNUSABLE) break;
 		const bool more = base + 64u <= wend;  // another whole window may follow
 		uint32_t next_hi = 0;
-		if (more) next_hi = __ldcg(slab_hi + 2 * (size_t)(base + 32u + (uint32_t)e.lane));
-		queue_rounds4(a.x, a.y, pa, ta, acc);
-		queue_rounds4(a.z, a.w, pa, ta, acc);
-		if (more) a = __ldcg(q + QUEUE_BLOCKS * 32);
-		queue_rounds4(b.x, b.y, pa, ta, acc);
-		queue_rounds4(b.z, b.w, pa, ta, acc);
-		if (more) b = __ldcg(q + QUEUE_BLOCKS * 32 + 32);
+		if (MG_WALK_VARIANT & 2) {
+			if (more) next_hi = __ldcg(slab_hi + 2 * (size_t)(base + 32u + (uint32_t)e.lane));
+		} else if (MG_WALK_VARIANT & 4) {
+			// experiment: lanes 0-15 copy two whole slots each, past L1 (cp.async.cg moves 16 bytes)
+			if (more && e.lane < 16)
+				asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(e.stage_addr + 16u * (uint32_t)e.lane),
+				             "l"(e.slab + (size_t)(base + 32u + 2u * (uint32_t)e.lane))
+				             : "memory");
+			if (more) asm volatile("cp.async.commit_group;" ::: "memory");
+		} else if (more) {
+			asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n\tcp.async.commit_group;" ::"r"(hi_stage),
+			             "l"(slab_hi + 2 * (size_t)(base + 32u + (uint32_t)e.lane))
+			             : "memory");
+		}
+		if (MG_WALK_VARIANT & 8) {
+			// experiment: every 8-byte piece of the queue is reloaded as soon as it has been used (three quarters
+			// of a window ahead of its next use instead of half a window)
+			const uint2* qn = reinterpret_cast<const uint2*>(q + QUEUE_BLOCKS * 32);
+			queue_rounds4(a.x, a.y, pa, ta, acc);
+			if (more) { const uint2 t = __ldcg(qn); a.x = t.x; a.y = t.y; }
+			queue_rounds4(a.z, a.w, pa, ta, acc);
+			if (more) { const uint2 t = __ldcg(qn + 1); a.z = t.x; a.w = t.y; }
+			queue_rounds4(b.x, b.y, pa, ta, acc);
+			if (more) { const uint2 t = __ldcg(qn + 64); b.x = t.x; b.y = t.y; }
+			queue_rounds4(b.z, b.w, pa, ta, acc);
+			if (more) { const uint2 t = __ldcg(qn + 65); b.z = t.x; b.w = t.y; }
+		} else {
+			queue_rounds4(a.x, a.y, pa, ta, acc);
+			queue_rounds4(a.z, a.w, pa, ta, acc);
+			if (more) a = __ldcg(q + QUEUE_BLOCKS * 32);
+			queue_rounds4(b.x, b.y, pa, ta, acc);
+			queue_rounds4(b.z, b.w, pa, ta, acc);
+			if (more) b = __ldcg(q + QUEUE_BLOCKS * 32 + 32);
+		}
 		if (head & QUEUE_MORE) {
 			// the rare window in which some lane owes more than 16 steps: eight more from the third block
 			const uint4 c = __ldcg(q + 64);
@@ -586,6 +620,15 @@ __device__ __forceinline__ bool walk_windows(const WalkEnv& e, Walker& k, uint32
 			k.t.acc = acc;
 			tally_flush(k.t);
 			acc = 0;
+		}
+		if (MG_WALK_VARIANT & 4) {
+			asm volatile("cp.async.wait_group 0;" ::: "memory");
+			__syncwarp();
+			asm volatile("ld.shared.u32 %0, [%1];" : "=r"(next_hi) : "r"(hi_stage) : "memory");
+			__syncwarp();  // all lanes have read before the next copy lands
+		} else if (!(MG_WALK_VARIANT & 2)) {
+			// the lane reads the word it copied itself: no warp-level ordering needed
+			asm volatile("cp.async.wait_group 0;\n\tld.shared.u32 %0, [%1];" : "=r"(next_hi) : "r"(hi_stage) : "memory");
 		}
 		if (!__all_sync(FULL, next_hi == ((T_LITERAL << 16) | 1u))) break;
 		q += QUEUE_BLOCKS * 32;
