@@ -526,7 +526,7 @@ def run_cuda(args) -> None:
 
     size = config3 = encode = None
     if rank == 0 and world == 1 and not args.no_size:
-        wave = props.multi_processor_count * 26
+        wave = chains
         try:
             c0 = mg.Context(b"wave probe wave probe", device=local)
             wave = c0.full_wave()
