@@ -574,38 +574,17 @@ __device__ __forceinline__ bool walk_windows(const WalkEnv& e, Walker& k, uint32
 		uint32_t next_hi = 0;
 		if (MG_WALK_VARIANT & 2) {
 			if (more) next_hi = __ldcg(slab_hi + 2 * (size_t)(base + 32u + (uint32_t)e.lane));
-		} else if (MG_WALK_VARIANT & 4) {
-			// experiment: lanes 0-15 copy two whole slots each, past L1 (cp.async.cg moves 16 bytes)
-			if (more && e.lane < 16)
-				asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(e.stage_addr + 16u * (uint32_t)e.lane),
-				             "l"(e.slab + (size_t)(base + 32u + 2u * (uint32_t)e.lane))
-				             : "memory");
-			if (more) asm volatile("cp.async.commit_group;" ::: "memory");
 		} else if (more) {
 			asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n\tcp.async.commit_group;" ::"r"(hi_stage),
 			             "l"(slab_hi + 2 * (size_t)(base + 32u + (uint32_t)e.lane))
 			             : "memory");
 		}
-		if (MG_WALK_VARIANT & 8) {
-			// experiment: every 8-byte piece of the queue is reloaded as soon as it has been used (three quarters
-			// of a window ahead of its next use instead of half a window)
-			const uint2* qn = reinterpret_cast<const uint2*>(q + QUEUE_BLOCKS * 32);
-			queue_rounds4(a.x, a.y, pa, ta, acc);
-			if (more) { const uint2 t = __ldcg(qn); a.x = t.x; a.y = t.y; }
-			queue_rounds4(a.z, a.w, pa, ta, acc);
-			if (more) { const uint2 t = __ldcg(qn + 1); a.z = t.x; a.w = t.y; }
-			queue_rounds4(b.x, b.y, pa, ta, acc);
-			if (more) { const uint2 t = __ldcg(qn + 64); b.x = t.x; b.y = t.y; }
-			queue_rounds4(b.z, b.w, pa, ta, acc);
-			if (more) { const uint2 t = __ldcg(qn + 65); b.z = t.x; b.w = t.y; }
-		} else {
-			queue_rounds4(a.x, a.y, pa, ta, acc);
-			queue_rounds4(a.z, a.w, pa, ta, acc);
-			if (more) a = __ldcg(q + QUEUE_BLOCKS * 32);
-			queue_rounds4(b.x, b.y, pa, ta, acc);
-			queue_rounds4(b.z, b.w, pa, ta, acc);
-			if (more) b = __ldcg(q + QUEUE_BLOCKS * 32 + 32);
-		}
+		queue_rounds4(a.x, a.y, pa, ta, acc);
+		queue_rounds4(a.z, a.w, pa, ta, acc);
+		if (more) a = __ldcg(q + QUEUE_BLOCKS * 32);
+		queue_rounds4(b.x, b.y, pa, ta, acc);
+		queue_rounds4(b.z, b.w, pa, ta, acc);
+		if (more) b = __ldcg(q + QUEUE_BLOCKS * 32 + 32);
 		if (head & QUEUE_MORE) {
 			// the rare window in which some lane owes more than 16 steps: eight more from the third block
 			const uint4 c = __ldcg(q + 64);
@@ -621,12 +600,7 @@ __device__ __forceinline__ bool walk_windows(const WalkEnv& e, Walker& k, uint32
 			tally_flush(k.t);
 			acc = 0;
 		}
-		if (MG_WALK_VARIANT & 4) {
-			asm volatile("cp.async.wait_group 0;" ::: "memory");
-			__syncwarp();
-			asm volatile("ld.shared.u32 %0, [%1];" : "=r"(next_hi) : "r"(hi_stage) : "memory");
-			__syncwarp();  // all lanes have read before the next copy lands
-		} else if (!(MG_WALK_VARIANT & 2)) {
+		if (!(MG_WALK_VARIANT & 2)) {
 			// the lane reads the word it copied itself: no warp-level ordering needed
 			asm volatile("cp.async.wait_group 0;\n\tld.shared.u32 %0, [%1];" : "=r"(next_hi) : "r"(hi_stage) : "memory");
 		}
