@@ -369,7 +369,8 @@ def run_cuda(args) -> None:
     step_no = [0]
     exchange_ms = [0.0]
 
-    sm_khz = int(getattr(props, "clock_rate", 0) or peaks()[0].get("sm_max_mhz", 1965.0) * 1000)
+    # SM clocks per millisecond: the library's own figure (cudaDevAttrClockRate), else torch's, else the measured peak file
+    sm_khz = int(ctx.sm_clock_khz() or getattr(props, "clock_rate", 0) or peaks()[0].get("sm_max_mhz", 1965.0) * 1000)
     cycle_budget = 0 if args.packet_budget else int(args.step_ms * sm_khz)
 
     def step(first_eval):

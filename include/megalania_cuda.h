@@ -98,6 +98,9 @@ MG_API int mg_ctx_set_finder_limits(mg_ctx* ctx, size_t window, uint32_t max_occ
 /* Chains that fill the device exactly once: SMs x chains per SM (one warp and one model in shared memory each).
  * Populations are best sized in multiples of it. */
 MG_API uint32_t mg_ctx_full_wave(const mg_ctx* ctx);
+/* The device's SM clock in kHz (cudaDevAttrClockRate; 0 if the driver does not say): what turns a wall-clock step
+ * length into mg_anneal_run_params.cycle_budget, which counts SM clocks (clock64()). */
+MG_API uint32_t mg_ctx_sm_clock_khz(const mg_ctx* ctx);
 
 /* ---- parity function 2: cost(data, slab) ----------------------------------------------- */
 

@@ -83,7 +83,7 @@ EXPORTS = [
     "mg_anneal_get_slab", "mg_anneal_get_trace", "mg_anneal_swap_chains", "mg_anneal_device_slab",
     "mg_anneal_refresh_chain", "mg_anneal_oneshot", "mg_debug_model_after_prefix", "mg_anneal_export_slab",
     "mg_anneal_import_slab", "mg_anneal_merge_regions", "mg_anneal_broadcast_chain", "mg_find_topk_stats",
-    "mg_anneal_merge_export", "mg_anneal_merge_import", "mg_debug_index", "mg_encode_stats", "mg_ctx_full_wave",
+    "mg_anneal_merge_export", "mg_anneal_merge_import", "mg_debug_index", "mg_encode_stats", "mg_ctx_full_wave", "mg_ctx_sm_clock_khz",
     "mg_comm_unique_id", "mg_comm_init", "mg_comm_destroy", "mg_comm_rank", "mg_comm_size", "mg_comm_exchange_best",
     "mg_comm_temper_exchange", "mg_temper_decide", "mg_comm_merge_regions", "mg_comm_stats", "mg_pool_trim",
     "mg_comm_broadcast_chain", "mg_comm_allgather_u64", "mg_ctx_set_finder_limits", "mg_anneal_greedy_init",
@@ -120,6 +120,8 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
     L.mg_ctx_set_finder_limits.argtypes = [vp, sz, u32]
     L.mg_ctx_full_wave.argtypes = [vp]
     L.mg_ctx_full_wave.restype = u32
+    L.mg_ctx_sm_clock_khz.argtypes = [vp]
+    L.mg_ctx_sm_clock_khz.restype = u32
     L.mg_score_slabs.argtypes = [vp, vp, sz, vp]
     L.mg_find_topk.argtypes = [vp, vp, i32, vp, sz, i32, vp, vp, vp]
     L.mg_find_topk_stats.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(u64)]
@@ -321,6 +323,10 @@ class Context:
     def full_wave(self) -> int:
         """Chains that fill the device exactly once (SMs x chains per SM)."""
         return int(self._lib.mg_ctx_full_wave(self._h))
+
+    def sm_clock_khz(self) -> int:
+        """The device's SM clock in kHz (0 if unknown): step lengths in milliseconds x this = cycle_budget."""
+        return int(self._lib.mg_ctx_sm_clock_khz(self._h))
 
     def bigram_index(self):
         """(occ_start[65537], occ[n-1]): the device-built index of src/substring_enumerator.c:26-47."""

@@ -354,6 +354,12 @@ extern "C" MG_API int mg_ctx_set_finder_limits(mg_ctx* ctx, size_t window, uint3
 	return MG_OK;
 }
 extern "C" MG_API uint32_t mg_ctx_full_wave(const mg_ctx* ctx) { return ctx ? (uint32_t)ctx->sm_count * (uint32_t)WARPS_PER_CTA : 0u; }
+extern "C" MG_API uint32_t mg_ctx_sm_clock_khz(const mg_ctx* ctx)
+{
+	int khz = 0;
+	if (!ctx || cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, ctx->device) != cudaSuccess || khz <= 0) return 0u;
+	return (uint32_t)khz;
+}
 extern "C" MG_API int mg_encode_stats(const mg_ctx* ctx, double* kernel_ms, uint64_t* events)
 {
 	if (!ctx) return fail(MG_EINVAL, "mg_encode_stats: null context");

@@ -46,6 +46,7 @@ typedef struct {
 	int rank;
 	unsigned char nccl_id[MG_COMM_ID_BYTES];
 	pthread_barrier_t* barrier;
+	unsigned sm_khz;         /* SM clocks per millisecond on this rank's device */
 	/* results */
 	int status;              /* 0 ok */
 	mg_ctx* ctx;
@@ -136,7 +137,7 @@ static int run_rounds(Worker* w, mg_anneal* an)
 		for (unsigned ch = 0; ch < chains; ch++) temps[ch] = (float)c->temp0 * (1.f - (float)(r + 1) / (float)c->rounds);
 		run.temperatures = temps; /* uphill moves with probability exp(-delta / T); the last round is T = 0 */
 		run.first_eval = MG_CONTINUE_EVALS;
-		run.cycle_budget = (uint64_t)c->round_ms * (uint64_t)c->sm_khz;
+		run.cycle_budget = (uint64_t)c->round_ms * (uint64_t)w->sm_khz;
 		run.regions = regions;
 		mg_anneal_stats stats;
 		if (mg_anneal_run(an, &run, &stats)) return die(w, "mg_anneal_run");
@@ -280,6 +281,10 @@ static void* worker_main(void* arg)
 			die(w, "mg_ctx_create");
 			break;
 		}
+		/* SM clocks per millisecond: the device's own figure (mg_ctx_sm_clock_khz) unless --sm-khz says otherwise;
+		 * 1965 MHz (B200) only if the driver reports nothing */
+		w->sm_khz = c->sm_khz ? c->sm_khz : mg_ctx_sm_clock_khz(w->ctx);
+		if (w->sm_khz == 0) w->sm_khz = 1965000;
 		if ((c->window || c->max_occ) && mg_ctx_set_finder_limits(w->ctx, c->window, c->max_occ)) {
 			die(w, "mg_ctx_set_finder_limits");
 			break;
@@ -323,7 +328,7 @@ int main(int argc, char** argv)
 	cfg.group = 8;
 	cfg.temp0 = 4096;    /* --temp: 1/2048 bit, cooled linearly to 0 */
 	cfg.gpus = 1;
-	cfg.sm_khz = 1965000; /* --sm-khz: SM clock used to turn --round-ms into an SM-cycle budget (B200: 1965 MHz) */
+	cfg.sm_khz = 0;      /* --sm-khz: SM clock that turns --round-ms into an SM-cycle budget; 0 = ask the device */
 	cfg.seed = 1673551;  /* src/main.c:68 */
 	unsigned time_s = 0; /* --time: annealing budget in seconds of SM time */
 	const char* filename = NULL;
@@ -363,7 +368,7 @@ int main(int argc, char** argv)
 		}
 	}
 	if (time_s > 0 && cfg.round_ms > 0) cfg.rounds = (time_s * 1000u + cfg.round_ms - 1) / cfg.round_ms;
-	if (filename == NULL || cfg.chains == 0 || cfg.gpus == 0 || cfg.gpus > 64 || cfg.sm_khz == 0 ||
+	if (filename == NULL || cfg.chains == 0 || cfg.gpus == 0 || cfg.gpus > 64 ||
 	    (cfg.rounds == 0 && (cfg.steps == 0 || cfg.epochs == 0))) {
 		usage(argv[0]);
 		return -1;
