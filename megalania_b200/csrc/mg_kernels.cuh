@@ -1055,7 +1055,8 @@ __global__ void __launch_bounds__(CTA_THREADS, MG_ANNEAL_MIN_CTAS) anneal_kernel
 	uint64_t* slab = a.slabs + (size_t)c * n;
 	WalkEnv e_init = make_env(lane, ws, sh, slab, a.data, n, a.tables.litq);
 	e_init.abs_dist = a.abs_dist;
-	const WalkEnv e = e_init;
+	// not const: rebuilt after every finder call instead of staying live across it (see the call)
+	WalkEnv e = e_init;
 	Record* ck_base = a.ck + (size_t)c * 2 * nck;
 	CkMeta* ck_meta = a.ck_meta + (size_t)c * 2 * nck;
 	uint8_t* ck_live = a.ck_live + (size_t)c * nck;
@@ -1282,9 +1283,25 @@ __global__ void __launch_bounds__(CTA_THREADS, MG_ANNEAL_MIN_CTAS) anneal_kernel
 				const long long t_find = clock64();
 				// in a clock-boxed launch the finder may give a long bucket up - never on the launch's first
 				// proposal, so every launch makes progress
-				const uint32_t count = warp_find(lane, e.probs, e.trans, e.recip, &ws->fs, a.data, n, a.occ_start, a.occ,
-				                                 walker_model(e, k), excluded, a.k,
-				                                 (a.suspend && attempts > 1) ? deadline : 0, a.limits);
+				// The finder is not inlined, and the registers it gets are the ones this kernel does not keep live
+				// across the call: with the proposal's state left in registers it ran out of local memory (400 B of
+				// spill stores, 71 local loads + 56 stores inside its 32-occurrence step).  So the state is parked in
+				// local memory around the call - once per find instead of once per step - and the walk's lane
+				// constants are rebuilt after it: 188 B of spill stores, 25 + 21 local accesses per step, the
+				// finder's share of the warp time 0.31 -> 0.24 (+7.9 % evaluations/s on the bench workload,
+				// profiles/r02_parked_ab.log).
+				const Model fm = walker_model(e, k);
+				struct Parked { Walker k; CkSink ck; EditLog lg; ChainState st; } parked = {k, ck, lg, st};
+				asm volatile("" ::"l"(&parked) : "memory");
+				const uint32_t count = warp_find(lane, e.probs, e.trans, e.recip, &ws->fs, a.data, n, a.occ_start, a.occ, fm,
+				                                 excluded, a.k, (a.suspend && attempts > 1) ? deadline : 0, a.limits);
+				asm volatile("" ::"l"(&parked) : "memory");
+				k = parked.k;
+				ck = parked.ck;
+				lg = parked.lg;
+				st = parked.st;
+				e = make_env(lane, ws, sh, slab, a.data, n, a.tables.litq);
+				e.abs_dist = a.abs_dist;
 				k.w.md_base = WINDOW_NONE;  // the finder's length tables share the window mirrors' memory
 				k.w.pf_base = WINDOW_NONE;  // ... and the staging area of the next window
 				if (count == FIND_GAVE_UP) {
