@@ -462,7 +462,7 @@ def run_cuda(args) -> None:
                       "note": "peak = 148 SMs x f_SM x 32 banks / 3 accesses per modelled bit (SURVEY 8d: every lane of every "
                               "shared-memory instruction useful); the per-lane literal queues issue ~2.1 shared-memory wavefronts per "
                               "9-bit literal (16 rounds x 3 accesses + conflicts per 32 literals: the hottest slots take one two-step "
-                              "table lookup per two literals, the other lanes wait for them), LSU data pipe 82 % busy in the steady state (profiles/r02_staged_steady_anneal_kernel_ncu.txt, DESIGN.md 5); the match finder is 24 % of the warp time"}
+                              "table lookup per two literals, the other lanes wait for them), LSU data pipe 86 % busy in the steady state (profiles/r02_parked_steady_anneal_kernel_ncu.txt, DESIGN.md 5); the match finder is 24 % of the warp time"}
 
     ctx_comm_stats = ctx.comm_stats() if dist is not None else None
     best_slab = None
