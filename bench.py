@@ -67,6 +67,7 @@ class ClockSampler:
         self.device = device
         self.proc = None
         self.lines: list[str] = []
+        self.first = 0
 
     def start(self):
         try:
@@ -81,6 +82,10 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
+    def mark(self):
+        """Samples read so far belong to the warm-up: the figures come from what follows."""
+        self.first = len(self.lines)
+
     def stop(self) -> dict:
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -91,7 +96,7 @@ class ClockSampler:
             self.proc.kill()
         sm, smax, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in self.lines:
+        for line in self.lines[self.first:]:
             f = [x.strip() for x in line.split(",")]
             if len(f) < 9:
                 continue
@@ -390,13 +395,20 @@ def run_cuda(args) -> None:
         return st
 
     first_eval = 0
-    for _ in range(args.warmup):
+    sampler = ClockSampler(local)
+    for w in range(args.warmup):
+        if w == args.warmup - 1:
+            # nvidia-smi holds the driver up for some tens of milliseconds while it starts (a 3-step run showed
+            # 31 ms per step of wall clock the device never saw): it starts under the last warm-up step and only
+            # the samples of the timed region count (mark())
+            sampler.start()
         step(first_eval)
         first_eval += args.evals
-    sampler = ClockSampler(local)
+    if args.warmup == 0:
+        sampler.start()
     barrier()
     exchange_ms[0] = 0.0
-    sampler.start()
+    sampler.mark()
     t0 = time.perf_counter()
     agg = None
     per_launch_ms = []
