@@ -43,6 +43,27 @@ def test_library_is_sm100a_only():
     assert not re.search(r"sm_(?!100a)\d+", out)
 
 
+def test_build_is_the_machine_code_the_gpu_tests_ran_on():
+    """The round's last GPU runs tested a build whose per-kernel SASS digests are committed
+    (profiles/r02_committed_sass.md5, tools/sass_digest.py).  Experiment switches were removed from the source
+    afterwards: the product build must still be that machine code, kernel by kernel."""
+    import shutil
+    import sys
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not available")
+    sys.path.insert(0, ROOT)
+    from megalania_b200 import build
+    from tools import sass_digest
+    want = {}
+    for line in open(os.path.join(ROOT, "profiles", "r02_committed_sass.md5")):
+        digest, name = line.split()
+        want[name] = digest
+    got = sass_digest.digests(build.build_library())
+    assert set(got) == set(want)
+    changed = sorted(k for k in want if got[k] != want[k])
+    assert not changed, f"kernels rebuilt to different machine code than the GPU-tested build: {changed}"
+
+
 def test_no_cpu_fallback():
     import megalania_b200 as mg
     lib = mg.load_library()
