@@ -2,7 +2,7 @@
  * TEST INFRASTRUCTURE ONLY — never linked, imported or executed by the product path.
  *
  * Thin C harness that is linked against the UNMODIFIED reference sources where they
- * lie (/root/reference/src/*.c minus main.c, see oracle/Makefile) and exposes the three
+ * lie (the .c files of /root/reference/src minus main.c, see oracle/Makefile) and exposes the three
  * parity functions of SURVEY.md §8(c) plus an annealing-epoch replay through a flat,
  * ctypes-friendly ABI.  Output goes to oracle/_ref/libmegalania_ref.so, which is
  * git-ignored but travels to the GPU box.
